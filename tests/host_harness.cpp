@@ -1,0 +1,105 @@
+// TEST-ONLY host harness: runs the product's host/device geometry header (csrc/box_geom.cuh) on the
+// CPU so the contour / hull / min-area-rect logic can be compared with cv2 without a GPU.  It is built
+// by tests/conftest.py into tests/_build/ and is never linked into libvtd_b200.so.
+//
+// Labelling here is a plain sequential flood fill (the GPU uses union-find, boxes.cu); the rule that
+// decides RETR_EXTERNAL membership and everything per component is the shared header.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "../video_text_detection_system_b200/csrc/box_geom.cuh"
+
+using namespace vtd::geom;
+
+struct HhComp {
+  int32_t start;        // raster index of first pixel
+  int32_t external;     // 1 if RETR_EXTERNAL would return it
+  int64_t area2;        // twice the signed contour area
+  float rect[5];        // cx, cy, w, h, angle
+  float box[8];         // boxPoints
+  int32_t nhull;
+  int32_t pad;
+};
+
+extern "C" int hh_components(const uint8_t* mask, int h, int w, HhComp* out, int cap) {
+  const int n = h * w;
+  std::vector<int> lab(n, -1);
+  std::vector<uint8_t> outside(n, 0);
+  std::vector<int> stack;
+  // background: 4-connected flood from every border background pixel => "outside" region
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      if (!(y == 0 || x == 0 || y == h - 1 || x == w - 1)) continue;
+      int i = y * w + x;
+      if (mask[i] || outside[i]) continue;
+      outside[i] = 1; stack.push_back(i);
+      while (!stack.empty()) {
+        int j = stack.back(); stack.pop_back();
+        int jy = j / w, jx = j % w;
+        const int nx[4] = {jx - 1, jx + 1, jx, jx}, ny[4] = {jy, jy, jy - 1, jy + 1};
+        for (int k = 0; k < 4; ++k) {
+          if (nx[k] < 0 || ny[k] < 0 || nx[k] >= w || ny[k] >= h) continue;
+          int q = ny[k] * w + nx[k];
+          if (!mask[q] && !outside[q]) { outside[q] = 1; stack.push_back(q); }
+        }
+      }
+    }
+  int count = 0;
+  auto fg = [&](int x, int y) { return x >= 0 && y >= 0 && x < w && y < h && mask[y * w + x] != 0; };
+  std::vector<int> rowmin, rowmax;
+  std::vector<Pt> hull;
+  std::vector<float> scratch;
+  for (int i = 0; i < n; ++i) {
+    if (!mask[i] || lab[i] >= 0) continue;
+    // flood the 8-connected component; i is its raster-first pixel
+    int ymin = i / w, ymax = ymin;
+    lab[i] = i; stack.push_back(i);
+    std::vector<int> pix;
+    while (!stack.empty()) {
+      int j = stack.back(); stack.pop_back(); pix.push_back(j);
+      int jy = j / w, jx = j % w;
+      ymax = std::max(ymax, jy);
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          int qx = jx + dx, qy = jy + dy;
+          if (qx < 0 || qy < 0 || qx >= w || qy >= h) continue;
+          int q = qy * w + qx;
+          if (mask[q] && lab[q] < 0) { lab[q] = i; stack.push_back(q); }
+        }
+    }
+    if (count >= cap) return -1;
+    HhComp& c = out[count++];
+    std::memset(&c, 0, sizeof(c));
+    c.start = i;
+    int x0 = i % w, y0 = i / w;
+    c.external = (x0 == 0 || y0 == 0) ? 1 : (outside[i - 1] ? 1 : 0);
+    c.area2 = trace_outer_area2(fg, x0, y0, 8LL * n, nullptr);
+    int nrows = ymax - ymin + 1;
+    rowmin.assign(nrows, 1 << 30); rowmax.assign(nrows, -1);
+    for (int j : pix) {
+      int jy = j / w - ymin, jx = j % w;
+      rowmin[jy] = std::min(rowmin[jy], jx); rowmax[jy] = std::max(rowmax[jy], jx);
+    }
+    hull.resize(2 * nrows + 2);
+    int nh = hull_from_rows(rowmin.data(), rowmax.data(), ymin, nrows, hull.data());
+    c.nhull = nh;
+    if (nh >= 3) {
+      scratch.resize(3 * nh);
+      RotRect rr = min_area_rect(hull.data(), nh, scratch.data(), scratch.data() + nh, scratch.data() + 2 * nh);
+      c.rect[0] = rr.cx; c.rect[1] = rr.cy; c.rect[2] = rr.w; c.rect[3] = rr.h; c.rect[4] = rr.angle;
+      PtF bp[4];
+      box_points(rr, bp);
+      for (int k = 0; k < 4; ++k) { c.box[2 * k] = bp[k].x; c.box[2 * k + 1] = bp[k].y; }
+    }
+  }
+  return count;
+}
+
+// hull of an arbitrary point list given as row extremes (for direct comparison with cv2.convexHull)
+extern "C" int hh_hull_rows(const int* rowmin, const int* rowmax, int y0, int nrows, int* out_xy) {
+  std::vector<Pt> hull(2 * nrows + 2);
+  int nh = hull_from_rows(rowmin, rowmax, y0, nrows, hull.data());
+  for (int i = 0; i < nh; ++i) { out_xy[2 * i] = hull[i].x; out_xy[2 * i + 1] = hull[i].y; }
+  return nh;
+}

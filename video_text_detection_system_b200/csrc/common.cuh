@@ -1,0 +1,129 @@
+// Shared declarations of libvtd_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <string.h>
+
+namespace vtd {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- element load/store helpers (activations are fp32 or bf16, math is fp32) -------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+struct LaunchCounter { long long n = 0; };
+
+// ---- implicit-GEMM convolution description (NHWC activations, [Cout][kh][kw][Cin] weights) ------
+enum { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2 };          // residual add: same size / nearest-2x upsampled
+enum { OUT_NHWC = 0, OUT_D2S = 1 };                        // plain store / depth-to-space 2x (ConvTranspose k2 s2)
+
+struct ConvDesc {
+  const void* in;      // [N,H,W,Cin]
+  const void* w;       // [Cout][KH*KW*Cin]  (same element type as activations)
+  const float* bias;   // [Cout] fp32 (folded BN)
+  const void* res;     // residual, see res_mode (RES_SAME: [N,Ho,Wo,Cout]; RES_UP2: [N,Ho/2,Wo/2,Cout])
+  void* out;           // OUT_NHWC: [N,Ho,Wo,Cout]; OUT_D2S: [N,2Ho,2Wo,Cout/4], channel co = (dy*2+dx)*(Cout/4)+c
+  int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad;
+  int relu, res_mode, out_mode;
+  int out_f32;         // 1: `out` is fp32 regardless of the activation type (logits, gate pre-activations)
+};
+
+// generic CUDA-core path (any shape); T = float or bf16
+template <typename T> cudaError_t conv_generic(const ConvDesc& d, cudaStream_t s, LaunchCounter* lc);
+
+// tensor-core path (bf16, Cin%64==0, Cout%64==0, stride 1|2); returns cudaErrorNotSupported if shape unsupported
+struct TcPlan;   // opaque: tensor maps + launch geometry, built once per layer
+TcPlan* tc_plan_create(const ConvDesc& d, std::string* err);
+void tc_plan_destroy(TcPlan*);
+cudaError_t conv_tcgen05(const TcPlan* p, int n_actual, cudaStream_t s, LaunchCounter* lc);
+bool tc_supported(const ConvDesc& d);
+
+// ---- pooling -------------------------------------------------------------------------------------
+template <typename T>
+cudaError_t maxpool_nhwc(const T* in, T* out, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                         int ph, int pw, cudaStream_t s, LaunchCounter* lc);
+
+// ---- preprocess ----------------------------------------------------------------------------------
+struct ResizeTab {           // Pillow coefficient tables for one axis, device memory
+  int in_size = 0, out_size = 0, ksize = 0;
+  int* lo = nullptr;         // [out]
+  int* cnt = nullptr;        // [out]
+  int* kk = nullptr;         // [out][ksize]
+};
+template <typename T>
+cudaError_t preprocess_frames(const uint8_t* const* frames_dev /*device array of n pointers*/, int n, int h, int w,
+                              int pitch, int pixfmt, const ResizeTab& tx, const ResizeTab& ty, uint8_t* tmp_u8,
+                              T* out /*[n,dh,dw,4]*/, cudaStream_t s, LaunchCounter* lc);
+
+// ---- fused DB head tail ----------------------------------------------------------------------------
+struct HeadTailWeights {     // both branches; fp32
+  const float* w1;           // [2][256 (dy,dx,co)][64 ci]   folded BN
+  const float* b1;           // [2][256]
+  const float* w2;           // [2][64 co][4 (dy2,dx2)]
+  const float* b2;           // [2]
+};
+template <typename T>
+cudaError_t db_head_tail(const T* feat /*[N,H4,W4,128]*/, const HeadTailWeights& hw, int N, int H4, int W4,
+                         const float* logit_bias /*[N,4H4,4W4] or null*/, float thr, float* prob, float* thresh,
+                         uint8_t* mask, cudaStream_t s, LaunchCounter* lc);
+
+// ---- box extraction ----------------------------------------------------------------------------------
+struct BoxParams {
+  int n, n_alloc, mh, mw;    // planes in this call / planes the workspace was laid out for / plane size
+  int clip_h, clip_w;        // the reference's literal 640s
+  int orig_h, orig_w;
+  int kmax;
+  float unclip;
+};
+struct BoxWorkLayout {       // byte offsets into one device workspace (see boxes.cu)
+  size_t labels, slot_plane, outside, comp, cand_slot, tmp, pool, zero_begin, comp_count, cand_count, pool_used,
+      zero_end, overflow;
+  int cap, kc, pool_words;
+};
+size_t box_work_bytes(int n_alloc, int mh, int mw, int kc, BoxWorkLayout* lay);
+cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParams& p, uint8_t* work,
+                          const BoxWorkLayout& lay, void* records /*vtd_record [n][kmax]*/, int* counts /*[n]*/,
+                          cudaStream_t s, LaunchCounter* lc);
+cudaError_t threshold_mask(const float* prob, uint8_t* mask, long long count, float thr, cudaStream_t s,
+                           LaunchCounter* lc);
+
+// ---- crop gather ---------------------------------------------------------------------------------------
+cudaError_t scan_counts(const int* counts, int n, int* offsets /*[n+1]*/, cudaStream_t s, LaunchCounter* lc);
+// crops [first_crop, first_crop+n_crops) of the batch (record order) -> out [n_crops,32,crop_w,4]
+template <typename T>
+cudaError_t crop_resize_records(const uint8_t* const* frames_dev, int src_h, int src_w, int pitch,
+                                const void* records, const int* offsets, int n, int kmax, int first_crop,
+                                int n_crops, int crop_w, T* out, cudaStream_t s, LaunchCounter* lc);
+template <typename T>
+cudaError_t crop_resize_list(const uint8_t* const* crops_dev, const int* h, const int* w, const int* pitch,
+                             int n_crops, int crop_w, T* out, cudaStream_t s, LaunchCounter* lc);
+
+// ---- LSTM ------------------------------------------------------------------------------------------------
+// One layer, both directions. xproj: [B,T,2,4H] fp32 (= W_ih x + b_ih + b_hh, gate order i,f,g,o);
+// whh: [2][4H][H]; out: [B,T,2H] (T type); hbuf: [2 ping-pong][2 dirs][B][H] fp32; cbuf: [2][B][H] fp32.
+template <typename T, typename WT>
+cudaError_t bilstm_layer(const float* xproj, const WT* whh, T* out, float* hbuf, float* cbuf, int B, int Tn,
+                         int H, cudaStream_t s, LaunchCounter* lc);
+
+// ---- CTC --------------------------------------------------------------------------------------------------
+cudaError_t ctc_greedy(const float* x /*[B,T,V]*/, int B, int T, int V, int is_prob, int canonical,
+                       uint8_t* ids /*[B][ids_stride]*/, int ids_stride, int* lens, float* conf, cudaStream_t s,
+                       LaunchCounter* lc);
+cudaError_t ctc_into_records(const float* logits, int n_crops, int first_crop, int T, int V, int canonical,
+                             const int* offsets, int n, int kmax, void* records, cudaStream_t s, LaunchCounter* lc);
+
+// ---- layout helpers ----------------------------------------------------------------------------------------
+template <typename T>
+cudaError_t nchw_f32_to_nhwc(const float* in, T* out, int N, int C, int H, int W, int Cpad, cudaStream_t s,
+                             LaunchCounter* lc);
+template <typename T>
+cudaError_t nhwc_to_nchw_f32(const T* in, float* out, int N, int C, int H, int W, int Cstride, cudaStream_t s,
+                             LaunchCounter* lc);
+
+}  // namespace vtd
