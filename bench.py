@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p detect+recognize frames/s of the B200 hot path (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], the configuration the metric "detect+recognize frames/sec" is quoted on;
+it fits one GPU): synthetic 1080p BGR frames -> 736x1312 -> DBNet-ResNet18 + fused DB head -> box extraction
+(~50 planted boxes/frame) -> 50 crops/frame 32x128 -> CRNN -> CTC greedy.  bf16 tier.
+A step is one batch of --batch frames through the whole path.
+
+  value : frames/s with the frames already resident in HBM (frame pool larger than L2), results left on device
+  e2e   : frames/s through vtd_run_batch with HOST (pinned) frames: H2D of every frame and D2H of the records
+          inside the timed region
+  roofline     : dominant kernel (tcgen05 implicit-GEMM conv, all launches of the timed region), algorithmic
+                 FLOPs / CUDA-event time, against MEASURED_PEAKS.json bf16_tflops_sustained
+  cpu_baseline : oracle/port.py (the reference's PyTorch/PIL/OpenCV arithmetic) on the host cores, bounded sample
+
+`--impl reference` times that CPU path alone (one frame per step).  N>1: one process per GPU (torchrun), frames
+sharded by rank, records gathered to rank 0 every step with NCCL; time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SRC_H, SRC_W = 1080, 1920
+DET_H, DET_W = 736, 1312
+CROP_W = 128
+BOXES = 50
+GF_DET_PER_FRAME = 184.51          # SURVEY.md 8d, DBNet-R18 @736x1312, live layers
+GF_CRNN_PER_CROP = 1.787           # @32x128
+METRIC = "1080p detect+recognize frames/sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": float(d.get("bf16_tflops_sustained", 1357.9)), "tflops_burst": float(d.get("bf16_tflops", 1635.9)),
+                "hbm": float(d.get("hbm_gbs", 6531.9)), "source": "measured"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (pynvml; same counters as nvidia-smi)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_models():
+    import torch
+    from oracle import port
+    torch.set_num_threads(os.cpu_count() or 1)
+    return port, port.build_dbnet("resnet18", seed=0), port.build_crnn(seed=0)
+
+
+def cpu_frame(port, det, rec, frame, bias):
+    """The reference's per-frame path (pipeliine.py:143-172): detect, then batch-1 recognise per crop."""
+    import torch
+    return port.process_frame(det, rec, frame, 0.5, DET_H, DET_W, CROP_W, torch.from_numpy(bias)[None, None],
+                              per_crop=True)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    port, det, rec = cpu_models()
+    n = args.warmup + args.steps
+    frames = port.synthetic_frames(min(n, 4), SRC_H, SRC_W, seed=0)
+    bias = port.planted_logit_bias(1, DET_H, DET_W, seed=0, boxes=BOXES)[0]
+    for i in range(args.warmup):
+        cpu_frame(port, det, rec, frames[i % len(frames)], bias)
+    t0 = time.perf_counter()
+    nb = 0
+    for i in range(args.steps):
+        nb += len(cpu_frame(port, det, rec, frames[(args.warmup + i) % len(frames)], bias))
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(1, 1),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d frames, 1 frame per step, per-crop recognise as pipeliine.py:117-125, "
+                                       "%.1f boxes/frame" % (args.steps, nb / max(args.steps, 1))},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, world):
+    return {"workload": "configs[2]: full pipeline DBNet-ResNet18 detect (1080p -> 736x1312, fused DB head, box "
+                        "extraction) + CRNN recognise (32x128 crops, CTC greedy), ~50 planted boxes/frame",
+            "frame": [SRC_H, SRC_W], "det": [DET_H, DET_W], "crop": [32, CROP_W], "boxes_per_frame": BOXES,
+            "frames_per_step_per_gpu": batch, "parallelism": "frame-sharded dp%d" % world,
+            "l2": "frame pool of 32 distinct 1080p frames (199 MB) + per-step activations exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-op device-time table (JSON) here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from oracle import port                       # synthetic workload generators only (frames, planted plane)
+    from video_text_detection_system_b200 import _lib, parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    POOL = 32
+    eng = _lib.Engine(device=local_rank, backbone=18, dtype=args.dtype, det_h=DET_H, det_w=DET_W, crop_w=CROP_W,
+                      max_batch=B, max_boxes=64, max_src_h=SRC_H, max_src_w=SRC_W)
+    eng.load_detector(port.build_dbnet("resnet18", seed=0).state_dict())
+    eng.load_recognizer(port.build_crnn(seed=0).state_dict())
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)            # one stream for kernels, NCCL and the timing events
+
+    # synthetic inputs: every rank owns its shard of a global pool (rank-strided), seeded
+    rng = np.random.default_rng(1000 + rank)
+    host_pool = torch.from_numpy(rng.integers(0, 256, (POOL, SRC_H, SRC_W, 3), dtype=np.uint8)).pin_memory()
+    dev_pool = host_pool.to(dev)
+    bias = torch.from_numpy(port.planted_logit_bias(B, DET_H, DET_W, seed=7 + rank, boxes=BOXES)).to(dev)
+    frame_bytes = SRC_H * SRC_W * 3
+    import ctypes as C
+
+    def ptrs_of(base_ptr, step):
+        arr = (C.c_void_p * B)()
+        for i in range(B):
+            arr[i] = base_ptr + ((step * B + i) % POOL) * frame_bytes
+        return arr
+
+    rec_ptr, cnt_ptr = eng.device_records()
+    rec_t = parallel.device_bytes_as_tensor(rec_ptr, B * 64 * 128, dev).view(B, 64 * 128)
+    cnt_t = parallel.device_bytes_as_tensor(cnt_ptr, B * 4, dev).view(torch.int32)
+    host_rec = torch.empty((B, 64 * 128), dtype=torch.uint8).pin_memory()
+    host_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+    def step_resident(i):
+        eng.run_batch_raw(ptrs_of(dev_pool.data_ptr(), i), B, SRC_H, SRC_W, SRC_W * 3, True, 0.5, True, bias.data_ptr())
+        if world > 1:
+            parallel.gather_records(rec_t, cnt_t, 0)
+
+    def step_e2e(i):
+        eng.run_batch_raw(ptrs_of(host_pool.data_ptr(), i), B, SRC_H, SRC_W, SRC_W * 3, False, 0.5, True, bias.data_ptr(),
+                          host_rec.data_ptr(), host_cnt.data_ptr())
+        if world > 1:
+            parallel.gather_records(rec_t, cnt_t, 0)
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            eng.set_profiling(True)
+        l0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = eng.launch_count() - l0
+        prof = None
+        if profile:
+            eng.set_profiling(False)
+            prof = {"detector": eng.op_profile(0), "recogniser": eng.op_profile(1)}
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, prof
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+
+    # sanity: the path really produced ~50 boxes per frame with text
+    torch.cuda.synchronize()
+    counts = cnt_t.cpu().numpy()
+    frames_total = args.steps * B * world
+    value = frames_total / (ms / 1e3)
+    e2e = frames_total / (ms_e2e / 1e3)
+
+    pk = peaks()
+    # roofline of the dominant kernel family: every tcgen05 conv launch of the timed region
+    tc_flops = tc_ms = 0.0
+    top = None
+    for which, per_unit in (("detector", B), ("recogniser", int(counts.sum()))):
+        for op in prof[which]:
+            if op["kind"] != 0 or op["launches"] == 0:
+                continue
+            units = per_unit
+            fl = 2.0 * units * op["Ho"] * op["Wo"] * op["Cout"] * op["Cin"] * op["KH"] * op["KW"] * op["launches"]
+            op["gflop"] = fl / 1e9
+            op["tflops"] = fl / (op["ms"] * 1e-3) / 1e12 if op["ms"] > 0 else None
+            if op["tensor_core"]:
+                tc_flops += fl
+                tc_ms += op["ms"]
+                if top is None or op["ms"] > top["ms"]:
+                    top = op
+    if top is not None:
+        per_launch_flops = top["gflop"] * 1e9 / top["launches"]
+        per_launch_ms = top["ms"] / top["launches"]
+        ach = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM) %dx%d %d->%d k%d" %
+                (top["H"], top["W"], top["Cin"], top["Cout"], top["KH"]),
+                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "ms_per_launch": per_launch_ms, "gflop_per_launch": per_launch_flops / 1e9,
+                "all_tc_convs": {"tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None,
+                                 "share_of_step": tc_ms / ms if ms > 0 else None}}
+    else:
+        fl = 2.0 * 0
+        roof = {"bound": "tensor", "achieved": None, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": None, "traffic": None}
+    alg_gf = GF_DET_PER_FRAME + GF_CRNN_PER_CROP * float(counts.mean())
+    if args.profile_out and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
+        json.dump({"ms_total": ms, "steps": args.steps, "batch": B, "ops": prof}, open(args.profile_out, "w"), indent=1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        p2, det, rec = cpu_models()
+        fr = host_pool[:max(1, args.cpu_frames)].numpy()
+        b0 = bias[0].cpu().numpy()
+        cpu_frame(p2, det, rec, fr[0], b0)                          # warm-up
+        t0 = time.perf_counter()
+        nb = sum(len(cpu_frame(p2, det, rec, f, b0)) for f in fr)
+        dt = time.perf_counter() - t0
+        cpu = {"value": len(fr) / dt, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "%d frames of the same workload, reference-style per-frame detect + per-crop recognise, "
+                         "%.1f boxes/frame, torch threads=%d" % (len(fr), nb / len(fr), os.cpu_count() or 1)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(B, world),
+                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * frame_bytes,
+                        "d2h_bytes_per_step": B * 64 * 128 + B * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof,
+                "cpu_baseline": cpu,
+                "boxes_per_frame": float(counts.mean()),
+                "alg_gflop_per_frame": alg_gf,
+                "e2e_tensor_frac": (alg_gf * 1e9 * value / world) / (pk["tflops"] * 1e12)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

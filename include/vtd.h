@@ -160,6 +160,14 @@ int  vtd_get_records(vtd_ctx* ctx, vtd_record** records_dev, int** counts_dev); 
  * names: "input","c2","c3","c4","c5","p2_in","p2","head","crops","cnn","rnn0","rnn1","logits". */
 int  vtd_debug_tensor(vtd_ctx* ctx, const char* name, int n, float* host_out, int64_t capacity, int64_t* shape4);
 
+/* ---- measurement: per-launch device times of the conv / pool programs, taken with CUDA events on the
+ * launching stream while the normal entry points run (bench.py's roofline figures).  which: 0 detector,
+ * 1 recogniser.  info[16] = {kind (0 conv, 1 pool), tensor_core, H, W, Cin, Ho, Wo, Cout, KH, KW, stride,
+ * launches timed, 0...}; *ms = summed device time of those launches. */
+int  vtd_set_profiling(vtd_ctx* ctx, int on);
+int  vtd_op_count(vtd_ctx* ctx, int which);
+int  vtd_op_info(vtd_ctx* ctx, int which, int idx, int64_t* info, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

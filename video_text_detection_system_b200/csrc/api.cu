@@ -26,6 +26,8 @@ struct DebugEntry { const void* p; int C, H, W, Cstride; bool f32; bool per_crop
 
 struct Op {
   enum Kind { CONV, POOL } kind = CONV;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // profiling (vtd_set_profiling): last launch of this op
+  double prof_ms = 0.0; long long prof_n = 0; bool prof_pending = false;
   ConvDesc d{};
   TcPlan* plan = nullptr;
   // pool
@@ -48,6 +50,7 @@ struct vtd_ctx {
   std::string err;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   LaunchCounter lc;
+  bool profiling = false;
   std::vector<void*> allocs;
   size_t esz = 4;                       // activation element size
   bool bf16_mode = false;
@@ -252,8 +255,28 @@ cudaError_t run_op(vtd_ctx* c, const Op& op, int n) {
   return conv_generic<float>(d, c->stream, &c->lc);
 }
 
-int run_prog(vtd_ctx* c, const std::vector<Op>& prog, int n) {
-  for (const Op& op : prog) CK(run_op(c, op, n));
+// With profiling on, every op of a program is bracketed by CUDA events on the launching stream; the pair of
+// the previous launch is harvested (it has long completed) before it is re-recorded, so there is no sync.
+void prof_harvest(Op& op) {
+  if (!op.prof_pending) return;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, op.ev0, op.ev1) == cudaSuccess) { op.prof_ms += ms; op.prof_n++; op.prof_pending = false; }
+  else cudaGetLastError();   // not ready yet: keep pending, clear the sticky-free error
+}
+
+int run_op_prof(vtd_ctx* c, Op& op, int n) {
+  if (!c->profiling) { CK(run_op(c, op, n)); return VTD_OK; }
+  if (!op.ev0) { CK(cudaEventCreate(&op.ev0)); CK(cudaEventCreate(&op.ev1)); }
+  if (op.prof_pending) { cudaEventSynchronize(op.ev1); prof_harvest(op); }
+  CK(cudaEventRecord(op.ev0, c->stream));
+  CK(run_op(c, op, n));
+  CK(cudaEventRecord(op.ev1, c->stream));
+  op.prof_pending = true;
+  return VTD_OK;
+}
+
+int run_prog(vtd_ctx* c, std::vector<Op>& prog, int n) {
+  for (Op& op : prog) { int r = run_op_prof(c, op, n); if (r) return r; }
   return VTD_OK;
 }
 
@@ -476,7 +499,7 @@ int run_crnn(vtd_ctx* c, int nc) {
   int r = run_prog(c, c->rec_prog, nc); if (r) return r;
   for (int l = 0; l < 2; ++l) {
     // the second layer's xproj reuses its own buffer (allocated by add_conv)
-    CK(run_op(c, c->xproj_op[l], nc));
+    { int r2 = run_op_prof(c, c->xproj_op[l], nc); if (r2) return r2; }
     const float* xp = (const float*)c->xproj_op[l].d.out;
     if (c->bf16_mode)
       CK((bilstm_layer<bf16, bf16>(xp, (const bf16*)c->whh[l], (bf16*)c->rnn_out[l], c->hbuf, c->cbuf, nc, c->T, 256,
@@ -485,7 +508,7 @@ int run_crnn(vtd_ctx* c, int nc) {
       CK((bilstm_layer<float, float>(xp, (const float*)c->whh[l], (float*)c->rnn_out[l], c->hbuf, c->cbuf, nc, c->T, 256,
                                      c->stream, &c->lc)));
   }
-  CK(run_op(c, c->fc_op, nc));
+  { int r2 = run_op_prof(c, c->fc_op, nc); if (r2) return r2; }
   return VTD_OK;
 }
 
@@ -979,6 +1002,49 @@ int vtd_read_records(vtd_ctx* c, int n, vtd_record* rh, int* ch) {
 int vtd_get_records(vtd_ctx* c, vtd_record** r, int** cnt) {
   if (!c) return VTD_ERR_ARG;
   if (r) *r = c->records; if (cnt) *cnt = c->counts;
+  return VTD_OK;
+}
+
+static std::vector<Op*> prof_ops(vtd_ctx* c, int which) {
+  std::vector<Op*> v;
+  if (which == 0) for (Op& o : c->det_prog) v.push_back(&o);
+  else {
+    for (Op& o : c->rec_prog) v.push_back(&o);
+    if (c->rec_loaded) { v.push_back(&c->xproj_op[0]); v.push_back(&c->xproj_op[1]); v.push_back(&c->fc_op); }
+  }
+  return v;
+}
+
+int vtd_set_profiling(vtd_ctx* c, int on) {
+  if (!c) return VTD_ERR_ARG;
+  Guard g(c);
+  CK(cudaStreamSynchronize(c->stream));
+  for (int w = 0; w < 2; ++w)
+    for (Op* o : prof_ops(c, w)) { prof_harvest(*o); if (on) { o->prof_ms = 0.0; o->prof_n = 0; o->prof_pending = false; } }
+  c->profiling = on != 0;
+  return VTD_OK;
+}
+
+int vtd_op_count(vtd_ctx* c, int which) { if (!c) return 0; Guard g(c); return (int)prof_ops(c, which).size(); }
+
+/* info[16]: kind(0 conv,1 pool), tensor_core(0/1), H, W, Cin, Ho, Wo, Cout, KH, KW, stride, launches, 0... ; ms = summed
+ * device time of those launches */
+int vtd_op_info(vtd_ctx* c, int which, int idx, int64_t* info, double* ms) {
+  if (!c || !info) return VTD_ERR_ARG;
+  Guard g(c);
+  std::vector<Op*> v = prof_ops(c, which);
+  if (idx < 0 || idx >= (int)v.size()) FAIL(VTD_ERR_ARG, "op index out of range");
+  Op& o = *v[idx];
+  if (o.prof_pending) { cudaEventSynchronize(o.ev1); prof_harvest(o); }
+  for (int i = 0; i < 16; ++i) info[i] = 0;
+  if (o.kind == Op::CONV) {
+    info[0] = 0; info[1] = o.plan ? 1 : 0; info[2] = o.d.H; info[3] = o.d.W; info[4] = o.d.Cin; info[5] = o.d.Ho;
+    info[6] = o.d.Wo; info[7] = o.d.Cout; info[8] = o.d.KH; info[9] = o.d.KW; info[10] = o.d.stride;
+  } else {
+    info[0] = 1; info[2] = o.H; info[3] = o.W; info[4] = o.C; info[8] = o.kh; info[9] = o.kw; info[10] = o.sh;
+  }
+  info[11] = o.prof_n;
+  if (ms) *ms = o.prof_ms;
   return VTD_OK;
 }
 

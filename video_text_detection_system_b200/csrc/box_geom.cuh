@@ -116,17 +116,18 @@ VTD_HD int hull_from_rows(const int* rowmin, const int* rowmax, int y0, int nrow
     }
   }
   if (n < 3) return n;
-  // cv::minAreaRect calls convexHull(points, clockwise=true): start at the left-most point (smallest y among
-  // ties), then towards larger y (down the image), the right-most point, the top, and back -- the reverse
-  // walk of the one built above.
-  for (int a = 0, b = n - 1; a < b; ++a, --b) { Pt t = hull[a]; hull[a] = hull[b]; hull[b] = t; }
+  // cv::minAreaRect calls convexHull(points, clockwise=false): the walk built above (top -> right -> bottom ->
+  // left on screen) is already that direction.  OpenCV then shifts the sequence cyclically so that the
+  // indices into the contour descend; the contour starts at the component's raster-first pixel, so the
+  // vertex (min y, then min x) comes LAST.  (Verified against cv2 4.13 on >6000 blobs; contours that pass
+  // twice through 1-pixel-wide appendages can start elsewhere, which only matters for exact ties.)
   int best = 0;
   for (int i = 1; i < n; ++i)
-    if (hull[i].x < hull[best].x || (hull[i].x == hull[best].x && hull[i].y < hull[best].y)) best = i;
-  if (best != 0) {
-    // in-place rotation by three reversals
+    if (hull[i].y < hull[best].y || (hull[i].y == hull[best].y && hull[i].x < hull[best].x)) best = i;
+  const int shift = (best + 1) % n;      // new first element
+  if (shift != 0) {
     auto rev = [&](int a, int b) { while (a < b) { Pt t = hull[a]; hull[a] = hull[b]; hull[b] = t; ++a; --b; } };
-    rev(0, best - 1); rev(best, n - 1); rev(0, n - 1);
+    rev(0, shift - 1); rev(shift, n - 1); rev(0, n - 1);
   }
   return n;
 }
@@ -170,16 +171,17 @@ VTD_HD RotRect min_area_rect(const Pt* hp, int n, float* inv_len, float* vx, flo
   int best_left = 0, best_bottom = 0;
   float best_a = 0.f, best_b = 0.f, best_w = 0.f, best_h = 0.f;
   for (int k = 0; k < n; ++k) {
-    float dp[4];
-    dp[0] = fadd(fmul(+base_a, vx[seq[0]]), fmul(base_b, vy[seq[0]]));
-    dp[1] = fadd(fmul(-base_b, vx[seq[1]]), fmul(base_a, vy[seq[1]]));
-    dp[2] = fsub(fmul(-base_a, vx[seq[2]]), fmul(base_b, vy[seq[2]]));
-    dp[3] = fsub(fmul(+base_b, vx[seq[3]]), fmul(base_a, vy[seq[3]]));
+    // OpenCV >= 4.5: pick the caliper whose (rotated) polygon edge is right-most, by cross-product sign
+    float rvx[4], rvy[4];
+    rvx[0] = vx[seq[0]];  rvy[0] = vy[seq[0]];
+    rvx[1] = vy[seq[1]];  rvy[1] = -vx[seq[1]];     // rotate90CW
+    rvx[2] = -vx[seq[2]]; rvy[2] = -vy[seq[2]];     // rotate180
+    rvx[3] = -vy[seq[3]]; rvy[3] = vx[seq[3]];      // rotate90CCW
     int main_element = 0;
-    float maxcos = fmul(dp[0], inv_len[seq[0]]);
     for (int i = 1; i < 4; ++i) {
-      float cosalpha = fmul(dp[i], inv_len[seq[i]]);
-      if (cosalpha > maxcos) { main_element = i; maxcos = cosalpha; }
+      // firstVecIsRight(rv[i], rv[main]): rotate90CW(v1) . v2 < 0
+      float tx = rvy[i], ty = -rvx[i];
+      if (fadd(fmul(tx, rvx[main_element]), fmul(ty, rvy[main_element])) < 0.f) main_element = i;
     }
     {
       int pindex = seq[main_element];
@@ -221,10 +223,12 @@ VTD_HD RotRect min_area_rect(const Pt* hp, int n, float* inv_len, float* vx, flo
   rr.cy = fadd(py, fmul(fadd(o1y, o2y), 0.5f));
   rr.w = (float)sqrt(dadd(dmul((double)o1x, (double)o1x), dmul((double)o1y, (double)o1y)));
   rr.h = (float)sqrt(dadd(dmul((double)o2x, (double)o2x), dmul((double)o2y, (double)o2y)));
-  float ang = (float)atan2((double)o1y, (double)o1x);
-  rr.angle = (float)((double)ang * 180.0 / 3.1415926535897932384626433832795);
-  // OpenCV reports the angle in [-90, 0): a non-negative angle is the same rectangle with its sides swapped
-  if (rr.angle >= 0.f) { float t = rr.w; rr.w = rr.h; rr.h = t; rr.angle = fsub(rr.angle, 90.f); }
+  // angle in degrees, computed in double and folded into [-90, 0) before the single rounding to float
+  // (cv2 4.13 behaviour, verified bit-exact: >= 90 -> -180 keeping the sides, else -90 swapping them)
+  double ang = atan2((double)o1y, (double)o1x) * 180.0 / 3.1415926535897932384626433832795;
+  if (ang >= 90.0) ang -= 180.0;
+  else if (ang >= 0.0 || ang < -90.0) { float t = rr.w; rr.w = rr.h; rr.h = t; ang += (ang >= 0.0 ? -90.0 : 90.0); }
+  rr.angle = (float)ang;
   return rr;
 }
 

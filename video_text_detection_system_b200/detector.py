@@ -1,0 +1,114 @@
+"""TextDetector with the reference's call surface (app/ml/models/text_detector.py:88-178).
+
+`detect()` = vtd_run_batch on one frame: Pillow-exact preprocess -> DBNet conv stack -> fused DB head ->
+GPU box extraction, all inside libvtd_b200.so; only the final records cross back to the host.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import threading
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+
+from ._lib import Engine, records_to_detections
+from .models import DBNet
+
+logger = logging.getLogger(__name__)
+
+
+class _Transform:
+    """Stands in for the torchvision Compose at text_detector.py:99-104 (`detector.transform`): callable
+    on an RGB HxWx3 uint8 array, returns the normalised [3,Hd,Wd] tensor -- computed by the CUDA
+    preprocess kernel, bit-exact to ToPILImage/Resize/ToTensor/Normalize."""
+
+    def __init__(self, det: "TextDetector"):
+        self._det = det
+
+    def __call__(self, image_rgb: np.ndarray) -> torch.Tensor:
+        if image_rgb.ndim != 3 or image_rgb.shape[2] != 3 or image_rgb.dtype != np.uint8:
+            raise TypeError("transform expects an HxWx3 uint8 array")
+        bgr = np.ascontiguousarray(image_rgb[:, :, ::-1])
+        eng = self._det._engine_for(bgr.shape[0], bgr.shape[1])
+        with self._det._lock:
+            eng.preprocess([bgr])
+            x = eng.debug_tensor("input", 1)
+        return torch.from_numpy(x[0])
+
+
+class TextDetector:
+    def __init__(self, model_path: str = None, device: str = None, *, backbone: str = "resnet50",
+                 pretrained: bool = True, det_size=(640, 640), dtype: Optional[str] = None, max_boxes: int = 256,
+                 unclip_ratio: float = 1.0):
+        # text_detector.py:90 -- CUDA initialisation itself is deferred to the first call (prefork-safe, D10)
+        self.device = device or "cuda"
+        self.det_h, self.det_w = int(det_size[0]), int(det_size[1])
+        self.max_boxes = max_boxes
+        self.unclip_ratio = unclip_ratio
+        self.model = DBNet(backbone=backbone, pretrained=pretrained)
+        self.model.dtype_tier = (dtype or os.environ.get("VTD_DTYPE", "fp32")).lower()
+        if model_path:
+            self.load_model(model_path)
+        self.model.eval()
+        self.transform = _Transform(self)
+        self._lock = threading.Lock()
+
+    def load_model(self, model_path: str):
+        try:
+            checkpoint = torch.load(model_path, map_location="cpu")
+            self.model.load_state_dict(checkpoint["model_state_dict"])
+            logger.info(f"Model loaded from {model_path}")
+        except Exception as e:
+            logger.error(f"Failed to load model: {e}")
+            raise
+
+    # ---- engine plumbing
+    def _engine_for(self, src_h: int, src_w: int, max_batch: int = 1, crop_w: int = 128) -> Engine:
+        mh = max(2160, src_h)
+        mw = max(3840, src_w)
+        return self.model.get_engine(self.det_h, self.det_w, max_batch=max_batch, max_boxes=self.max_boxes,
+                                     crop_w=crop_w, max_src_h=mh, max_src_w=mw, device=self.device,
+                                     unclip_ratio=self.unclip_ratio)
+
+    def _forward_is_patched(self) -> bool:
+        return "forward" in vars(self.model)
+
+    # ---- reference surface
+    def detect(self, image: np.ndarray, confidence_threshold: float = 0.5) -> List[Dict[str, Any]]:
+        try:
+            original_height, original_width = image.shape[:2]
+            if image.ndim != 3 or image.shape[2] != 3:
+                # the reference's Normalize fails on anything but 3 channels and detect() returns []
+                raise ValueError("expected an HxWx3 BGR image, got shape %s" % (image.shape,))
+            if image.dtype != np.uint8:
+                raise TypeError("expected uint8 pixels, got %s" % image.dtype)
+            if self._forward_is_patched():
+                # test-compat path (tests/test_models.py:30): the caller replaced model.forward
+                x = self.transform(np.ascontiguousarray(image[:, :, ::-1])).unsqueeze(0)
+                with torch.no_grad():
+                    output = self.model(x)
+                prob_map = output["probability"].detach().cpu().numpy()[0, 0]
+                return self._post_process(prob_map, original_width, original_height, confidence_threshold)
+            eng = self._engine_for(original_height, original_width)
+            with self._lock:
+                rec, cnt = eng.run_batch([image], thr=confidence_threshold, recognize=False)
+            dets = records_to_detections(rec[0], int(cnt[0]), with_text=False)
+            return dets
+        except Exception as e:
+            logger.error(f"Detection failed: {e}")
+            return []
+
+    def _post_process(self, prob_map: np.ndarray, orig_width: int, orig_height: int, threshold: float
+                      ) -> List[Dict[str, Any]]:
+        """text_detector.py:143-178 on a caller-supplied map of any size (the clip/scale constants stay the
+        detector size, 640 in the reference)."""
+        prob_map = np.asarray(prob_map)
+        if prob_map.ndim != 2:
+            raise ValueError("prob_map must be 2-D")
+        eng = self._engine_for(1, 1)
+        with self._lock:
+            rec = eng.postprocess_map(prob_map.astype(np.float32, copy=False), orig_width, orig_height, threshold,
+                                      clip_h=self.det_h, clip_w=self.det_w)
+        return records_to_detections(rec, len(rec), with_text=False)

@@ -1,0 +1,237 @@
+"""DBNet and CRNN with the reference's constructor signatures and state-dict layout.
+
+Reference: app/ml/models/text_detector.py:12-86 (DBNet, FeaturePyramidNetwork, DBHead) and
+app/ml/models/text_recognizer.py:12-37 (CRNN).  These nn.Modules only HOLD parameters (so
+`load_state_dict`, `state_dict`, `.to()`, `.eval()` and `patch.object(model, 'forward')` behave as the
+reference's callers and tests expect); `forward` does not run PyTorch ops -- it hands the parameters to
+libvtd_b200.so and runs the sm_100a kernels.  Key names and shapes are those of SURVEY.md Appendix D, so
+a checkpoint written by the reference loads unchanged.
+
+Differences from the reference as shipped, all forced: the FPN feeds lateral i with
+backbone level C(5-i) (D5), 'resnet18' is accepted (D6) and `pretrained=True` only takes effect when
+torchvision can supply weights offline (D7).
+"""
+from __future__ import annotations
+
+import logging
+import threading
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ._lib import Engine
+
+logger = logging.getLogger(__name__)
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter containers with torchvision's ResNet naming (conv1/bn1/.../downsample.{0,1})
+# ---------------------------------------------------------------------------------------------------
+class _Block(nn.Module):
+    def __init__(self, inplanes: int, planes: int, stride: int, bottleneck: bool):
+        super().__init__()
+        if bottleneck:
+            self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+            self.bn1 = nn.BatchNorm2d(planes)
+            self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+            self.bn2 = nn.BatchNorm2d(planes)
+            self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+            self.bn3 = nn.BatchNorm2d(planes * 4)
+            out = planes * 4
+        else:
+            self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False)
+            self.bn1 = nn.BatchNorm2d(planes)
+            self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+            self.bn2 = nn.BatchNorm2d(planes)
+            out = planes
+        self.relu = nn.ReLU(inplace=True)
+        if stride != 1 or inplanes != out:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, out, 1, stride, bias=False), nn.BatchNorm2d(out))
+        else:
+            self.downsample = None
+        self.out_channels = out
+
+
+def _resnet_trunk(depth: int) -> Tuple[nn.Sequential, int]:
+    """children()[:-2] of a torchvision ResNet: conv1, bn1, relu, maxpool, layer1..4."""
+    bottleneck = depth == 50
+    counts = {18: (2, 2, 2, 2), 50: (3, 4, 6, 3)}[depth]
+    mods = [nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+            nn.MaxPool2d(3, 2, 1)]
+    inplanes = 64
+    for li, n in enumerate(counts):
+        planes = 64 << li
+        blocks = []
+        for bi in range(n):
+            b = _Block(inplanes, planes, 2 if (bi == 0 and li > 0) else 1, bottleneck)
+            inplanes = b.out_channels
+            blocks.append(b)
+        mods.append(nn.Sequential(*blocks))
+    trunk = nn.Sequential(*mods)
+    for m in trunk.modules():                      # torchvision's ResNet initialisation
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+    return trunk, inplanes
+
+
+class FeaturePyramidNetwork(nn.Module):
+    """text_detector.py:31-40 (parameters only)."""
+
+    def __init__(self, in_channels: int, out_channels: int = 256):
+        super().__init__()
+        self.inner_blocks = nn.ModuleList()
+        self.layer_blocks = nn.ModuleList()
+        for i in range(4):
+            self.inner_blocks.append(nn.Conv2d(in_channels // (2 ** i), out_channels, 1))
+            self.layer_blocks.append(nn.Conv2d(out_channels, out_channels, 3, padding=1))
+
+
+class DBHead(nn.Module):
+    """text_detector.py:58-81 (parameters only)."""
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+
+        def branch():
+            q = in_channels // 4
+            return nn.Sequential(nn.Conv2d(in_channels, q, 3, padding=1), nn.BatchNorm2d(q), nn.ReLU(inplace=True),
+                                 nn.ConvTranspose2d(q, q, 2, stride=2), nn.BatchNorm2d(q), nn.ReLU(inplace=True),
+                                 nn.ConvTranspose2d(q, 1, 2, stride=2), nn.Sigmoid())
+        self.probability_head = branch()
+        self.threshold_head = branch()
+
+
+class _EngineOwner:
+    """Mixin: lazily created, cached libvtd contexts keyed by their configuration."""
+
+    def _init_engines(self):
+        object.__setattr__(self, "_engines", {})
+        object.__setattr__(self, "_engine_lock", threading.Lock())
+        object.__setattr__(self, "_weights_version", 0)
+
+    def invalidate_engines(self):
+        with self._engine_lock:
+            for e, _ in self._engines.values():
+                e.close()
+            self._engines.clear()
+            object.__setattr__(self, "_weights_version", self._weights_version + 1)
+
+
+def _device_index(device) -> int:
+    if device is None:
+        return torch.cuda.current_device() if torch.cuda.is_available() else 0
+    d = torch.device(device) if not isinstance(device, torch.device) else device
+    if d.type != "cuda":
+        return torch.cuda.current_device() if torch.cuda.is_available() else 0
+    return d.index if d.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+
+
+class DBNet(nn.Module, _EngineOwner):
+    def __init__(self, backbone: str = "resnet50", pretrained: bool = True):
+        super().__init__()
+        self._init_engines()
+        if backbone not in ("resnet18", "resnet50"):
+            raise ValueError("backbone must be 'resnet18' or 'resnet50', got %r" % (backbone,))
+        self.backbone_name = backbone
+        depth = 50 if backbone == "resnet50" else 18
+        self.backbone, in_channels = _resnet_trunk(depth)                 # text_detector.py:17-20
+        self.fpn = FeaturePyramidNetwork(in_channels)                     # :22
+        self.head = DBHead(256)                                           # :23
+        self.dtype_tier = "fp32"
+        if pretrained:
+            self._try_load_pretrained(depth)
+
+    def _try_load_pretrained(self, depth: int):
+        try:
+            import torchvision
+            ctor = torchvision.models.resnet50 if depth == 50 else torchvision.models.resnet18
+            rn = ctor(weights="DEFAULT")
+            trunk = nn.Sequential(*list(rn.children())[:-2])
+            self.backbone.load_state_dict(trunk.state_dict())
+        except Exception as e:  # offline: keep the random initialisation
+            logger.warning("pretrained ImageNet weights unavailable (%s); backbone keeps its random init", e)
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate_engines()
+        return r
+
+    def get_engine(self, det_h: int, det_w: int, dtype: Optional[str] = None, max_batch: int = 1,
+                   max_boxes: int = 256, crop_w: int = 128, max_src_h: int = 2160, max_src_w: int = 3840,
+                   device=None, unclip_ratio: float = 1.0) -> Engine:
+        dtype = dtype or self.dtype_tier
+        key = (det_h, det_w, dtype, max_batch, max_boxes, crop_w, max_src_h, max_src_w, _device_index(device),
+               float(unclip_ratio))
+        with self._engine_lock:
+            hit = self._engines.get(key)
+            if hit is not None:
+                return hit[0]
+            eng = Engine(device=key[8], backbone=50 if self.backbone_name == "resnet50" else 18, dtype=dtype,
+                         det_h=det_h, det_w=det_w, crop_w=crop_w, max_batch=max_batch, max_boxes=max_boxes,
+                         max_src_h=max_src_h, max_src_w=max_src_w, unclip_ratio=unclip_ratio)
+            eng.load_detector(self.state_dict())
+            self._engines[key] = (eng, self._weights_version)
+            return eng
+
+    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """text_detector.py:25-29: {'probability','threshold'} each [N,1,H,W] fp32, on x's device."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError("expected [N,3,H,W]")
+        h, w = int(x.shape[2]), int(x.shape[3])
+        eng = self.get_engine(h, w, device=x.device if x.is_cuda else None)
+        p, t = eng.dbnet_forward(x.detach().float().cpu().numpy())
+        return {"probability": torch.from_numpy(p).to(x.device), "threshold": torch.from_numpy(t).to(x.device)}
+
+
+class CRNN(nn.Module, _EngineOwner):
+    def __init__(self, vocab_size: int, hidden_size: int = 256, num_layers: int = 2):
+        super().__init__()
+        self._init_engines()
+        self.cnn = nn.Sequential(                                         # text_recognizer.py:16-24
+            nn.Conv2d(3, 64, 3, 1, 1), nn.BatchNorm2d(64), nn.ReLU(True), nn.MaxPool2d(2, 2),
+            nn.Conv2d(64, 128, 3, 1, 1), nn.BatchNorm2d(128), nn.ReLU(True), nn.MaxPool2d(2, 2),
+            nn.Conv2d(128, 256, 3, 1, 1), nn.BatchNorm2d(256), nn.ReLU(True),
+            nn.Conv2d(256, 256, 3, 1, 1), nn.BatchNorm2d(256), nn.ReLU(True), nn.MaxPool2d((2, 1), (2, 1)),
+            nn.Conv2d(256, 512, 3, 1, 1), nn.BatchNorm2d(512), nn.ReLU(True),
+            nn.Conv2d(512, 512, 3, 1, 1), nn.BatchNorm2d(512), nn.ReLU(True), nn.MaxPool2d((2, 1), (2, 1)),
+            nn.Conv2d(512, 512, 2, 1, 0), nn.BatchNorm2d(512), nn.ReLU(True))
+        self.rnn = nn.LSTM(512, hidden_size, num_layers, batch_first=True, bidirectional=True)   # :26
+        self.classifier = nn.Linear(hidden_size * 2, vocab_size)                                 # :27
+        self.vocab_size, self.hidden_size, self.num_layers = vocab_size, hidden_size, num_layers
+        self.dtype_tier = "fp32"
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate_engines()
+        return r
+
+    def _check_supported(self):
+        if self.vocab_size != 97 or self.hidden_size != 256 or self.num_layers != 2:
+            raise NotImplementedError("the sm_100a recogniser is built for vocab 97 / hidden 256 / 2 layers "
+                                      "(text_recognizer.py:81,26); got %d/%d/%d"
+                                      % (self.vocab_size, self.hidden_size, self.num_layers))
+
+    def get_engine(self, crop_w: int = 128, dtype: Optional[str] = None, device=None) -> Engine:
+        self._check_supported()
+        dtype = dtype or self.dtype_tier
+        key = (crop_w, dtype, _device_index(device))
+        with self._engine_lock:
+            hit = self._engines.get(key)
+            if hit is not None:
+                return hit[0]
+            # recogniser-only context: the detector side is sized minimally and never loaded
+            eng = Engine(device=key[2], backbone=18, dtype=dtype, det_h=32, det_w=32, crop_w=crop_w, max_batch=1,
+                         max_boxes=1024, max_src_h=32, max_src_w=32)
+            eng.load_recognizer(self.state_dict())
+            self._engines[key] = (eng, self._weights_version)
+            return eng
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """text_recognizer.py:29-37: [B,3,32,W] -> [B,T,vocab] logits."""
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != 32:
+            raise ValueError("expected [B,3,32,W]")
+        eng = self.get_engine(int(x.shape[3]), device=x.device if x.is_cuda else None)
+        out = eng.crnn_forward(x.detach().float().cpu().numpy())
+        return torch.from_numpy(out).to(x.device)

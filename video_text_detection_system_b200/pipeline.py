@@ -1,0 +1,178 @@
+"""VideoTextPipeline with the reference's call surface (app/ml/inference/pipeliine.py:17-210).
+
+The reference runs batch-1 detection on a 4-thread pool and batch-1 recognition per crop in a Python loop
+(pipeliine.py:96-125).  Here a batch of frames is ONE vtd_run_batch call: preprocess, DBNet, fused head, box
+extraction, crop gather, CRNN and CTC decode all run on the device and only the packed detection records
+come back.  The result dictionaries are the reference's, field for field (plain Python scalars).
+"""
+from __future__ import annotations
+
+import asyncio
+import logging
+import time
+from concurrent.futures import ThreadPoolExecutor
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from ._lib import records_to_detections
+from .detector import TextDetector
+from .recognizer import TextRecognizer
+from .utils import ImageProcessor, VideoProcessor
+
+logger = logging.getLogger(__name__)
+
+
+class VideoTextPipeline:
+    def __init__(self, detector_path: Optional[str] = None, recognizer_path: Optional[str] = None,
+                 use_transformer_ocr: bool = True, confidence_threshold: float = 0.5, batch_size: int = 16,
+                 **engine_kwargs):
+        det_kw = {k: engine_kwargs[k] for k in ("backbone", "pretrained", "det_size", "dtype", "max_boxes",
+                                                "unclip_ratio") if k in engine_kwargs}
+        rec_kw = {k: engine_kwargs[k] for k in ("crop_w", "dtype") if k in engine_kwargs}
+        self.detector = TextDetector(detector_path, **det_kw)
+        self.recognizer = TextRecognizer(recognizer_path, use_transformer=use_transformer_ocr, **rec_kw)
+        self.video_processor = VideoProcessor()
+        self.image_processor = ImageProcessor()
+        self.confidence_threshold = confidence_threshold
+        self.batch_size = batch_size
+        self.executor = ThreadPoolExecutor(max_workers=4)
+        self._rec_version = None
+
+    # ---- fused batch path -----------------------------------------------------------------------------
+    def _patched(self) -> bool:
+        """True when a caller replaced detect/recognize/forward (the reference's tests do): fall back to
+        the reference's per-frame control flow so the replacements take effect."""
+        return ("detect" in vars(self.detector) or "recognize" in vars(self.recognizer)
+                or self.detector._forward_is_patched() or self.recognizer._forward_is_patched())
+
+    def _engine(self, src_h: int, src_w: int, n: int):
+        cap = max(int(self.batch_size), n, 1)
+        eng = self.detector._engine_for(src_h, src_w, max_batch=cap, crop_w=self.recognizer.crop_w)
+        if not eng.rec_loaded:
+            self.recognizer.model._check_supported()
+            eng.load_recognizer(self.recognizer.model.state_dict())
+        return eng
+
+    def detect_and_recognize(self, frames: List[np.ndarray]) -> List[List[Dict[str, Any]]]:
+        """One fused device pass over same-sized BGR frames -> per-frame text regions."""
+        if not frames:
+            return []
+        h, w = frames[0].shape[:2]
+        eng = self._engine(h, w, len(frames))
+        with self.detector._lock:
+            rec, cnt = eng.run_batch(frames, thr=self.confidence_threshold, recognize=True)
+        out = []
+        for i in range(len(frames)):
+            regions = []
+            for d in records_to_detections(rec[i], int(cnt[i]), with_text=True):
+                regions.append({"bbox": d["bbox"], "text": d["text"], "detection_confidence": d["confidence"],
+                                "recognition_confidence": d["recognition_confidence"], "polygon": d["polygon"]})
+            out.append(regions)
+        return out
+
+    # ---- reference surface ----------------------------------------------------------------------------
+    async def process_video(self, video_path: str, output_dir: str, progress_callback=None) -> Dict[str, Any]:
+        try:
+            start_time = time.time()
+            video_info = self.video_processor.get_video_info(video_path)
+            frames = self.video_processor.extract_frames_generator(video_path)
+            all_results: List[Dict] = []
+            frame_count = 0
+            total_frames = video_info.get("frame_count", 0)
+            batch_frames: List[np.ndarray] = []
+            batch_numbers: List[Tuple] = []
+            async for frame, frame_number, timestamp in frames:
+                batch_frames.append(frame)
+                batch_numbers.append((frame_number, timestamp))
+                if len(batch_frames) >= self.batch_size:
+                    all_results.extend(await self._process_frame_batch(batch_frames, batch_numbers, output_dir))
+                    frame_count += len(batch_frames)
+                    batch_frames.clear()
+                    batch_numbers.clear()
+                    if progress_callback:
+                        progress = frame_count / total_frames if total_frames > 0 else 0
+                        await progress_callback(progress, frame_count, total_frames)
+            if batch_frames:
+                all_results.extend(await self._process_frame_batch(batch_frames, batch_numbers, output_dir))
+                frame_count += len(batch_frames)
+            processing_time = time.time() - start_time
+            summary = self._generate_summary(all_results, processing_time, frame_count)
+            return {"status": "success", "results": all_results, "summary": summary, "video_info": video_info}
+        except Exception as e:
+            logger.error(f"Video processing failed: {e}")
+            return {"status": "failed", "error": str(e), "results": []}
+
+    async def _process_frame_batch(self, frames: List[np.ndarray], frame_info: List[Tuple], output_dir: str
+                                   ) -> List[Dict]:
+        loop = asyncio.get_event_loop()
+        same = all(isinstance(f, np.ndarray) and f.ndim == 3 and f.shape == frames[0].shape and f.dtype == np.uint8
+                   for f in frames)
+        if same and not self._patched():
+            per_frame = await loop.run_in_executor(self.executor, self.detect_and_recognize, list(frames))
+            return [{"frame_number": fn, "timestamp": ts, "detections": regions}
+                    for (fn, ts), regions in zip(frame_info, per_frame)]
+        # reference control flow (pipeliine.py:96-139): honours patched detect()/recognize()
+        tasks = [loop.run_in_executor(self.executor, self.detector.detect, f, self.confidence_threshold)
+                 for f in frames]
+        batch_detections = await asyncio.gather(*tasks)
+        results = []
+        for i, detections in enumerate(batch_detections):
+            frame_number, timestamp = frame_info[i]
+            frame = frames[i]
+            if not detections:
+                results.append({"frame_number": frame_number, "timestamp": timestamp, "detections": []})
+                continue
+            text_regions = []
+            for detection in detections:
+                x1, y1, x2, y2 = detection["bbox"]
+                crop = frame[y1:y2, x1:x2]
+                if crop.size == 0:
+                    continue
+                t = self.recognizer.recognize(crop)
+                text_regions.append({"bbox": detection["bbox"], "text": t["text"],
+                                     "detection_confidence": detection["confidence"],
+                                     "recognition_confidence": t["confidence"],
+                                     "polygon": detection.get("polygon", [])})
+            results.append({"frame_number": frame_number, "timestamp": timestamp, "detections": text_regions})
+        return results
+
+    def process_single_frame(self, frame: np.ndarray) -> Dict[str, Any]:
+        try:
+            if not self._patched() and isinstance(frame, np.ndarray) and frame.ndim == 3 and frame.dtype == np.uint8:
+                regions = self.detect_and_recognize([frame])[0]
+                # pipeliine.py:161-166: the single-frame path returns no 'polygon'
+                return {"detections": [{k: v for k, v in r.items() if k != "polygon"} for r in regions]}
+            detections = self.detector.detect(frame, self.confidence_threshold)
+            if not detections:
+                return {"detections": []}
+            text_regions = []
+            for detection in detections:
+                x1, y1, x2, y2 = detection["bbox"]
+                crop = frame[y1:y2, x1:x2]
+                if crop.size == 0:
+                    continue
+                t = self.recognizer.recognize(crop)
+                text_regions.append({"bbox": detection["bbox"], "text": t["text"],
+                                     "detection_confidence": detection["confidence"],
+                                     "recognition_confidence": t["confidence"]})
+            return {"detections": text_regions}
+        except Exception as e:
+            logger.error(f"Single frame processing failed: {e}")
+            return {"detections": [], "error": str(e)}
+
+    def _generate_summary(self, results: List[Dict], processing_time: float, frame_count: int) -> Dict[str, Any]:
+        dets = [d for fr in results for d in fr["detections"]]
+        total = len(dets)
+        texts = {d["text"].strip() for d in dets if d["text"].strip()}
+        return {
+            "total_frames": frame_count,
+            "frames_with_text": sum(1 for fr in results if fr["detections"]),
+            "total_detections": total,
+            "unique_texts": len(texts),
+            "detected_texts": list(texts),
+            "avg_detection_confidence": float(np.mean([d["detection_confidence"] for d in dets])) if total else 0.0,
+            "avg_recognition_confidence": float(np.mean([d["recognition_confidence"] for d in dets])) if total else 0.0,
+            "processing_time_seconds": processing_time,
+            "fps_processed": frame_count / processing_time if processing_time > 0 else 0,
+        }
