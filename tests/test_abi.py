@@ -1,0 +1,70 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/vtd.h declares; with no GPU
+every compute entry point fails loudly (there is no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "vtd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vtd_[a-z_0-9A-Z]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(lib_built):
+    from video_text_detection_system_b200 import _lib
+    assert sorted(_lib.exported_symbols()) == header_functions()
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+    lib = ctypes.CDLL(lib_built)
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    lib.vtd_abi_version.restype = ctypes.c_int
+    assert lib.vtd_abi_version() == 1
+
+
+def test_struct_layouts():
+    from video_text_detection_system_b200 import _lib
+    assert ctypes.sizeof(_lib.VtdRecord) == 128 == _lib.RECORD_DTYPE.itemsize
+    assert ctypes.sizeof(_lib.VtdConfig) == 4 * 16
+    for f in ("frame", "bbox", "polygon", "det_conf", "rec_conf", "len", "ids", "start_index"):
+        assert getattr(_lib.VtdRecord, f).offset == _lib.RECORD_DTYPE.fields[f][1]
+
+
+def test_built_for_sm100a_with_tcgen05_and_tma(lib_built):
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", lib_built], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):      # tcgen05.mma, TMA tensor load, tcgen05.ld
+        assert mnemonic in out, mnemonic
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_fails_loudly_without_gpu(lib_built):
+    from video_text_detection_system_b200 import _lib
+    with pytest.raises(_lib.VtdError) as ei:
+        _lib.Engine()
+    assert "no CPU fallback" in str(ei.value)
+    from video_text_detection_system_b200 import DBNet, TextDetector
+    with pytest.raises(_lib.VtdError):
+        DBNet("resnet18", pretrained=False)(torch.zeros(1, 3, 64, 64))
+    # the reference's never-raise convention at the detect() surface: [] plus a logged error
+    assert TextDetector(backbone="resnet18", pretrained=False).detect(np.zeros((64, 64, 3), np.uint8)) == []
+
+
+def test_bad_config_rejected(lib_built):
+    from video_text_detection_system_b200 import _lib
+    for kw in ({"backbone": 34}, {"det_h": 100}, {"crop_w": 130}, {"max_boxes": 5000}, {"max_batch": 0}):
+        with pytest.raises(_lib.VtdError):
+            _lib.Engine(**kw)

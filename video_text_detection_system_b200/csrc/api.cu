@@ -697,6 +697,12 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   cudaMemcpy(c->store_ptrs_dev, c->frame_ptrs_pinned, sizeof(void*) * B, cudaMemcpyHostToDevice);
   c->frame_ptrs_dev = c->store_ptrs_dev;
   cudaMemset(c->counts, 0, sizeof(int) * B);
+  {
+    Act a; a.p = c->pre; a.H = dh; a.W = dw; a.C = 4;
+    reg_dbg(c, "input", a);
+    Act k; k.p = c->crops; k.H = 32; k.W = cfg->crop_w; k.C = 4;
+    reg_dbg(c, "crops", k, false, true);
+  }
   *out = c;
   return VTD_OK;
 }
