@@ -10,6 +10,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 #include <string>
@@ -22,7 +23,7 @@ namespace {
 std::string g_create_error;
 std::mutex g_create_mutex;
 
-struct DebugEntry { const void* p; int C, H, W, Cstride; bool f32; bool per_crop; };
+struct DebugEntry { const void* p; int C, H, W; OutLayout lay; bool f32; bool per_crop; };
 
 struct Op {
   enum Kind { CONV, POOL } kind = CONV;
@@ -61,7 +62,12 @@ struct vtd_ctx {
   bool det_loaded = false, rec_loaded = false;
   std::vector<Op> det_prog, rec_prog;
   std::map<std::string, DebugEntry> dbg;
-  void* pre = nullptr;                  // [B,dh,dw,4]
+  bool use_win = false, use_tchead = false, use_tclstm = false;   // tcgen05 stems / head tail / LSTM (bf16 tier)
+  OutLayout pre_lay{}, crops_lay{};
+  TcPlan* head_plan = nullptr;
+  TcPlan* lstm_plan[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [layer][step parity]
+  bf16* h16 = nullptr;                  // [2 ping-pong][2 dirs][rc][256]
+  void* pre = nullptr;                  // [B,dh,dw,4]  (bf16 + use_win: zero-bordered [B,dh+6,dw+8,4])
   void* head_feat = nullptr;            // [B,dh/4,dw/4,128]
   HeadTailWeights htw{};
   float *prob = nullptr, *thresh = nullptr; uint8_t* mask = nullptr;
@@ -281,7 +287,10 @@ int run_prog(vtd_ctx* c, std::vector<Op>& prog, int n) {
 }
 
 void reg_dbg(vtd_ctx* c, const char* name, const Act& a, bool f32 = false, bool per_crop = false) {
-  c->dbg[name] = DebugEntry{a.p, a.C, a.H, a.W, a.C, f32, per_crop};
+  c->dbg[name] = DebugEntry{a.p, a.C, a.H, a.W, dense_layout(a.H, a.W, a.C), f32, per_crop};
+}
+void reg_dbg_lay(vtd_ctx* c, const char* name, const void* p, int C, int H, int W, OutLayout lay, bool per_crop) {
+  c->dbg[name] = DebugEntry{p, C, H, W, lay, false, per_crop};
 }
 
 // ---- Pillow resize coefficient tables (ImagingResample precompute_coeffs + normalize_coeffs_8bpc) ----
@@ -328,11 +337,34 @@ int build_detector(vtd_ctx* c, const SD& sd) {
   std::vector<Op>& P = c->det_prog;
   int r;
   Act x; x.p = c->pre; x.H = dh; x.W = dw; x.C = 4;
-  reg_dbg(c, "input", x);
   HostConv hc;
   if ((r = fold_conv(c, sd, "backbone.0", "backbone.1", 4, &hc))) return r;
   Act a;
-  if ((r = add_conv(c, &P, hc, B, x, 2, 3, true, nullptr, RES_NONE, false, &a))) return r;
+  if (c->use_win) {
+    if (hc.KH != 7 || hc.KW != 7 || hc.Cout != 64) FAIL(VTD_ERR_WEIGHT, "stem must be 7x7, 64 channels");
+    // window weights [64][7 rows][8 taps][4 ch]: tap 0 is the extra left pixel of the 16-byte aligned window
+    std::vector<float> ww((size_t)64 * 7 * 32, 0.f);
+    for (int o = 0; o < 64; ++o)
+      for (int rr = 0; rr < 7; ++rr)
+        for (int ss = 0; ss < 7; ++ss)
+          for (int ch = 0; ch < 4; ++ch)
+            ww[(((size_t)o * 7 + rr) * 8 + ss + 1) * 4 + ch] = hc.w[(((size_t)o * 7 + rr) * 7 + ss) * 4 + ch];
+    void* wdev = nullptr; float* bdev = nullptr; void* o = nullptr;
+    if ((r = upload_act_type(c, ww, &wdev)) || (r = upload_f32(c, hc.b, &bdev)) ||
+        (r = dev_alloc(c, &o, (size_t)B * (dh / 2) * (dw / 2) * 64 * c->esz)))
+      return r;
+    Op op;
+    op.kind = Op::CONV;
+    op.d.H = dh; op.d.W = dw; op.d.Cin = 4; op.d.Ho = dh / 2; op.d.Wo = dw / 2; op.d.Cout = 64; op.d.KH = op.d.KW = 7;
+    op.d.stride = 2; op.d.pad = 3; op.d.N = B;
+    std::string e;
+    op.plan = tc_plan_create_win(c->pre, B, dh + 6, dw + 8, 4, 2, 7, dh / 2, dw / 2, wdev, bdev, o, 1, &e);
+    if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 stem plan: %s (set VTD_NO_WIN=1 to use the CUDA-core stem)", e.c_str());
+    P.push_back(op);
+    a.p = o; a.H = dh / 2; a.W = dw / 2; a.C = 64;
+  } else {
+    if ((r = add_conv(c, &P, hc, B, x, 2, 3, true, nullptr, RES_NONE, false, &a))) return r;
+  }
   if ((r = add_pool(c, &P, B, a, 3, 3, 2, 2, 1, 1, &a))) return r;
   const bool r50 = c->cfg.backbone == 50;
   const int nblocks18[4] = {2, 2, 2, 2}, nblocks50[4] = {3, 4, 6, 3};
@@ -426,6 +458,14 @@ int build_detector(vtd_ctx* c, const SD& sd) {
       (r = upload_f32(c, b2, &db2)))
     return r;
   c->htw.w1 = dw1; c->htw.b1 = db1; c->htw.w2 = dw2; c->htw.b2 = db2;
+  if (c->use_tchead) {
+    void* w1b = nullptr;
+    if ((r = upload_act_type(c, w1, &w1b))) return r;
+    std::string e;
+    c->head_plan = tc_plan_create_dbhead(c->head_feat, B, dh / 4, dw / 4, w1b, b1.data(), w2.data(), b2.data(), c->prob,
+                                         c->thresh, c->mask, &e);
+    if (!c->head_plan) FAIL(VTD_ERR_CUDA, "tcgen05 head plan: %s", e.c_str());
+  }
   return VTD_OK;
 }
 
@@ -435,7 +475,6 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
   std::vector<Op>& P = c->rec_prog;
   int r;
   Act a; a.p = c->crops; a.H = 32; a.W = cw; a.C = 4;
-  reg_dbg(c, "crops", a, false, true);
   struct L { int conv, bn, k, pad; int pool; };   // pool: 0 none, 1 = 2x2 s2, 2 = (2,1) s(2,1)
   const L layers[7] = {{0, 1, 3, 1, 1}, {4, 5, 3, 1, 1}, {8, 9, 3, 1, 0}, {11, 12, 3, 1, 2},
                        {15, 16, 3, 1, 0}, {18, 19, 3, 1, 2}, {22, 23, 2, 0, 0}};
@@ -445,7 +484,31 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
                        i == 0 ? 4 : 0, &hc)))
       return r;
     if (hc.KH != layers[i].k) FAIL(VTD_ERR_WEIGHT, "cnn.%d has an unexpected kernel size", layers[i].conv);
-    if ((r = add_conv(c, &P, hc, B, a, 1, layers[i].pad, true, nullptr, RES_NONE, false, &a))) return r;
+    if (i == 0 && c->use_win) {
+      if (hc.Cout != 64) FAIL(VTD_ERR_WEIGHT, "cnn.0 must have 64 output channels");
+      // window weights [64][3 rows][4 taps][8 ch]: taps 0..2 are the filter columns, tap 3 and channels 3..7 are zero
+      std::vector<float> ww((size_t)64 * 3 * 32, 0.f);
+      for (int o = 0; o < 64; ++o)
+        for (int rr = 0; rr < 3; ++rr)
+          for (int ss = 0; ss < 3; ++ss)
+            for (int ch = 0; ch < 3; ++ch)
+              ww[(((size_t)o * 3 + rr) * 4 + ss) * 8 + ch] = hc.w[(((size_t)o * 3 + rr) * 3 + ss) * 4 + ch];
+      void* wdev = nullptr; float* bdev = nullptr; void* o = nullptr;
+      if ((r = upload_act_type(c, ww, &wdev)) || (r = upload_f32(c, hc.b, &bdev)) ||
+          (r = dev_alloc(c, &o, (size_t)B * 32 * cw * 64 * c->esz)))
+        return r;
+      Op op;
+      op.kind = Op::CONV;
+      op.d.H = 32; op.d.W = cw; op.d.Cin = 4; op.d.Ho = 32; op.d.Wo = cw; op.d.Cout = 64; op.d.KH = op.d.KW = 3;
+      op.d.stride = 1; op.d.pad = 1; op.d.N = B;
+      std::string e;
+      op.plan = tc_plan_create_win(c->crops, B, 34, cw + 4, 8, 1, 3, 32, cw, wdev, bdev, o, 1, &e);
+      if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 CRNN stem plan: %s (set VTD_NO_WIN=1 to use the CUDA-core stem)", e.c_str());
+      P.push_back(op);
+      a.p = o; a.H = 32; a.W = cw; a.C = 64;
+    } else {
+      if ((r = add_conv(c, &P, hc, B, a, 1, layers[i].pad, true, nullptr, RES_NONE, false, &a))) return r;
+    }
     if (layers[i].pool == 1) { if ((r = add_pool(c, &P, B, a, 2, 2, 2, 2, 0, 0, &a))) return r; }
     else if (layers[i].pool == 2) { if ((r = add_pool(c, &P, B, a, 2, 1, 2, 1, 0, 0, &a))) return r; }
   }
@@ -466,9 +529,16 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
       if (!wih || !wh || !bi || !bh || numel(wih) != 4 * H * 512 || numel(wh) != 4 * H * H || numel(bi) != 4 * H ||
           numel(bh) != 4 * H)
         FAIL(VTD_ERR_WEIGHT, "missing or mis-shaped LSTM tensors '%s'", sfx[d].c_str());
-      memcpy(&xp.w[(size_t)d * 4 * H * 512], wih->data, sizeof(float) * 4 * H * 512);
-      for (int i = 0; i < 4 * H; ++i) xp.b[d * 4 * H + i] = bi->data[i] + bh->data[i];
-      memcpy(&whh[(size_t)d * 4 * H * H], wh->data, sizeof(float) * 4 * H * H);
+      // row order of the gate dimension: PyTorch's (gate, unit), or -- for the tcgen05 recurrence -- (unit tile of
+      // 64, gate, unit in tile), so that one 256-column MMA tile holds i,f,g,o of the same 64 hidden units
+      for (int g = 0; g < 4; ++g)
+        for (int u = 0; u < H; ++u) {
+          const int src = g * H + u;
+          const int dst = c->use_tclstm ? (u / 64) * 256 + g * 64 + (u % 64) : src;
+          memcpy(&xp.w[((size_t)d * 4 * H + dst) * 512], wih->data + (size_t)src * 512, sizeof(float) * 512);
+          xp.b[d * 4 * H + dst] = bi->data[src] + bh->data[src];
+          memcpy(&whh[((size_t)d * 4 * H + dst) * H], wh->data + (size_t)src * H, sizeof(float) * H);
+        }
     }
     Act xo;
     if ((r = add_conv(c, nullptr, xp, B, in, 1, 0, false, nullptr, RES_NONE, true, &xo, &c->xproj_op[l]))) return r;
@@ -479,6 +549,17 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
     reg_dbg(c, l == 0 ? "rnn0" : "rnn1", in, false, true);
   }
   if ((r = dalloc(c, &c->hbuf, (size_t)2 * 2 * B * H * 4)) || (r = dalloc(c, &c->cbuf, (size_t)2 * B * H * 4))) return r;
+  if (c->use_tclstm) {
+    if ((r = dalloc(c, &c->h16, (size_t)2 * 2 * B * H * 2))) return r;
+    for (int l = 0; l < 2; ++l)
+      for (int pp = 0; pp < 2; ++pp) {
+        std::string e;
+        c->lstm_plan[l][pp] = tc_plan_create_lstm(c->h16 + (size_t)pp * 2 * B * H, c->h16 + (size_t)(pp ^ 1) * 2 * B * H, B,
+                                                  c->whh[l], (const float*)c->xproj_op[l].d.out, c->cbuf, c->rnn_out[l],
+                                                  c->T, &e);
+        if (!c->lstm_plan[l][pp]) FAIL(VTD_ERR_CUDA, "tcgen05 LSTM plan: %s", e.c_str());
+      }
+  }
   HostConv fc;
   {
     const vtd_tensor *w = sd.get("classifier.weight"), *b = sd.get("classifier.bias");
@@ -501,7 +582,11 @@ int run_crnn(vtd_ctx* c, int nc) {
     // the second layer's xproj reuses its own buffer (allocated by add_conv)
     { int r2 = run_op_prof(c, c->xproj_op[l], nc); if (r2) return r2; }
     const float* xp = (const float*)c->xproj_op[l].d.out;
-    if (c->bf16_mode)
+    if (c->use_tclstm) {
+      CK(cudaMemsetAsync(c->h16, 0, (size_t)2 * c->rc * 256 * 2, c->stream));          // h_0 = 0 (parity 0)
+      CK(cudaMemsetAsync(c->cbuf, 0, (size_t)2 * c->rc * 256 * 4, c->stream));         // c_0 = 0
+      for (int step = 0; step < c->T; ++step) CK(lstm_step_tcgen05(c->lstm_plan[l][step & 1], nc, step, c->stream, &c->lc));
+    } else if (c->bf16_mode)
       CK((bilstm_layer<bf16, bf16>(xp, (const bf16*)c->whh[l], (bf16*)c->rnn_out[l], c->hbuf, c->cbuf, nc, c->T, 256,
                                    c->stream, &c->lc)));
     else
@@ -515,7 +600,9 @@ int run_crnn(vtd_ctx* c, int nc) {
 int detect_maps_locked(vtd_ctx* c, int n, float thr, const float* logit_bias) {
   int r = run_prog(c, c->det_prog, n); if (r) return r;
   const int dh = c->cfg.det_h, dw = c->cfg.det_w;
-  if (c->bf16_mode)
+  if (c->head_plan)
+    CK(dbhead_tcgen05(c->head_plan, n, thr, logit_bias, c->stream, &c->lc));
+  else if (c->bf16_mode)
     CK(db_head_tail<bf16>((const bf16*)c->head_feat, c->htw, n, dh / 4, dw / 4, logit_bias, thr, c->prob, c->thresh,
                           c->mask, c->stream, &c->lc));
   else
@@ -560,10 +647,10 @@ int preprocess_locked(vtd_ctx* c, const uint8_t* const* frames, int n, int h, in
   }
   if (c->bf16_mode)
     CK(preprocess_frames<bf16>(c->frame_ptrs_dev, n, h, w, dev_pitch, pixfmt, c->tx, c->ty, nullptr, (bf16*)c->pre,
-                               c->stream, &c->lc));
+                               c->pre_lay, c->stream, &c->lc));
   else
     CK(preprocess_frames<float>(c->frame_ptrs_dev, n, h, w, dev_pitch, pixfmt, c->tx, c->ty, nullptr, (float*)c->pre,
-                                c->stream, &c->lc));
+                                c->pre_lay, c->stream, &c->lc));
   c->cur_h = h; c->cur_w = w; c->cur_pitch = dev_pitch; c->cur_n = n; c->cur_pix = pixfmt;
   return VTD_OK;
 }
@@ -587,10 +674,10 @@ int recognize_locked(vtd_ctx* c, int n) {
     const int nc = total - first < c->rc ? total - first : c->rc;
     if (c->bf16_mode)
       CK(crop_resize_records<bf16>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
-                                   c->cfg.max_boxes, first, nc, c->cfg.crop_w, (bf16*)c->crops, c->stream, &c->lc));
+                                   c->cfg.max_boxes, first, nc, c->cfg.crop_w, (bf16*)c->crops, c->crops_lay, c->stream, &c->lc));
     else
       CK(crop_resize_records<float>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
-                                    c->cfg.max_boxes, first, nc, c->cfg.crop_w, (float*)c->crops, c->stream, &c->lc));
+                                    c->cfg.max_boxes, first, nc, c->cfg.crop_w, (float*)c->crops, c->crops_lay, c->stream, &c->lc));
     int r = run_crnn(c, nc); if (r) return r;
     CK(ctc_into_records(c->logits, nc, first, c->T, 97, c->cfg.canonical_ctc, c->offsets, n, c->cfg.max_boxes,
                         c->records, c->stream, &c->lc));
@@ -658,6 +745,9 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   c->bf16_mode = cfg->dtype == VTD_BF16;
   c->esz = c->bf16_mode ? 2 : 4;
   c->T = cfg->crop_w / 4 - 1;
+  c->use_win = c->bf16_mode && !getenv("VTD_NO_WIN");
+  c->use_tchead = c->bf16_mode && !getenv("VTD_NO_TCHEAD");
+  c->use_tclstm = c->bf16_mode && !getenv("VTD_NO_TCLSTM");
   long long want = (long long)cfg->max_batch * cfg->max_boxes;
   c->rc = (int)(want < 1024 ? want : 1024);
   auto fail = [&](int code) { g_create_error = c->err; vtd_destroy(c); *out = nullptr; return code; };
@@ -671,11 +761,11 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   c->frame_bytes_cap = (((size_t)cfg->max_src_h * cfg->max_src_w * 3) + 255) & ~(size_t)255;
   if ((r = dalloc(c, &c->frames_store, c->frame_bytes_cap * B)) || (r = dalloc(c, &c->store_ptrs_dev, sizeof(void*) * B)) ||
       (r = dalloc(c, &c->ext_ptrs_dev, sizeof(void*) * B)) ||
-      (r = dev_alloc(c, &c->pre, (size_t)B * px * 4 * c->esz)) || (r = dalloc(c, &c->prob, (size_t)B * px * 4)) ||
+      (r = dev_alloc(c, &c->pre, (size_t)B * (c->use_win ? (size_t)(dh + 6) * (dw + 8) : px) * 4 * c->esz)) || (r = dalloc(c, &c->prob, (size_t)B * px * 4)) ||
       (r = dalloc(c, &c->thresh, (size_t)B * px * 4)) || (r = dalloc(c, &c->mask, (size_t)B * px)) ||
       (r = dalloc(c, &c->records, sizeof(vtd_record) * (size_t)B * cfg->max_boxes)) ||
       (r = dalloc(c, &c->counts, sizeof(int) * B)) || (r = dalloc(c, &c->offsets, sizeof(int) * (B + 1))) ||
-      (r = dev_alloc(c, &c->crops, (size_t)c->rc * 32 * cfg->crop_w * 4 * c->esz)) ||
+      (r = dev_alloc(c, &c->crops, (size_t)c->rc * (c->use_win ? (size_t)34 * (cfg->crop_w + 4) * 8 : (size_t)32 * cfg->crop_w * 4) * c->esz)) ||
       (r = dalloc(c, &c->ids_dev, (size_t)c->rc * VTD_IDS_STRIDE)) || (r = dalloc(c, &c->len_dev, (size_t)c->rc * 4)) ||
       (r = dalloc(c, &c->conf_dev, (size_t)c->rc * 4)) || (r = dalloc(c, &c->list_ptrs, sizeof(void*) * c->rc)) ||
       (r = dalloc(c, &c->list_meta, sizeof(int) * 3 * c->rc)))
@@ -697,12 +787,17 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   cudaMemcpy(c->store_ptrs_dev, c->frame_ptrs_pinned, sizeof(void*) * B, cudaMemcpyHostToDevice);
   c->frame_ptrs_dev = c->store_ptrs_dev;
   cudaMemset(c->counts, 0, sizeof(int) * B);
-  {
-    Act a; a.p = c->pre; a.H = dh; a.W = dw; a.C = 4;
-    reg_dbg(c, "input", a);
-    Act k; k.p = c->crops; k.H = 32; k.W = cfg->crop_w; k.C = 4;
-    reg_dbg(c, "crops", k, false, true);
+  if (c->use_win) {   // zero-bordered stem inputs: 4 px left/right + 3 rows top/bottom (7x7 s2), 1 px + 1 row (3x3)
+    c->pre_lay = padded_layout(dh, dw, 4, 3, 3, 4, 4);
+    c->crops_lay = padded_layout(32, cfg->crop_w, 8, 1, 1, 1, 3);
+    cudaMemset(c->pre, 0, (size_t)B * (dh + 6) * (dw + 8) * 4 * c->esz);
+    cudaMemset(c->crops, 0, (size_t)c->rc * 34 * (cfg->crop_w + 4) * 8 * c->esz);
+  } else {
+    c->pre_lay = dense_layout(dh, dw, 4);
+    c->crops_lay = dense_layout(32, cfg->crop_w, 4);
   }
+  reg_dbg_lay(c, "input", c->pre, 4, dh, dw, c->pre_lay, false);
+  reg_dbg_lay(c, "crops", c->crops, 4, 32, cfg->crop_w, c->crops_lay, true);
   *out = c;
   return VTD_OK;
 }
@@ -715,6 +810,8 @@ void vtd_destroy(vtd_ctx* c) {
   for (Op& op : c->rec_prog) if (op.plan) tc_plan_destroy(op.plan);
   for (int l = 0; l < 2; ++l) if (c->xproj_op[l].plan) tc_plan_destroy(c->xproj_op[l].plan);
   if (c->fc_op.plan) tc_plan_destroy(c->fc_op.plan);
+  if (c->head_plan) tc_plan_destroy(c->head_plan);
+  for (int l = 0; l < 2; ++l) for (int pp = 0; pp < 2; ++pp) if (c->lstm_plan[l][pp]) tc_plan_destroy(c->lstm_plan[l][pp]);
   for (void* p : c->allocs) cudaFree(p);
   for (ResizeTab* t : {&c->tx, &c->ty}) if (t->lo) { cudaFree(t->lo); cudaFree(t->cnt); cudaFree(t->kk); }
   if (c->pp_work) { cudaFree(c->pp_work); cudaFree(c->pp_prob); cudaFree(c->pp_mask); cudaFree(c->pp_records); cudaFree(c->pp_counts); }
@@ -818,8 +915,8 @@ int vtd_dbnet_forward(vtd_ctx* c, const float* x, int n, float* ph, float* th) {
   for (int i0 = 0; i0 < n; i0 += B) {
     const int m = n - i0 < B ? n - i0 : B;
     CK(cudaMemcpyAsync(c->stage_f32, x + (size_t)i0 * 3 * px, (size_t)m * 3 * px * 4, cudaMemcpyHostToDevice, c->stream));
-    if (c->bf16_mode) CK(nchw_f32_to_nhwc<bf16>(c->stage_f32, (bf16*)c->pre, m, 3, dh, dw, 4, c->stream, &c->lc));
-    else CK(nchw_f32_to_nhwc<float>(c->stage_f32, (float*)c->pre, m, 3, dh, dw, 4, c->stream, &c->lc));
+    if (c->bf16_mode) CK(nchw_f32_to_nhwc<bf16>(c->stage_f32, (bf16*)c->pre, m, 3, dh, dw, c->pre_lay, c->stream, &c->lc));
+    else CK(nchw_f32_to_nhwc<float>(c->stage_f32, (float*)c->pre, m, 3, dh, dw, c->pre_lay, c->stream, &c->lc));
     int r = detect_maps_locked(c, m, 0.5f, nullptr); if (r) return r;
     if (ph) CK(cudaMemcpyAsync(ph + (size_t)i0 * px, c->prob, (size_t)m * px * 4, cudaMemcpyDeviceToHost, c->stream));
     if (th) CK(cudaMemcpyAsync(th + (size_t)i0 * px, c->thresh, (size_t)m * px * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -918,10 +1015,10 @@ int vtd_recognize_crops(vtd_ctx* c, const uint8_t* const* crops, const int* h, c
     CK(cudaMemcpyAsync(c->list_meta, meta.data(), sizeof(int) * 3 * c->rc, cudaMemcpyHostToDevice, c->stream));
     if (c->bf16_mode)
       CK(crop_resize_list<bf16>(c->list_ptrs, c->list_meta, c->list_meta + c->rc, c->list_meta + 2 * c->rc, nc,
-                                c->cfg.crop_w, (bf16*)c->crops, c->stream, &c->lc));
+                                c->cfg.crop_w, (bf16*)c->crops, c->crops_lay, c->stream, &c->lc));
     else
       CK(crop_resize_list<float>(c->list_ptrs, c->list_meta, c->list_meta + c->rc, c->list_meta + 2 * c->rc, nc,
-                                 c->cfg.crop_w, (float*)c->crops, c->stream, &c->lc));
+                                 c->cfg.crop_w, (float*)c->crops, c->crops_lay, c->stream, &c->lc));
     int r = run_crnn(c, nc); if (r) return r;
     CK(ctc_greedy(c->logits, nc, T, 97, 0, c->cfg.canonical_ctc, c->ids_dev, VTD_IDS_STRIDE, c->len_dev, c->conf_dev,
                   c->stream, &c->lc));
@@ -950,8 +1047,8 @@ int vtd_crnn_forward(vtd_ctx* c, const float* x, int n, float* logits_host) {
   for (int first = 0; first < n; first += c->rc) {
     const int nc = n - first < c->rc ? n - first : c->rc;
     CK(cudaMemcpyAsync(c->stage_f32, x + (size_t)first * per, (size_t)nc * per * 4, cudaMemcpyHostToDevice, c->stream));
-    if (c->bf16_mode) CK(nchw_f32_to_nhwc<bf16>(c->stage_f32, (bf16*)c->crops, nc, 3, 32, cw, 4, c->stream, &c->lc));
-    else CK(nchw_f32_to_nhwc<float>(c->stage_f32, (float*)c->crops, nc, 3, 32, cw, 4, c->stream, &c->lc));
+    if (c->bf16_mode) CK(nchw_f32_to_nhwc<bf16>(c->stage_f32, (bf16*)c->crops, nc, 3, 32, cw, c->crops_lay, c->stream, &c->lc));
+    else CK(nchw_f32_to_nhwc<float>(c->stage_f32, (float*)c->crops, nc, 3, 32, cw, c->crops_lay, c->stream, &c->lc));
     int r = run_crnn(c, nc); if (r) return r;
     CK(cudaMemcpyAsync(logits_host + (size_t)first * T * 97, c->logits, (size_t)nc * T * 97 * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1070,8 +1167,8 @@ int vtd_debug_tensor(vtd_ctx* c, const char* name, int n, float* host_out, int64
   float* tmp = nullptr;
   CK(cudaMalloc(&tmp, ne * 4));
   cudaError_t e;
-  if (d.f32 || !c->bf16_mode) e = nhwc_to_nchw_f32<float>((const float*)d.p, tmp, n, C, d.H, d.W, d.Cstride, c->stream, &c->lc);
-  else e = nhwc_to_nchw_f32<bf16>((const bf16*)d.p, tmp, n, C, d.H, d.W, d.Cstride, c->stream, &c->lc);
+  if (d.f32 || !c->bf16_mode) e = nhwc_to_nchw_f32<float>((const float*)d.p, tmp, n, C, d.H, d.W, d.lay, c->stream, &c->lc);
+  else e = nhwc_to_nchw_f32<bf16>((const bf16*)d.p, tmp, n, C, d.H, d.W, d.lay, c->stream, &c->lc);
   if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, tmp, ne * 4, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(tmp);

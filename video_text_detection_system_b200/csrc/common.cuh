@@ -40,6 +40,15 @@ template <typename T> cudaError_t conv_generic(const ConvDesc& d, cudaStream_t s
 // tensor-core path (bf16, Cin%64==0, Cout%64==0, stride 1|2); returns cudaErrorNotSupported if shape unsupported
 struct TcPlan;   // opaque: tensor maps + launch geometry, built once per layer
 TcPlan* tc_plan_create(const ConvDesc& d, std::string* err);
+TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int stride, int nr, int Ho, int Wo,
+                           const void* w, const float* bias, void* out, int relu, std::string* err);
+TcPlan* tc_plan_create_dbhead(const void* feat, int N, int H4, int W4, const void* w1, const float* b1_host,
+                              const float* w2_host, const float* b2_host, float* prob, float* thresh, uint8_t* mask,
+                              std::string* err);
+TcPlan* tc_plan_create_lstm(const void* h_prev, void* h_next, int Bcap, const void* whh, const float* xproj, float* cbuf,
+                            void* seq_out, int T, std::string* err);
+cudaError_t dbhead_tcgen05(TcPlan* pl, int n, float thr, const float* logit_bias, cudaStream_t s, LaunchCounter* lc);
+cudaError_t lstm_step_tcgen05(const TcPlan* pl, int B, int step, cudaStream_t s, LaunchCounter* lc);
 void tc_plan_destroy(TcPlan*);
 cudaError_t conv_tcgen05(const TcPlan* p, int n_actual, cudaStream_t s, LaunchCounter* lc);
 bool tc_supported(const ConvDesc& d);
@@ -56,10 +65,18 @@ struct ResizeTab {           // Pillow coefficient tables for one axis, device m
   int* cnt = nullptr;        // [out]
   int* kk = nullptr;         // [out][ksize]
 };
+// Placement of an NHWC image batch inside a (possibly zero-bordered) buffer, all in elements:
+// element (n,y,x,c) lives at offset + n*img_pitch + y*row_pitch + x*cpp + c.
+struct OutLayout { long long offset, img_pitch, row_pitch; int cpp; };
+inline OutLayout dense_layout(int H, int W, int cpp) { return OutLayout{0, (long long)H * W * cpp, (long long)W * cpp, cpp}; }
+inline OutLayout padded_layout(int H, int W, int cpp, int pt, int pb, int pl, int pr) {
+  const long long row = (long long)(W + pl + pr) * cpp;
+  return OutLayout{pt * row + (long long)pl * cpp, row * (H + pt + pb), row, cpp};
+}
 template <typename T>
 cudaError_t preprocess_frames(const uint8_t* const* frames_dev /*device array of n pointers*/, int n, int h, int w,
                               int pitch, int pixfmt, const ResizeTab& tx, const ResizeTab& ty, uint8_t* tmp_u8,
-                              T* out /*[n,dh,dw,4]*/, cudaStream_t s, LaunchCounter* lc);
+                              T* out /*4 channels per pixel*/, OutLayout lay, cudaStream_t s, LaunchCounter* lc);
 
 // ---- fused DB head tail ----------------------------------------------------------------------------
 struct HeadTailWeights {     // both branches; fp32
@@ -99,10 +116,10 @@ cudaError_t scan_counts(const int* counts, int n, int* offsets /*[n+1]*/, cudaSt
 template <typename T>
 cudaError_t crop_resize_records(const uint8_t* const* frames_dev, int src_h, int src_w, int pitch,
                                 const void* records, const int* offsets, int n, int kmax, int first_crop,
-                                int n_crops, int crop_w, T* out, cudaStream_t s, LaunchCounter* lc);
+                                int n_crops, int crop_w, T* out, OutLayout lay, cudaStream_t s, LaunchCounter* lc);
 template <typename T>
 cudaError_t crop_resize_list(const uint8_t* const* crops_dev, const int* h, const int* w, const int* pitch,
-                             int n_crops, int crop_w, T* out, cudaStream_t s, LaunchCounter* lc);
+                             int n_crops, int crop_w, T* out, OutLayout lay, cudaStream_t s, LaunchCounter* lc);
 
 // ---- LSTM ------------------------------------------------------------------------------------------------
 // One layer, both directions. xproj: [B,T,2,4H] fp32 (= W_ih x + b_ih + b_hh, gate order i,f,g,o);
@@ -120,10 +137,10 @@ cudaError_t ctc_into_records(const float* logits, int n_crops, int first_crop, i
 
 // ---- layout helpers ----------------------------------------------------------------------------------------
 template <typename T>
-cudaError_t nchw_f32_to_nhwc(const float* in, T* out, int N, int C, int H, int W, int Cpad, cudaStream_t s,
+cudaError_t nchw_f32_to_nhwc(const float* in, T* out, int N, int C, int H, int W, OutLayout lay, cudaStream_t s,
                              LaunchCounter* lc);
 template <typename T>
-cudaError_t nhwc_to_nchw_f32(const T* in, float* out, int N, int C, int H, int W, int Cstride, cudaStream_t s,
+cudaError_t nhwc_to_nchw_f32(const T* in, float* out, int N, int C, int H, int W, OutLayout lay, cudaStream_t s,
                              LaunchCounter* lc);
 
 }  // namespace vtd

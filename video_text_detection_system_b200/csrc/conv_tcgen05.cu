@@ -21,6 +21,22 @@
 //   warps 2..5    : epilogue: tcgen05.ld 32 lanes x 32 columns -> +bias (folded BN) -> +residual (same size,
 //                   or nearest-2x upsampled = the FPN top-down add) -> ReLU -> bf16 (or fp32) NHWC store.
 // Every mbarrier wait is bounded (clock64) and traps instead of hanging the GPU.
+//
+// The same warp-specialised skeleton runs four modes (template parameter MODE):
+//   MODE_CONV   : the implicit-GEMM convolution described above.
+//   MODE_WIN    : 3-channel stems (DBNet 7x7 s2, CRNN 3x3): activations live in a zero-bordered buffer with 4 or 8
+//                 channels per pixel, and one K step is a whole filter ROW: a 5-D tensor map whose ox dimension has a
+//                 16-byte stride (overlapping 64-byte windows = 8 or 4 consecutive pixels) delivers, per output
+//                 pixel, the 32 bf16 that one filter row touches; 64B swizzle, K = rows x 32 (zero weights pad it).
+//   MODE_DBHEAD : the DB head tail (text_detector.py:61-81 after the 3x3): per branch ConvT(64->64,k2,s2)+BN+ReLU is a
+//                 [pixels x 64] x [64 x 256] GEMM (256 = 2x2 positions x 64 ch); its epilogue applies ReLU, the second
+//                 ConvT (64->1, k2, s2: four 64-long dot products per position, weights in the constant bank),
+//                 the optional logit bias, sigmoid and `> thr`, and writes the 4x4 output block of the pixel:
+//                 probability, threshold and mask leave in one pass, no intermediate map exists.
+//   MODE_LSTM   : one timestep of a BiLSTM layer for both directions: gates = h_{t-1} W_hh^T as a GEMM with rows of
+//                 W_hh permuted so that a 256-column tile holds i,f,g,o of 64 hidden units; the epilogue adds the
+//                 input projection, applies the cell update and writes h (bf16, next step's A operand), c and the
+//                 layer output.
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
@@ -31,14 +47,14 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // bf16 elements = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 
 struct alignas(64) TcMaps {
   CUtensorMap a[4];     // activation maps; [0] only for stride 1, [py*2+px] for stride 2
   CUtensorMap b;        // weights
 };
+
+enum { MODE_CONV = 0, MODE_WIN = 1, MODE_DBHEAD = 2, MODE_LSTM = 3 };
 
 struct TcParams {
   int N, Ho, Wo, Cout, Cin;
@@ -50,7 +66,25 @@ struct TcParams {
   const float* bias;
   const bf16* res;
   void* out;
+  // MODE_WIN
+  int nr, sdiv;               // filter rows (= K steps), row phases (= conv stride)
+  // MODE_DBHEAD
+  const float* logit_bias; float* prob; float* thresh; uint8_t* mask;
+  // MODE_LSTM
+  const float* xproj; float* cbuf; bf16* h_next; bf16* seq_out;
+  int lstm_T, lstm_step, lstm_B, lstm_Bcap;
 };
+
+struct HeadConsts {            // DB head tail constants, passed in the kernel parameter (constant) bank
+  float b1[2][256];            // [head][(dy,dx,c)]  folded BN shift of ConvT1
+  float w2[2][64][4];          // [head][c][(dy2,dx2)]
+  float b2[2];
+  float thr;
+  float pad_;
+};
+struct NoExtra { int unused; };
+template <int MODE> struct ExtraOf { typedef NoExtra type; };
+template <> struct ExtraOf<MODE_DBHEAD> { typedef HeadConsts type; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -88,6 +122,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -95,14 +136,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart.
+// K-major swizzled shared-memory matrix descriptor: rows of ROWB (128 or 64) bytes, 8-row atoms 8*ROWB apart.
+template <int ROWB>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);      // start address, 16-byte units
   d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row atoms
+  d |= (uint64_t)((8 * ROWB) >> 4) << 32;       // stride byte offset between 8-row atoms
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  d |= (uint64_t)(ROWB == 128 ? 2 : 4) << 61;   // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
@@ -136,21 +178,204 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 
-template <int BLOCK_N>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+template <int BLOCK_N, int MODE>
 struct TcCfg {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int ROWB = MODE == MODE_WIN ? 64 : 128;           // bytes of K per smem row
+  static constexpr int A_BYTES = BLOCK_M * ROWB;
+  static constexpr int B_STAGE_BYTES = BLOCK_N * ROWB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = MODE == MODE_WIN ? 12 : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+
+// ---- epilogues ---------------------------------------------------------------------------------------------
+
+// MODE_CONV / MODE_WIN: bias + residual + ReLU -> NHWC bf16 / fp32
 template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_acc, int q, bool valid, size_t opix,
+                                              size_t rpix, int nb) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (valid) {
+      const int co = nb * BLOCK_N + c0;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
+          f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+        }
+      }
+      if (p.res_mode != RES_NONE) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + co);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u = __ldg(rp + j);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 r2 = __bfloat1622float2(h[e]);
+            f[j * 8 + e * 2] += r2.x; f[j * 8 + e * 2 + 1] += r2.y;
+          }
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (p.out_f32) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.Cout + co);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.Cout + co);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 u;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+          u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+          u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+          op[j] = u;
+        }
+      }
+    }
+  }
+}
+
+// MODE_DBHEAD: ReLU(ConvT1) -> ConvT2 -> (+logit bias) -> sigmoid -> 4x4 block of prob / thresh (+ mask)
+template <int HEAD>
+__device__ __forceinline__ void epilogue_dbhead(const TcParams& p, const HeadConsts& ex, uint32_t tmem_acc, int q,
+                                                bool valid, int n, int oy, int ox) {
+  float o[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) o[k] = ex.b2[HEAD];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {                     // (dy,dx) position of the first transposed conv
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + half * 32), v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = half * 32 + j;
+        const float h = fmaxf(__uint_as_float(v[j]) + ex.b1[HEAD][g * 64 + c], 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[g * 4 + k] = fmaf(h, ex.w2[HEAD][c][k], o[g * 4 + k]);
+      }
+    }
+  }
+  if (!valid) return;
+  const int Wd = 4 * p.Wo, Hd = 4 * p.Ho;
+  float* __restrict__ outp = HEAD == 0 ? p.prob : p.thresh;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int dy = r >> 1, dy2 = r & 1;
+    float v0 = o[(dy * 2 + 0) * 4 + dy2 * 2 + 0], v1 = o[(dy * 2 + 0) * 4 + dy2 * 2 + 1];
+    float v2 = o[(dy * 2 + 1) * 4 + dy2 * 2 + 0], v3 = o[(dy * 2 + 1) * 4 + dy2 * 2 + 1];
+    const size_t oidx = ((size_t)n * Hd + 4 * oy + r) * Wd + 4 * ox;
+    if (HEAD == 0 && p.logit_bias) {
+      float4 lb = __ldg(reinterpret_cast<const float4*>(p.logit_bias + oidx));
+      v0 += lb.x; v1 += lb.y; v2 += lb.z; v3 += lb.w;
+    }
+    v0 = 1.0f / (1.0f + expf(-v0)); v1 = 1.0f / (1.0f + expf(-v1));
+    v2 = 1.0f / (1.0f + expf(-v2)); v3 = 1.0f / (1.0f + expf(-v3));
+    *reinterpret_cast<float4*>(outp + oidx) = make_float4(v0, v1, v2, v3);
+    if (HEAD == 0) {
+      const float thr = ex.thr;
+      uint32_t m = (v0 > thr ? 1u : 0u) | (v1 > thr ? 0x100u : 0u) | (v2 > thr ? 0x10000u : 0u) |
+                   (v3 > thr ? 0x1000000u : 0u);
+      *reinterpret_cast<uint32_t*>(p.mask + oidx) = m;
+    }
+  }
+}
+
+// MODE_LSTM: gates -> cell update.  Tile columns = [i(64) | f(64) | g(64) | o(64)] of hidden units jt*64..+63.
+__device__ __forceinline__ void epilogue_lstm(const TcParams& p, uint32_t tmem_acc, int q, int b, int nb) {
+  const int dir = nb >> 2, jt = nb & 3;
+  const bool valid = b < p.lstm_B;
+  const int t = dir == 0 ? p.lstm_step : p.lstm_T - 1 - p.lstm_step;
+  const int bb = valid ? b : 0;
+  const float* __restrict__ xp = p.xproj + (((size_t)bb * p.lstm_T + t) * 2 + dir) * 1024 + jt * 256;
+  float* __restrict__ cs = p.cbuf + ((size_t)dir * p.lstm_Bcap + bb) * 256 + jt * 64;
+  bf16* __restrict__ hn = p.h_next + ((size_t)dir * p.lstm_Bcap + bb) * 256 + jt * 64;
+  bf16* __restrict__ so = p.seq_out + ((size_t)bb * p.lstm_T + t) * 512 + dir * 256 + jt * 64;
+#pragma unroll 1
+  for (int qq = 0; qq < 4; ++qq) {                  // 16 hidden units at a time
+    uint32_t vi[16], vf[16], vg[16], vo[16];
+    const uint32_t base = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(qq * 16);
+    tmem_ld16(base, vi); tmem_ld16(base + 64, vf); tmem_ld16(base + 128, vg); tmem_ld16(base + 192, vo);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (valid) {
+      float hv[16];
+#pragma unroll
+      for (int u4 = 0; u4 < 16; u4 += 4) {
+        const int u = qq * 16 + u4;
+        float4 xi = __ldg(reinterpret_cast<const float4*>(xp + u));
+        float4 xf = __ldg(reinterpret_cast<const float4*>(xp + 64 + u));
+        float4 xg = __ldg(reinterpret_cast<const float4*>(xp + 128 + u));
+        float4 xo = __ldg(reinterpret_cast<const float4*>(xp + 192 + u));
+        float4 c4 = *reinterpret_cast<const float4*>(cs + u);
+        const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
+        const float xgv[4] = {xg.x, xg.y, xg.z, xg.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+        float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float gi = __uint_as_float(vi[u4 + e]) + xiv[e], gf = __uint_as_float(vf[u4 + e]) + xfv[e];
+          float gg = __uint_as_float(vg[u4 + e]) + xgv[e], go = __uint_as_float(vo[u4 + e]) + xov[e];
+          float cn = fast_sigmoid(gf) * cv[e] + fast_sigmoid(gi) * fast_tanh(gg);
+          cv[e] = cn;
+          hv[u4 + e] = fast_sigmoid(go) * fast_tanh(cn);
+        }
+        *reinterpret_cast<float4*>(cs + u) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+      }
+      uint4 w0, w1;
+      __nv_bfloat162 h2[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h2[e] = __floats2bfloat162_rn(hv[2 * e], hv[2 * e + 1]);
+      w0.x = *reinterpret_cast<uint32_t*>(&h2[0]); w0.y = *reinterpret_cast<uint32_t*>(&h2[1]);
+      w0.z = *reinterpret_cast<uint32_t*>(&h2[2]); w0.w = *reinterpret_cast<uint32_t*>(&h2[3]);
+      w1.x = *reinterpret_cast<uint32_t*>(&h2[4]); w1.y = *reinterpret_cast<uint32_t*>(&h2[5]);
+      w1.z = *reinterpret_cast<uint32_t*>(&h2[6]); w1.w = *reinterpret_cast<uint32_t*>(&h2[7]);
+      uint4* hp = reinterpret_cast<uint4*>(hn + qq * 16);
+      hp[0] = w0; hp[1] = w1;
+      uint4* sp = reinterpret_cast<uint4*>(so + qq * 16);
+      sp[0] = w0; sp[1] = w1;
+    }
+  }
+}
+
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
+               const __grid_constant__ typename ExtraOf<MODE>::type ex) {
+  using Cfg = TcCfg<BLOCK_N, MODE>;
+  constexpr int ROWB = Cfg::ROWB;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte aligned operand ring (SWIZZLE_128B atoms), barriers after it
+  // 1024-byte aligned operand ring (swizzle atoms), barriers after it
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t ring = (raw + 1023u) & ~1023u;
   uint8_t* ring_ptr = smem_raw + (ring - raw);
@@ -184,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const int BW = 1 << p.lw, BH = 1 << p.lh;
   const int BNt = BLOCK_M >> (p.lw + p.lh);
   const int kchunks = p.Cin / BLOCK_K;
-  const int ksteps = p.KH * p.KW * kchunks;
+  const int ksteps = MODE == MODE_WIN ? p.nr : p.KH * p.KW * kchunks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -196,25 +421,38 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
         const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
         const int x0 = tx * BW, y0 = ty * BH, n0 = (int)t * BNt;
-        for (int r = 0; r < p.KH; ++r) {
-          for (int s = 0; s < p.KW; ++s) {
-            int mi = 0, xo, yo;
-            if (p.stride == 1) { xo = s - p.pad; yo = r - p.pad; }
-            else {
-              const int tyy = r - p.pad, txx = s - p.pad;
-              const int py = tyy & 1, px = txx & 1;
-              mi = py * 2 + px; yo = (tyy - py) / 2; xo = (txx - px) / 2;
-            }
-            const int kbase = (r * p.KW + s) * p.Cin;
-            for (int kc = 0; kc < kchunks; ++kc) {
-              mbar_wait(empty0 + 8 * stage, phase ^ 1);
-              const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
-              const uint32_t sb = sa + A_STAGE_BYTES;
-              const uint32_t fb = full0 + 8 * stage;
-              mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-              tma_load_4d(sa, &maps.a[mi], fb, kc * BLOCK_K, x0 + xo, y0 + yo, n0);
-              tma_load_2d(sb, &maps.b, fb, kbase + kc * BLOCK_K, nb * BLOCK_N);
-              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (MODE == MODE_WIN) {
+          for (int r = 0; r < p.nr; ++r) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+            tma_load_5d(sa, &maps.a[0], fb, 0, x0, r % p.sdiv, y0 + r / p.sdiv, n0);
+            tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, r * 32, nb * BLOCK_N);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          for (int r = 0; r < p.KH; ++r) {
+            for (int s = 0; s < p.KW; ++s) {
+              int mi = 0, xo, yo, coff = 0;
+              if (MODE == MODE_DBHEAD) { xo = yo = 0; coff = nb * 64; }
+              else if (MODE == MODE_LSTM) { xo = yo = 0; mi = nb >> 2; }
+              else if (p.stride == 1) { xo = s - p.pad; yo = r - p.pad; }
+              else {
+                const int tyy = r - p.pad, txx = s - p.pad;
+                const int py = tyy & 1, px = txx & 1;
+                mi = py * 2 + px; yo = (tyy - py) / 2; xo = (txx - px) / 2;
+              }
+              const int kbase = (r * p.KW + s) * p.Cin;
+              for (int kc = 0; kc < kchunks; ++kc) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
+                const uint32_t fb = full0 + 8 * stage;
+                mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+                tma_load_4d(sa, &maps.a[mi], fb, coff + kc * BLOCK_K, x0 + xo, y0 + yo, n0);
+                tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, kbase + kc * BLOCK_K, nb * BLOCK_N);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+              }
             }
           }
         }
@@ -235,9 +473,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           mbar_wait(full0 + 8 * stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
-          const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + A_STAGE_BYTES);
+          const uint64_t ad = umma_desc<ROWB>(sa), bd = umma_desc<ROWB>(sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          for (int k = 0; k < ROWB / 32; ++k)
             umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ks | k) ? 1u : 0u);
           umma_commit(empty0 + 8 * stage);              // frees the slot when these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -261,63 +499,18 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const int as = (int)(it & 1);
       mbar_wait(tfull0 + 8 * as, (uint32_t)((it >> 1) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
-      size_t rpix = 0;
-      if (p.res_mode == RES_SAME) rpix = opix;
-      else if (p.res_mode == RES_UP2) rpix = ((size_t)n * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (valid) {
-          const int co = nb * BLOCK_N + c0;
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
-          }
-          if (p.res_mode != RES_NONE) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + co);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u = __ldg(rp + j);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 r2 = __bfloat1622float2(h[e]);
-                f[j * 8 + e * 2] += r2.x; f[j * 8 + e * 2 + 1] += r2.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.Cout + co);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.Cout + co);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-              op[j] = u;
-            }
-          }
-        }
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
+      if constexpr (MODE == MODE_DBHEAD) {
+        if (nb == 0) epilogue_dbhead<0>(p, ex, tmem_acc, q, valid, n, oy, ox);
+        else epilogue_dbhead<1>(p, ex, tmem_acc, q, valid, n, oy, ox);
+      } else if constexpr (MODE == MODE_LSTM) {
+        epilogue_lstm(p, tmem_acc, q, ox, nb);
+      } else {
+        const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
+        size_t rpix = 0;
+        if (p.res_mode == RES_SAME) rpix = opix;
+        else if (p.res_mode == RES_UP2) rpix = ((size_t)n * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
+        epilogue_conv<BLOCK_N>(p, tmem_acc, q, valid, opix, rpix, nb);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -355,15 +548,57 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// tile shape: BN x BH x BW = 128, all powers of two, least padding; ties prefer wider rows
+void pick_tile(int N, int Ho, int Wo, int* lw_out, int* lh_out) {
+  int best_lw = 0, best_lh = 0; long long best = -1;
+  for (int lw = 0; lw <= 7; ++lw)
+    for (int lh = 0; lw + lh <= 7; ++lh) {
+      const int bw = 1 << lw, bh = 1 << lh, bnn = 128 >> (lw + lh);
+      long long tiles = (long long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((N + bnn - 1) / bnn);
+      if (best < 0 || tiles < best || (tiles == best && lw > best_lw)) { best = tiles; best_lw = lw; best_lh = lh; }
+    }
+  *lw_out = best_lw; *lh_out = best_lh;
+}
+
+CUresult encode_weights(EncodeTiledFn enc, CUtensorMap* m, const void* w, long long K, int Cout, int box_k, int box_n,
+                        CUtensorMapSwizzle sw) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_n};
+  cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+CUresult encode_act4d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int C, int W, int H, int N,
+                      long long sW, long long sH, long long sN /*element strides*/, int bw, int bh, int bnn) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bnn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
 
 }  // namespace
 
 struct TcPlan {
   TcMaps maps;
   TcParams p;
+  HeadConsts hc;
   int block_n;
-  int grid;
+  int mode;
 };
 
 bool tc_supported(const ConvDesc& d) {
@@ -375,6 +610,19 @@ bool tc_supported(const ConvDesc& d) {
   return true;
 }
 
+static void fill_common(TcPlan* pl, int N, int Ho, int Wo, int Cout, int Cin, int bn) {
+  TcParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cin = Cin;
+  p.KH = p.KW = 1; p.stride = 1; p.pad = 0;
+  pick_tile(N, Ho, Wo, &p.lw, &p.lh);
+  const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
+  p.tiles_x = (Wo + bw - 1) / bw; p.tiles_y = (Ho + bh - 1) / bh; p.tiles_n = (N + bnn - 1) / bnn;
+  p.n_blocks = Cout / bn;
+  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
+  pl->block_n = bn;
+}
+
 TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   auto fail = [&](const std::string& m) -> TcPlan* { if (err) *err = m; return nullptr; };
   if (!tc_supported(d)) return fail("shape not supported by the tcgen05 path");
@@ -382,78 +630,131 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   if (!enc) return fail("cuTensorMapEncodeTiled not available from the driver");
   TcPlan* pl = new TcPlan();
   memset(&pl->maps, 0, sizeof(pl->maps));
+  pl->mode = MODE_CONV;
   const int bn = d.Cout % 256 == 0 ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
-  pl->block_n = bn;
-  // tile shape: BN x BH x BW = 128, all powers of two, least padding
-  int best_lw = 0, best_lh = 0; long long best = -1;
-  for (int lw = 0; lw <= 7; ++lw)
-    for (int lh = 0; lw + lh <= 7; ++lh) {
-      const int bw = 1 << lw, bh = 1 << lh, bnn = 128 >> (lw + lh);
-      long long tiles = (long long)((d.Wo + bw - 1) / bw) * ((d.Ho + bh - 1) / bh) * ((d.N + bnn - 1) / bnn);
-      // tie-break: prefer wider rows (longer contiguous stores / TMA lines)
-      if (best < 0 || tiles < best || (tiles == best && lw > best_lw)) { best = tiles; best_lw = lw; best_lh = lh; }
-    }
+  fill_common(pl, d.N, d.Ho, d.Wo, d.Cout, d.Cin, bn);
   TcParams& p = pl->p;
-  p.N = d.N; p.Ho = d.Ho; p.Wo = d.Wo; p.Cout = d.Cout; p.Cin = d.Cin;
   p.KH = d.KH; p.KW = d.KW; p.stride = d.stride; p.pad = d.pad;
-  p.lw = best_lw; p.lh = best_lh;
-  const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
-  p.tiles_x = (d.Wo + bw - 1) / bw; p.tiles_y = (d.Ho + bh - 1) / bh; p.tiles_n = (d.N + bnn - 1) / bnn;
-  p.n_blocks = d.Cout / bn;
-  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
   p.relu = d.relu; p.res_mode = d.res_mode; p.out_f32 = d.out_f32;
   p.bias = d.bias; p.res = reinterpret_cast<const bf16*>(d.res); p.out = d.out;
-  // activation map(s)
+  const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
   const int nmaps = d.stride == 1 ? 1 : 4;
   for (int mi = 0; mi < nmaps; ++mi) {
-    const int py = mi >> 1, px = mi & 1;
-    const int st = d.stride;
-    cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)((d.W - px + st - 1) / st),
-                          (cuuint64_t)((d.H - py + st - 1) / st), (cuuint64_t)d.N};
-    cuuint64_t strides[3] = {(cuuint64_t)d.Cin * 2 * st, (cuuint64_t)d.W * d.Cin * 2 * st,
-                             (cuuint64_t)d.H * d.W * d.Cin * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bnn};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    char* base = reinterpret_cast<char*>(const_cast<void*>(d.in)) + ((size_t)py * d.W + px) * d.Cin * 2;
-    CUresult r = enc(&pl->maps.a[mi], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const int py = mi >> 1, px = mi & 1, st = d.stride;
+    const char* base = reinterpret_cast<const char*>(d.in) + ((size_t)py * d.W + px) * d.Cin * 2;
+    CUresult r = encode_act4d(enc, &pl->maps.a[mi], base, d.Cin, (d.W - px + st - 1) / st, (d.H - py + st - 1) / st, d.N,
+                              (long long)d.Cin * st, (long long)d.W * d.Cin * st, (long long)d.H * d.W * d.Cin, bw, bh, bnn);
     if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r)); }
   }
-  {
-    const long long K = (long long)d.KH * d.KW * d.Cin;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d.Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)bn};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&pl->maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
+  CUresult r = encode_weights(enc, &pl->maps.b, d.w, (long long)d.KH * d.KW * d.Cin, d.Cout, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
+  return pl;
+}
+
+// Stem plan (MODE_WIN).  `in` points at a zero-bordered bf16 buffer [N][Hp][Wp][cpp] whose pixel (0,0) is the
+// top-left corner of the receptive field of output (0,0); consecutive outputs are `stride` pixels apart and
+// stride*cpp must be 8 elements (16 bytes).  Weights: [Cout=64][nr][32] bf16 (one 64-byte row per filter row).
+TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int stride, int nr, int Ho, int Wo,
+                           const void* w, const float* bias, void* out, int relu, std::string* err) {
+  auto fail = [&](const std::string& m) -> TcPlan* { if (err) *err = m; return nullptr; };
+  if (stride * cpp != 8 || (stride != 1 && stride != 2)) return fail("window stride must be 16 bytes");
+  if ((Wo - 1) * stride * cpp + 32 > Wp * cpp) return fail("padded row too short for the last window");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available from the driver");
+  TcPlan* pl = new TcPlan();
+  memset(&pl->maps, 0, sizeof(pl->maps));
+  pl->mode = MODE_WIN;
+  fill_common(pl, N, Ho, Wo, 64, 32, 64);
+  TcParams& p = pl->p;
+  p.nr = nr; p.sdiv = stride; p.relu = relu; p.bias = bias; p.out = out;
+  const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
+  const long long row = (long long)Wp * cpp;            // elements per padded row
+  // dims: window element, ox (16-byte stride: overlapping windows), row phase, oy, image
+  cuuint64_t dims[5] = {32, (cuuint64_t)Wo, (cuuint64_t)stride, (cuuint64_t)((Hp + stride - 1) / stride), (cuuint64_t)N};
+  cuuint64_t strides[4] = {16, (cuuint64_t)row * 2, (cuuint64_t)row * stride * 2, (cuuint64_t)row * Hp * 2};
+  cuuint32_t box[5] = {32, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bnn};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&pl->maps.a[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(window) failed: " + std::to_string((int)r)); }
+  r = encode_weights(enc, &pl->maps.b, w, (long long)nr * 32, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
+  return pl;
+}
+
+// DB head tail plan (MODE_DBHEAD).  feat: [N][H4][W4][128] bf16 (channels 0..63 probability branch, 64..127
+// threshold branch); w1: [2][256][64] bf16.
+TcPlan* tc_plan_create_dbhead(const void* feat, int N, int H4, int W4, const void* w1, const float* b1_host,
+                              const float* w2_host, const float* b2_host, float* prob, float* thresh, uint8_t* mask,
+                              std::string* err) {
+  auto fail = [&](const std::string& m) -> TcPlan* { if (err) *err = m; return nullptr; };
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available from the driver");
+  TcPlan* pl = new TcPlan();
+  memset(&pl->maps, 0, sizeof(pl->maps));
+  pl->mode = MODE_DBHEAD;
+  fill_common(pl, N, H4, W4, 512, 64, 256);
+  TcParams& p = pl->p;
+  p.prob = prob; p.thresh = thresh; p.mask = mask;
+  memcpy(pl->hc.b1, b1_host, sizeof(pl->hc.b1));
+  memcpy(pl->hc.w2, w2_host, sizeof(pl->hc.w2));
+  memcpy(pl->hc.b2, b2_host, sizeof(pl->hc.b2));
+  const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
+  CUresult r = encode_act4d(enc, &pl->maps.a[0], feat, 128, W4, H4, N, 128, (long long)W4 * 128, (long long)H4 * W4 * 128,
+                            bw, bh, bnn);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(head feature) failed: " + std::to_string((int)r)); }
+  r = encode_weights(enc, &pl->maps.b, w1, 64, 512, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(head weights) failed: " + std::to_string((int)r)); }
+  return pl;
+}
+
+// LSTM step plan (MODE_LSTM).  h_prev: [2 dirs][Bcap][256] bf16; whh: [2*1024][256] bf16, rows permuted to
+// (dir, unit tile of 64, gate, unit).
+TcPlan* tc_plan_create_lstm(const void* h_prev, void* h_next, int Bcap, const void* whh, const float* xproj, float* cbuf,
+                            void* seq_out, int T, std::string* err) {
+  auto fail = [&](const std::string& m) -> TcPlan* { if (err) *err = m; return nullptr; };
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available from the driver");
+  TcPlan* pl = new TcPlan();
+  memset(&pl->maps, 0, sizeof(pl->maps));
+  pl->mode = MODE_LSTM;
+  fill_common(pl, 1, 1, Bcap, 2048, 256, 256);
+  TcParams& p = pl->p;
+  p.lw = 7; p.lh = 0;                                   // 128 sequences per tile
+  p.tiles_x = (Bcap + 127) / 128; p.tiles_y = 1; p.tiles_n = 1;
+  p.total_tiles = (long long)p.tiles_x * p.n_blocks;
+  p.xproj = xproj; p.cbuf = cbuf; p.h_next = reinterpret_cast<bf16*>(h_next); p.seq_out = reinterpret_cast<bf16*>(seq_out);
+  p.lstm_T = T; p.lstm_Bcap = Bcap;
+  for (int dir = 0; dir < 2; ++dir) {
+    const char* base = reinterpret_cast<const char*>(h_prev) + (size_t)dir * Bcap * 256 * 2;
+    CUresult r = encode_act4d(enc, &pl->maps.a[dir], base, 256, Bcap, 1, 1, 256, (long long)Bcap * 256, (long long)Bcap * 256,
+                              128, 1, 1);
+    if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(h) failed: " + std::to_string((int)r)); }
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  pl->grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  CUresult r = encode_weights(enc, &pl->maps.b, whh, 256, 2048, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(W_hh) failed: " + std::to_string((int)r)); }
   return pl;
 }
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
-template <int BN>
-static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, cudaStream_t s) {
+template <int BN, int MODE>
+static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, const typename ExtraOf<MODE>::type& ex, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcCfg<BN>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcCfg<BN, MODE>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  conv_tc_kernel<BN><<<pl->grid, NUM_THREADS, TcCfg<BN>::SMEM_BYTES, s>>>(pl->maps, p);
+  const int sms = sm_count();
+  const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  conv_tc_kernel<BN, MODE><<<grid, NUM_THREADS, TcCfg<BN, MODE>::SMEM_BYTES, s>>>(pl->maps, p, ex);
   return cudaGetLastError();
 }
 
-// n_actual: images actually present in this call (<= the N the plan was built for)
+// n_actual: images (MODE_LSTM: sequences) actually present in this call (<= what the plan was built for)
 cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchCounter* lc) {
   if (n_actual <= 0) return cudaSuccess;
   TcParams p = pl->p;
@@ -461,17 +762,41 @@ cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchC
   p.N = n_actual < pl->p.N ? n_actual : pl->p.N;
   p.tiles_n = (p.N + bnn - 1) / bnn;
   p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
-  TcPlan tmp = *pl;   // grid for the reduced tile count
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  tmp.grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  NoExtra none{0};
   cudaError_t e;
-  switch (pl->block_n) {
-    case 256: e = launch_tc<256>(&tmp, p, s); break;
-    case 128: e = launch_tc<128>(&tmp, p, s); break;
-    default: e = launch_tc<64>(&tmp, p, s); break;
+  if (pl->mode == MODE_WIN) e = launch_tc<64, MODE_WIN>(pl, p, none, s);
+  else switch (pl->block_n) {
+    case 256: e = launch_tc<256, MODE_CONV>(pl, p, none, s); break;
+    case 128: e = launch_tc<128, MODE_CONV>(pl, p, none, s); break;
+    default: e = launch_tc<64, MODE_CONV>(pl, p, none, s); break;
   }
+  if (lc) lc->n++;
+  return e;
+}
+
+cudaError_t dbhead_tcgen05(TcPlan* pl, int n, float thr, const float* logit_bias, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return cudaSuccess;
+  TcParams p = pl->p;
+  const int bnn = 128 >> (p.lw + p.lh);
+  p.N = n < pl->p.N ? n : pl->p.N;
+  p.tiles_n = (p.N + bnn - 1) / bnn;
+  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
+  p.logit_bias = logit_bias;
+  pl->hc.thr = thr;
+  cudaError_t e = launch_tc<256, MODE_DBHEAD>(pl, p, pl->hc, s);
+  if (lc) lc->n++;
+  return e;
+}
+
+cudaError_t lstm_step_tcgen05(const TcPlan* pl, int B, int step, cudaStream_t s, LaunchCounter* lc) {
+  if (B <= 0) return cudaSuccess;
+  TcParams p = pl->p;
+  p.lstm_B = B; p.lstm_step = step;
+  p.Wo = B;                                              // rows beyond B are masked in the epilogue
+  p.tiles_x = (B + 127) / 128;
+  p.total_tiles = (long long)p.tiles_x * p.n_blocks;
+  NoExtra none{0};
+  cudaError_t e = launch_tc<256, MODE_LSTM>(pl, p, none, s);
   if (lc) lc->n++;
   return e;
 }

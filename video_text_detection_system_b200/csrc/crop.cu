@@ -36,20 +36,28 @@ __device__ __forceinline__ Tap cv_tap(int d, int n_in, int n_out) {
   return t;
 }
 
+// one pixel = cpp (4 or 8) channels: b, g, r, then zeros
 template <typename T>
-__device__ __forceinline__ void store_px(T* o, float b, float g, float r);
-template <> __device__ __forceinline__ void store_px<float>(float* o, float b, float g, float r) {
+__device__ __forceinline__ void store_px(T* o, float b, float g, float r, int cpp);
+template <> __device__ __forceinline__ void store_px<float>(float* o, float b, float g, float r, int cpp) {
   *reinterpret_cast<float4*>(o) = make_float4(b, g, r, 0.f);
+  if (cpp == 8) *reinterpret_cast<float4*>(o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
-template <> __device__ __forceinline__ void store_px<bf16>(bf16* o, float b, float g, float r) {
+template <> __device__ __forceinline__ void store_px<bf16>(bf16* o, float b, float g, float r, int cpp) {
   __nv_bfloat162 p0 = __floats2bfloat162_rn(b, g), p1 = __floats2bfloat162_rn(r, 0.f);
-  uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-  *reinterpret_cast<uint2*>(o) = u;
+  if (cpp == 8) {
+    uint4 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1); u.z = 0u; u.w = 0u;
+    *reinterpret_cast<uint4*>(o) = u;
+  } else {
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(o) = u;
+  }
 }
 
 template <typename T>
 __device__ void resize_one(const uint8_t* __restrict__ src, int pitch, int h, int w, int crop_w,
-                           T* __restrict__ out, Tap* xt /*smem [crop_w]*/, Tap* yt /*smem [CH]*/) {
+                           T* __restrict__ out /*pixel (0,0) of this crop*/, OutLayout lay, Tap* xt /*smem [crop_w]*/,
+                           Tap* yt /*smem [CH]*/) {
   for (int i = threadIdx.x; i < crop_w; i += blockDim.x) xt[i] = cv_tap(i, w, crop_w);
   for (int i = threadIdx.x; i < CH; i += blockDim.x) yt[i] = cv_tap(i, h, CH);
   __syncthreads();
@@ -67,7 +75,7 @@ __device__ void resize_one(const uint8_t* __restrict__ src, int pitch, int h, in
       o = o < 0 ? 0 : (o > 255 ? 255 : o);
       v[c] = __fdiv_rn((float)o, 255.0f);                      // .float() / 255.0
     }
-    store_px<T>(out + (size_t)i * 4, v[0], v[1], v[2]);
+    store_px<T>(out + dy * lay.row_pitch + (long long)dx * lay.cpp, v[0], v[1], v[2], lay.cpp);
   }
 }
 
@@ -77,7 +85,8 @@ __global__ void __launch_bounds__(256) crop_records_kernel(const uint8_t* const*
                                                            int src_w, int pitch,
                                                            const vtd_record* __restrict__ records,
                                                            const int* __restrict__ offsets, int n, int kmax,
-                                                           int first_crop, int crop_w, T* __restrict__ out) {
+                                                           int first_crop, int crop_w, T* __restrict__ out,
+                                                           OutLayout lay) {
   extern __shared__ Tap taps[];
   const int ci = first_crop + blockIdx.x;         // global crop index inside the batch
   if (ci >= offsets[n]) return;
@@ -88,23 +97,24 @@ __global__ void __launch_bounds__(256) crop_records_kernel(const uint8_t* const*
   int x1 = min(max(r.bbox[0], 0), src_w), x2 = min(max(r.bbox[2], 0), src_w);
   int y1 = min(max(r.bbox[1], 0), src_h), y2 = min(max(r.bbox[3], 0), src_h);
   int w = x2 - x1, h = y2 - y1;
-  T* o = out + (size_t)blockIdx.x * CH * crop_w * 4;
+  T* o = out + lay.offset + blockIdx.x * lay.img_pitch;
   if (w <= 0 || h <= 0) {                          // cannot happen after the >10 size filter; keep the slot defined
-    for (int i = threadIdx.x; i < CH * crop_w; i += blockDim.x) store_px<T>(o + (size_t)i * 4, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < CH * crop_w; i += blockDim.x)
+      store_px<T>(o + (i / crop_w) * lay.row_pitch + (long long)(i % crop_w) * lay.cpp, 0.f, 0.f, 0.f, lay.cpp);
     return;
   }
   const uint8_t* src = frames[f] + (size_t)y1 * pitch + (size_t)x1 * 3;
-  resize_one<T>(src, pitch, h, w, crop_w, o, taps, taps + crop_w);
+  resize_one<T>(src, pitch, h, w, crop_w, o, lay, taps, taps + crop_w);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) crop_list_kernel(const uint8_t* const* __restrict__ crops,
                                                         const int* __restrict__ hs, const int* __restrict__ ws,
                                                         const int* __restrict__ pitches, int crop_w,
-                                                        T* __restrict__ out) {
+                                                        T* __restrict__ out, OutLayout lay) {
   extern __shared__ Tap taps[];
   const int ci = blockIdx.x;
-  resize_one<T>(crops[ci], pitches[ci], hs[ci], ws[ci], crop_w, out + (size_t)ci * CH * crop_w * 4, taps,
+  resize_one<T>(crops[ci], pitches[ci], hs[ci], ws[ci], crop_w, out + lay.offset + ci * lay.img_pitch, lay, taps,
                 taps + crop_w);
 }
 
@@ -127,31 +137,31 @@ cudaError_t scan_counts(const int* counts, int n, int* offsets, cudaStream_t s, 
 template <typename T>
 cudaError_t crop_resize_records(const uint8_t* const* frames_dev, int src_h, int src_w, int pitch,
                                 const void* records, const int* offsets, int n, int kmax, int first_crop,
-                                int n_crops, int crop_w, T* out, cudaStream_t s, LaunchCounter* lc) {
+                                int n_crops, int crop_w, T* out, OutLayout lay, cudaStream_t s, LaunchCounter* lc) {
   if (n_crops <= 0) return cudaSuccess;
   size_t smem = sizeof(Tap) * (crop_w + CH);
   crop_records_kernel<T><<<n_crops, 256, smem, s>>>(frames_dev, src_h, src_w, pitch,
                                                     reinterpret_cast<const vtd_record*>(records), offsets, n, kmax,
-                                                    first_crop, crop_w, out);
+                                                    first_crop, crop_w, out, lay);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
 
 template <typename T>
 cudaError_t crop_resize_list(const uint8_t* const* crops_dev, const int* h, const int* w, const int* pitch,
-                             int n_crops, int crop_w, T* out, cudaStream_t s, LaunchCounter* lc) {
+                             int n_crops, int crop_w, T* out, OutLayout lay, cudaStream_t s, LaunchCounter* lc) {
   if (n_crops <= 0) return cudaSuccess;
   size_t smem = sizeof(Tap) * (crop_w + CH);
-  crop_list_kernel<T><<<n_crops, 256, smem, s>>>(crops_dev, h, w, pitch, crop_w, out);
+  crop_list_kernel<T><<<n_crops, 256, smem, s>>>(crops_dev, h, w, pitch, crop_w, out, lay);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
 
 #define INST(T)                                                                                                  \
   template cudaError_t crop_resize_records<T>(const uint8_t* const*, int, int, int, const void*, const int*, int, \
-                                              int, int, int, int, T*, cudaStream_t, LaunchCounter*);             \
+                                              int, int, int, int, T*, OutLayout, cudaStream_t, LaunchCounter*);  \
   template cudaError_t crop_resize_list<T>(const uint8_t* const*, const int*, const int*, const int*, int, int,  \
-                                           T*, cudaStream_t, LaunchCounter*);
+                                           T*, OutLayout, cudaStream_t, LaunchCounter*);
 INST(float)
 INST(bf16)
 

@@ -39,7 +39,8 @@ __global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, in
 
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int N, int C, int H, int W,
-                                    int Cpad) {
+                                    OutLayout lay) {
+  const int Cpad = lay.cpp;
   long long total = (long long)N * H * W * Cpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -49,13 +50,13 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict_
     int y = (int)(p % H);
     int n = (int)(p / H);
     float v = c < C ? in[(((long long)n * C + c) * H + y) * W + x] : 0.f;
-    out[i] = from_f<T>(v);
+    out[lay.offset + n * lay.img_pitch + y * lay.row_pitch + (long long)x * Cpad + c] = from_f<T>(v);
   }
 }
 
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int N, int C, int H, int W,
-                                    int Cstride) {
+                                    OutLayout lay) {
   long long total = (long long)N * C * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -64,7 +65,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict_
     int y = (int)(p % H); p /= H;
     int c = (int)(p % C);
     int n = (int)(p / C);
-    out[i] = to_f(in[(((long long)n * H + y) * W + x) * Cstride + c]);
+    out[i] = to_f(in[lay.offset + n * lay.img_pitch + y * lay.row_pitch + (long long)x * lay.cpp + c]);
   }
 }
 
@@ -95,21 +96,21 @@ cudaError_t maxpool_nhwc(const T* in, T* out, int N, int H, int W, int C, int kh
 }
 
 template <typename T>
-cudaError_t nchw_f32_to_nhwc(const float* in, T* out, int N, int C, int H, int W, int Cpad, cudaStream_t s,
+cudaError_t nchw_f32_to_nhwc(const float* in, T* out, int N, int C, int H, int W, OutLayout lay, cudaStream_t s,
                              LaunchCounter* lc) {
-  long long total = (long long)N * H * W * Cpad;
+  long long total = (long long)N * H * W * lay.cpp;
   if (total <= 0) return cudaSuccess;
-  nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(in, out, N, C, H, W, Cpad);
+  nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(in, out, N, C, H, W, lay);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t nhwc_to_nchw_f32(const T* in, float* out, int N, int C, int H, int W, int Cstride, cudaStream_t s,
+cudaError_t nhwc_to_nchw_f32(const T* in, float* out, int N, int C, int H, int W, OutLayout lay, cudaStream_t s,
                              LaunchCounter* lc) {
   long long total = (long long)N * C * H * W;
   if (total <= 0) return cudaSuccess;
-  nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(in, out, N, C, H, W, Cstride);
+  nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(in, out, N, C, H, W, lay);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
@@ -125,9 +126,10 @@ cudaError_t threshold_mask(const float* prob, uint8_t* mask, long long count, fl
 #define INST(T)                                                                                                  \
   template cudaError_t maxpool_nhwc<T>(const T*, T*, int, int, int, int, int, int, int, int, int, int,           \
                                        cudaStream_t, LaunchCounter*);                                            \
-  template cudaError_t nchw_f32_to_nhwc<T>(const float*, T*, int, int, int, int, int, cudaStream_t,              \
+  template cudaError_t nchw_f32_to_nhwc<T>(const float*, T*, int, int, int, int, OutLayout, cudaStream_t,        \
                                            LaunchCounter*);                                                      \
-  template cudaError_t nhwc_to_nchw_f32<T>(const T*, float*, int, int, int, int, int, cudaStream_t, LaunchCounter*);
+  template cudaError_t nhwc_to_nchw_f32<T>(const T*, float*, int, int, int, int, OutLayout, cudaStream_t,        \
+                                           LaunchCounter*);
 INST(float)
 INST(bf16)
 

@@ -40,7 +40,7 @@ __device__ __forceinline__ int nv12_bgr(const uint8_t* f, int h, int pitch, int 
 template <typename T, int PIX>
 __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __restrict__ frames, int h, int w,
                                                         int pitch, ResizeTab tx, ResizeTab ty, int rows_cap,
-                                                        T* __restrict__ out) {
+                                                        T* __restrict__ out, OutLayout lay) {
   extern __shared__ uint8_t tmp[];   // [rows][TW][3] horizontal-pass result, uint8 like Pillow's
   const uint8_t* __restrict__ f = frames[blockIdx.z];
   const int dw = tx.out_size, dh = ty.out_size;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
     v[1] = __fdiv_rn(__fsub_rn(__fdiv_rn(g, 255.0f), 0.456f), 0.224f);
     v[2] = __fdiv_rn(__fsub_rn(__fdiv_rn(b, 255.0f), 0.406f), 0.225f);
     v[3] = 0.f;
-    size_t o = (((size_t)blockIdx.z * dh + oy) * dw + ox0 + xo) * 4;
+    size_t o = (size_t)(lay.offset + blockIdx.z * lay.img_pitch + oy * lay.row_pitch + (long long)(ox0 + xo) * 4);
     if (sizeof(T) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
 
 template <typename T>
 cudaError_t preprocess_frames(const uint8_t* const* frames_dev, int n, int h, int w, int pitch, int pixfmt,
-                              const ResizeTab& tx, const ResizeTab& ty, uint8_t* /*tmp_u8*/, T* out,
+                              const ResizeTab& tx, const ResizeTab& ty, uint8_t* /*tmp_u8*/, T* out, OutLayout lay,
                               cudaStream_t s, LaunchCounter* lc) {
   if (n <= 0) return cudaSuccess;
   // rows of the intermediate one tile can need: TH output rows span at most TH*scale + ksize source rows
@@ -121,21 +121,21 @@ cudaError_t preprocess_frames(const uint8_t* const* frames_dev, int n, int h, in
       e = cudaFuncSetAttribute(preprocess_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    preprocess_kernel<T, 0><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, out);
+    preprocess_kernel<T, 0><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, out, lay);
   } else {
     if (smem > 48 * 1024) {
       e = cudaFuncSetAttribute(preprocess_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    preprocess_kernel<T, 1><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, out);
+    preprocess_kernel<T, 1><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, out, lay);
   }
   if (lc) lc->n++;
   return cudaGetLastError();
 }
 
 template cudaError_t preprocess_frames<float>(const uint8_t* const*, int, int, int, int, int, const ResizeTab&,
-                                              const ResizeTab&, uint8_t*, float*, cudaStream_t, LaunchCounter*);
+                                              const ResizeTab&, uint8_t*, float*, OutLayout, cudaStream_t, LaunchCounter*);
 template cudaError_t preprocess_frames<bf16>(const uint8_t* const*, int, int, int, int, int, const ResizeTab&,
-                                             const ResizeTab&, uint8_t*, bf16*, cudaStream_t, LaunchCounter*);
+                                             const ResizeTab&, uint8_t*, bf16*, OutLayout, cudaStream_t, LaunchCounter*);
 
 }  // namespace vtd
