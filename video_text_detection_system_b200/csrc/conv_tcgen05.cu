@@ -47,7 +47,8 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // bf16 elements = one 128-byte swizzle row
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
+constexpr int NUM_EPI_WARPS = 8;
 
 struct alignas(64) TcMaps {
   CUtensorMap a[4];     // activation maps; [0] only for stride 1, [py*2+px] for stride 2
@@ -199,18 +200,35 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = MODE == MODE_WIN ? 12 : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/ +
+                                    (MODE == MODE_DBHEAD ? 4096 : 0) /*head constants*/;
 };
 
 
 // ---- epilogues ---------------------------------------------------------------------------------------------
 
-// MODE_CONV / MODE_WIN: bias + residual + ReLU -> NHWC bf16 / fp32
+// MODE_CONV / MODE_WIN: bias + residual + ReLU -> NHWC bf16 / fp32.  Two warps share a TMEM lane quarter and split
+// the tile's columns (`half`).  All residual vectors of the warp's columns are requested BEFORE the accumulator
+// barrier is waited on, so their DRAM/L2 latency overlaps the MMAs instead of serialising per 32-column chunk.
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_acc, int q, bool valid, size_t opix,
-                                              size_t rpix, int nb) {
-#pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+__device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_acc, int q, int half, bool valid,
+                                              size_t opix, size_t rpix, int nb, uint32_t tfull_bar, uint32_t parity) {
+  constexpr int NCH = BLOCK_N / 64;                  // 32-column chunks per warp
+  const int cbase = half * (BLOCK_N / 2);
+  uint4 rv[NCH][4];
+  const bool has_res = p.res_mode != RES_NONE;
+  if (has_res && valid) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + nb * BLOCK_N + cbase);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rv[i][j] = __ldg(rp + i * 4 + j);
+  }
+  mbar_wait(tfull_bar, parity);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c0 = cbase + i * 32;
     uint32_t v[32];
     tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -226,12 +244,10 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
           f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
         }
       }
-      if (p.res_mode != RES_NONE) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + co);
+      if (has_res) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4 u = __ldg(rp + j);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[i][j]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float2 r2 = __bfloat1622float2(h[e]);
@@ -265,47 +281,52 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
   }
 }
 
-// MODE_DBHEAD: ReLU(ConvT1) -> ConvT2 -> (+logit bias) -> sigmoid -> 4x4 block of prob / thresh (+ mask)
-template <int HEAD>
-__device__ __forceinline__ void epilogue_dbhead(const TcParams& p, const HeadConsts& ex, uint32_t tmem_acc, int q,
-                                                bool valid, int n, int oy, int ox) {
-  float o[16];
+// MODE_DBHEAD: ReLU(ConvT1) -> ConvT2 -> (+logit bias) -> sigmoid -> 4x4 block of prob / thresh (+ mask).
+// hs points at this head's constants in shared memory: b1[256], then w2[64][4].  Warp `half` owns ConvT1 positions
+// dy = half (g = 2*half, 2*half+1), i.e. output rows 2*half and 2*half+1 of the pixel's 4x4 block.  The loops over
+// (g, 32-channel chunk) stay rolled: the body is small enough for the instruction cache (a fully unrolled version
+// with immediate constants was instruction-fetch bound, profiles/r01_ncu_notes.md).
+__device__ __forceinline__ void epilogue_dbhead(const TcParams& p, const float* __restrict__ hs, float b2, float thr,
+                                                int head, uint32_t tmem_acc, int q, int half, bool valid, int n, int oy,
+                                                int ox) {
+  float o[8];                                       // [dx][(dy2,dx2)]
 #pragma unroll
-  for (int k = 0; k < 16; ++k) o[k] = ex.b2[HEAD];
+  for (int k = 0; k < 8; ++k) o[k] = b2;
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {                  // (dx, 32-channel half)
+    const int dx = it >> 1, ch = it & 1;
+    const int g = half * 2 + dx;
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + ch * 32), v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const float* b1 = hs + g * 64 + ch * 32;
+    const float4* w2 = reinterpret_cast<const float4*>(hs + 256) + ch * 32;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {                     // (dy,dx) position of the first transposed conv
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + half * 32), v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = half * 32 + j;
-        const float h = fmaxf(__uint_as_float(v[j]) + ex.b1[HEAD][g * 64 + c], 0.f);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o[g * 4 + k] = fmaf(h, ex.w2[HEAD][c][k], o[g * 4 + k]);
-      }
+    for (int j = 0; j < 32; ++j) {
+      const float h = fmaxf(__uint_as_float(v[j]) + b1[j], 0.f);
+      const float4 w = w2[j];
+      a0 = fmaf(h, w.x, a0); a1 = fmaf(h, w.y, a1); a2 = fmaf(h, w.z, a2); a3 = fmaf(h, w.w, a3);
     }
+    if (dx == 0) { o[0] += a0; o[1] += a1; o[2] += a2; o[3] += a3; }
+    else { o[4] += a0; o[5] += a1; o[6] += a2; o[7] += a3; }
   }
   if (!valid) return;
   const int Wd = 4 * p.Wo, Hd = 4 * p.Ho;
-  float* __restrict__ outp = HEAD == 0 ? p.prob : p.thresh;
+  float* __restrict__ outp = head == 0 ? p.prob : p.thresh;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int dy = r >> 1, dy2 = r & 1;
-    float v0 = o[(dy * 2 + 0) * 4 + dy2 * 2 + 0], v1 = o[(dy * 2 + 0) * 4 + dy2 * 2 + 1];
-    float v2 = o[(dy * 2 + 1) * 4 + dy2 * 2 + 0], v3 = o[(dy * 2 + 1) * 4 + dy2 * 2 + 1];
+  for (int dy2 = 0; dy2 < 2; ++dy2) {
+    const int r = half * 2 + dy2;
+    float v0 = o[dy2 * 2 + 0], v1 = o[dy2 * 2 + 1], v2 = o[4 + dy2 * 2 + 0], v3 = o[4 + dy2 * 2 + 1];
     const size_t oidx = ((size_t)n * Hd + 4 * oy + r) * Wd + 4 * ox;
-    if (HEAD == 0 && p.logit_bias) {
+    if (head == 0 && p.logit_bias) {
       float4 lb = __ldg(reinterpret_cast<const float4*>(p.logit_bias + oidx));
       v0 += lb.x; v1 += lb.y; v2 += lb.z; v3 += lb.w;
     }
     v0 = 1.0f / (1.0f + expf(-v0)); v1 = 1.0f / (1.0f + expf(-v1));
     v2 = 1.0f / (1.0f + expf(-v2)); v3 = 1.0f / (1.0f + expf(-v3));
     *reinterpret_cast<float4*>(outp + oidx) = make_float4(v0, v1, v2, v3);
-    if (HEAD == 0) {
-      const float thr = ex.thr;
+    if (head == 0) {
       uint32_t m = (v0 > thr ? 1u : 0u) | (v1 > thr ? 0x100u : 0u) | (v2 > thr ? 0x10000u : 0u) |
                    (v3 > thr ? 0x1000000u : 0u);
       *reinterpret_cast<uint32_t*>(p.mask + oidx) = m;
@@ -314,7 +335,7 @@ __device__ __forceinline__ void epilogue_dbhead(const TcParams& p, const HeadCon
 }
 
 // MODE_LSTM: gates -> cell update.  Tile columns = [i(64) | f(64) | g(64) | o(64)] of hidden units jt*64..+63.
-__device__ __forceinline__ void epilogue_lstm(const TcParams& p, uint32_t tmem_acc, int q, int b, int nb) {
+__device__ __forceinline__ void epilogue_lstm(const TcParams& p, uint32_t tmem_acc, int q, int half, int b, int nb) {
   const int dir = nb >> 2, jt = nb & 3;
   const bool valid = b < p.lstm_B;
   const int t = dir == 0 ? p.lstm_step : p.lstm_T - 1 - p.lstm_step;
@@ -324,7 +345,7 @@ __device__ __forceinline__ void epilogue_lstm(const TcParams& p, uint32_t tmem_a
   bf16* __restrict__ hn = p.h_next + ((size_t)dir * p.lstm_Bcap + bb) * 256 + jt * 64;
   bf16* __restrict__ so = p.seq_out + ((size_t)bb * p.lstm_T + t) * 512 + dir * 256 + jt * 64;
 #pragma unroll 1
-  for (int qq = 0; qq < 4; ++qq) {                  // 16 hidden units at a time
+  for (int qq = half * 2; qq < half * 2 + 2; ++qq) {   // 16 hidden units at a time; 32 units per warp
     uint32_t vi[16], vf[16], vg[16], vo[16];
     const uint32_t base = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(qq * 16);
     tmem_ld16(base, vi); tmem_ld16(base + 64, vf); tmem_ld16(base + 128, vg); tmem_ld16(base + 192, vo);
@@ -385,12 +406,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const uint32_t tfull0 = empty0 + 8 * Cfg::STAGES;            // [2]
   const uint32_t tempty0 = tfull0 + 16;                        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  float* head_s = reinterpret_cast<float*>(bars + 2 * Cfg::STAGES + 6);   // MODE_DBHEAD: [2 heads][256 b1 + 256 w2]
+  if constexpr (MODE == MODE_DBHEAD) {
+    for (int i = threadIdx.x; i < 2 * 512; i += NUM_THREADS) {
+      const int hd = i >> 9, r = i & 511;
+      head_s[i] = r < 256 ? ex.b1[hd][r] : (&ex.w2[hd][0][0])[r - 256];
+    }
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
@@ -484,8 +512,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                   // which half of the tile's columns / units / rows
     const int m = q * 32 + lane;                        // row of the tile = pixel
     const int xx = m & (BW - 1), yy = (m >> p.lw) & (BH - 1), nn = m >> (p.lw + p.lh);
     long long it = 0;
@@ -497,20 +526,22 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       const int ox = tx * BW + xx, oy = ty * BH + yy, n = (int)t * BNt + nn;
       const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
       const int as = (int)(it & 1);
-      mbar_wait(tfull0 + 8 * as, (uint32_t)((it >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
+      const uint32_t tfull_bar = tfull0 + 8 * as, parity = (uint32_t)((it >> 1) & 1);
       if constexpr (MODE == MODE_DBHEAD) {
-        if (nb == 0) epilogue_dbhead<0>(p, ex, tmem_acc, q, valid, n, oy, ox);
-        else epilogue_dbhead<1>(p, ex, tmem_acc, q, valid, n, oy, ox);
+        mbar_wait(tfull_bar, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        epilogue_dbhead(p, head_s + nb * 512, ex.b2[nb], ex.thr, nb, tmem_acc, q, half, valid, n, oy, ox);
       } else if constexpr (MODE == MODE_LSTM) {
-        epilogue_lstm(p, tmem_acc, q, ox, nb);
+        mbar_wait(tfull_bar, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        epilogue_lstm(p, tmem_acc, q, half, ox, nb);
       } else {
         const size_t opix = ((size_t)n * p.Ho + oy) * p.Wo + ox;
         size_t rpix = 0;
         if (p.res_mode == RES_SAME) rpix = opix;
         else if (p.res_mode == RES_UP2) rpix = ((size_t)n * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
-        epilogue_conv<BLOCK_N>(p, tmem_acc, q, valid, opix, rpix, nb);
+        epilogue_conv<BLOCK_N>(p, tmem_acc, q, half, valid, opix, rpix, nb, tfull_bar, parity);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();

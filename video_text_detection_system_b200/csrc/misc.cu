@@ -6,34 +6,66 @@
 namespace vtd {
 namespace {
 
-// nn.MaxPool2d semantics (implicit -inf padding). One thread per (pixel, 4-channel group).
-template <typename T>
-__global__ void maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H, int W, int C, int Ho,
-                               int Wo, int kh, int kw, int sh, int sw, int ph, int pw) {
-  const int C4 = C >> 2;
-  long long total = (long long)N * Ho * Wo * C4;
+// nn.MaxPool2d semantics (implicit -inf padding).  One thread per (output pixel, 16-byte channel group): all taps
+// are requested first (KH*KW independent 16-byte loads in flight), then reduced -- HBM/L2-bound, no reuse needed
+// beyond what L2 provides.
+template <typename T> struct PoolVec;
+template <> struct PoolVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ uint4 ninf() {
+    uint32_t u = 0xff800000u; return make_uint4(u, u, u, u);
+  }
+  static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) {
+    uint4 r;
+    r.x = __float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x)));
+    r.y = __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y)));
+    r.z = __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z)));
+    r.w = __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w)));
+    return r;
+  }
+};
+template <> struct PoolVec<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ uint4 ninf() {
+    uint32_t u = 0xff80ff80u; return make_uint4(u, u, u, u);
+  }
+  static __device__ __forceinline__ uint32_t m2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) {
+    return make_uint4(m2(a.x, b.x), m2(a.y, b.y), m2(a.z, b.z), m2(a.w, b.w));
+  }
+};
+
+template <typename T, int KH, int KW>
+__global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int N, int H,
+                                                      int W, int C, int Ho, int Wo, int sh, int sw, int ph, int pw) {
+  constexpr int V = PoolVec<T>::N;
+  const int CV = C / V;
+  const long long total = (long long)N * Ho * Wo * CV;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % C4);
-    long long p = i / C4;
-    int ox = (int)(p % Wo); p /= Wo;
-    int oy = (int)(p % Ho);
-    int n = (int)(p / Ho);
-    float m[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int r = 0; r < kh; ++r) {
-      int iy = oy * sh - ph + r;
-      if ((unsigned)iy >= (unsigned)H) continue;
-      for (int s = 0; s < kw; ++s) {
-        int ix = ox * sw - pw + s;
-        if ((unsigned)ix >= (unsigned)W) continue;
-        const T* q = in + (((long long)n * H + iy) * W + ix) * C + c4 * 4;
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    uint4 t[KH * KW];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], to_f(q[j]));
+    for (int r = 0; r < KH; ++r) {
+#pragma unroll
+      for (int s = 0; s < KW; ++s) {
+        const int iy = oy * sh - ph + r, ix = ox * sw - pw + s;
+        const bool ok = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+        t[r * KW + s] = ok ? __ldg(reinterpret_cast<const uint4*>(in + (((long long)n * H + iy) * W + ix) * C) + cv)
+                           : PoolVec<T>::ninf();
       }
     }
-    T* o = out + (((long long)n * Ho + oy) * Wo + ox) * C + c4 * 4;
+    uint4 m = t[0];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = from_f<T>(m[j]);
+    for (int k = 1; k < KH * KW; ++k) m = PoolVec<T>::vmax(m, t[k]);
+    reinterpret_cast<uint4*>(out + (((long long)n * Ho + oy) * Wo + ox) * C)[cv] = m;
   }
 }
 
@@ -88,9 +120,17 @@ template <typename T>
 cudaError_t maxpool_nhwc(const T* in, T* out, int N, int H, int W, int C, int kh, int kw, int sh, int sw, int ph,
                          int pw, cudaStream_t s, LaunchCounter* lc) {
   int Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
-  long long total = (long long)N * Ho * Wo * (C / 4);
+  constexpr int V = PoolVec<T>::N;
+  if (C % V != 0) return cudaErrorInvalidValue;
+  long long total = (long long)N * Ho * Wo * (C / V);
   if (total <= 0) return cudaSuccess;
-  maxpool_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(in, out, N, H, W, C, Ho, Wo, kh, kw, sh, sw, ph, pw);
+  long long g = (total + 255) / 256;
+  const long long cap = 148LL * 32;
+  const int grid = (int)(g < cap ? g : cap);
+  if (kh == 3 && kw == 3) maxpool_kernel<T, 3, 3><<<grid, 256, 0, s>>>(in, out, N, H, W, C, Ho, Wo, sh, sw, ph, pw);
+  else if (kh == 2 && kw == 2) maxpool_kernel<T, 2, 2><<<grid, 256, 0, s>>>(in, out, N, H, W, C, Ho, Wo, sh, sw, ph, pw);
+  else if (kh == 2 && kw == 1) maxpool_kernel<T, 2, 1><<<grid, 256, 0, s>>>(in, out, N, H, W, C, Ho, Wo, sh, sw, ph, pw);
+  else return cudaErrorInvalidValue;
   if (lc) lc->n++;
   return cudaGetLastError();
 }

@@ -37,50 +37,108 @@ __device__ __forceinline__ int nv12_bgr(const uint8_t* f, int h, int pitch, int 
   return clip8(val);
 }
 
+// Shared-memory plan of one CTA (TH x TW output tile):
+//   sx_lo/sx_cnt[TW], sx_k[TW][ksx]   horizontal coefficient slice        (ints)
+//   sy_lo/sy_cnt[TH], sy_k[TH][ksy]   vertical coefficient slice
+//   src[rows][srcb]                   the source rows the tile needs, BGR bytes, fetched with 16-byte loads
+//   tmp[rows][TW][3]                  horizontal-pass result, uint8 like Pillow's intermediate image
 template <typename T, int PIX>
 __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __restrict__ frames, int h, int w,
                                                         int pitch, ResizeTab tx, ResizeTab ty, int rows_cap,
-                                                        T* __restrict__ out, OutLayout lay) {
-  extern __shared__ uint8_t tmp[];   // [rows][TW][3] horizontal-pass result, uint8 like Pillow's
+                                                        int srcb_cap, T* __restrict__ out, OutLayout lay) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int ksx = tx.ksize, ksy = ty.ksize;
+  int* sx_lo = reinterpret_cast<int*>(smem);
+  int* sx_cnt = sx_lo + TW;
+  int* sx_k = sx_cnt + TW;
+  int* sy_lo = sx_k + TW * ksx;
+  int* sy_cnt = sy_lo + TH;
+  int* sy_k = sy_cnt + TH;
+  uint8_t* src = reinterpret_cast<uint8_t*>(sy_k + TH * ksy);
+  uint8_t* tmp = src + (size_t)rows_cap * srcb_cap;
+
   const uint8_t* __restrict__ f = frames[blockIdx.z];
   const int dw = tx.out_size, dh = ty.out_size;
   const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
-  const int oy1 = min(oy0 + TH, dh) - 1;
+  const int tw = min(TW, dw - ox0), th = min(TH, dh - oy0);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < tw; i += NT) { sx_lo[i] = tx.lo[ox0 + i]; sx_cnt[i] = tx.cnt[ox0 + i]; }
+  for (int i = tid; i < tw * ksx; i += NT) sx_k[i] = tx.kk[(size_t)ox0 * ksx + i];
+  for (int i = tid; i < th; i += NT) { sy_lo[i] = ty.lo[oy0 + i]; sy_cnt[i] = ty.cnt[oy0 + i]; }
+  for (int i = tid; i < th * ksy; i += NT) sy_k[i] = ty.kk[(size_t)oy0 * ksy + i];
   const int r0 = ty.lo[oy0];
-  const int r1 = ty.lo[oy1] + ty.cnt[oy1];       // exclusive (lo is non-decreasing in oy)
+  const int r1 = ty.lo[oy0 + th - 1] + ty.cnt[oy0 + th - 1];       // exclusive (lo is non-decreasing)
   const int rows = min(r1 - r0, rows_cap);
-  const int tw = min(TW, dw - ox0);
+  const int c0 = tx.lo[ox0];
+  const int c1 = tx.lo[ox0 + tw - 1] + tx.cnt[ox0 + tw - 1];       // exclusive source column
+  const int ncols = c1 - c0;
+
+  // ---- stage the source rows (bytes [c0*3, c1*3) of rows r0..r0+rows) with aligned 16-byte loads
+  if (PIX == 0) {
+    const int b0 = c0 * 3, b1 = c1 * 3;
+    for (int r = tid / 32; r < rows; r += NT / 32) {
+      const uint8_t* row = f + (size_t)(r0 + r) * pitch;
+      const size_t a0 = (reinterpret_cast<size_t>(row) + b0) & ~(size_t)15;     // aligned start address
+      const int skew = (int)(reinterpret_cast<size_t>(row) + b0 - a0);          // bytes before b0 in the first vector
+      const int nvec = (skew + (b1 - b0) + 15) >> 4;
+      uint8_t* dst = src + (size_t)r * srcb_cap;
+      const size_t row_end = reinterpret_cast<size_t>(f) + (size_t)h * pitch;   // never read past the frame
+      for (int v = tid & 31; v < nvec; v += 32) {
+        const size_t addr = a0 + (size_t)v * 16;
+        uint4 q;
+        if (addr + 16 <= row_end && addr >= reinterpret_cast<size_t>(f)) q = __ldg(reinterpret_cast<const uint4*>(addr));
+        else {
+          uint8_t t8[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            size_t ad = addr + k;
+            t8[k] = (ad >= reinterpret_cast<size_t>(f) && ad < row_end) ? *reinterpret_cast<const uint8_t*>(ad) : 0;
+          }
+          q = *reinterpret_cast<uint4*>(t8);
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)v * 16) = q;
+      }
+    }
+  } else {
+    // NV12: convert to BGR bytes while staging (BT.601 limited range, cv2's fixed point)
+    for (int it = tid; it < rows * ncols; it += NT) {
+      const int r = it / ncols, x = it - r * ncols;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) src[(size_t)r * srcb_cap + x * 3 + c] = (uint8_t)nv12_bgr(f, h, pitch, r0 + r, c0 + x, c);
+    }
+  }
+  __syncthreads();
 
   // ---- horizontal pass: items = rows x tw x 3
-  for (int it = threadIdx.x; it < rows * tw * 3; it += NT) {
-    int c = it % 3;
-    int q = it / 3;
-    int xo = q % tw, r = q / tw;
-    int ox = ox0 + xo, iy = r0 + r;
-    int lo = tx.lo[ox], cnt = tx.cnt[ox];
-    const int* kk = tx.kk + (size_t)ox * tx.ksize;
-    int acc = 1 << 21;
+  for (int it = tid; it < rows * tw * 3; it += NT) {
+    const int c = it % 3;
+    const int qx = it / 3;
+    const int xo = qx % tw, r = qx / tw;
+    const int lo = sx_lo[xo], cnt = sx_cnt[xo];
+    const int* kk = sx_k + xo * ksx;
+    int skew = 0;
     if (PIX == 0) {
-      const uint8_t* p = f + (size_t)iy * pitch + (size_t)lo * 3 + c;
-      for (int j = 0; j < cnt; ++j) acc += (int)p[j * 3] * kk[j];
-    } else {
-      for (int j = 0; j < cnt; ++j) acc += nv12_bgr(f, h, pitch, iy, lo + j, c) * kk[j];
+      const uint8_t* row = f + (size_t)(r0 + r) * pitch;
+      skew = (int)((reinterpret_cast<size_t>(row) + c0 * 3) & 15);
     }
+    const uint8_t* p = src + (size_t)r * srcb_cap + skew + (lo - c0) * 3 + c;
+    int acc = 1 << 21;
+    for (int j = 0; j < cnt; ++j) acc += (int)p[j * 3] * kk[j];
     tmp[(r * TW + xo) * 3 + c] = (uint8_t)clip8(acc >> 22);
   }
   __syncthreads();
 
   // ---- vertical pass + normalise: items = th x tw pixels
-  const int th = oy1 - oy0 + 1;
-  for (int it = threadIdx.x; it < th * tw; it += NT) {
-    int xo = it % tw, yo = it / tw;
-    int oy = oy0 + yo;
-    int lo = ty.lo[oy] - r0, cnt = ty.cnt[oy];
-    const int* kk = ty.kk + (size_t)oy * ty.ksize;
+  for (int it = tid; it < th * tw; it += NT) {
+    const int xo = it % tw, yo = it / tw;
+    const int oy = oy0 + yo;
+    const int lo = sy_lo[yo] - r0, cnt = sy_cnt[yo];
+    const int* kk = sy_k + yo * ksy;
     int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
     for (int j = 0; j < cnt; ++j) {
       const uint8_t* p = tmp + ((lo + j) * TW + xo) * 3;
-      int k = kk[j];
+      const int k = kk[j];
       a0 += (int)p[0] * k; a1 += (int)p[1] * k; a2 += (int)p[2] * k;
     }
     // source order is B,G,R; the network wants R,G,B (cvtColor at text_detector.py:120)
@@ -109,10 +167,14 @@ cudaError_t preprocess_frames(const uint8_t* const* frames_dev, int n, int h, in
                               const ResizeTab& tx, const ResizeTab& ty, uint8_t* /*tmp_u8*/, T* out, OutLayout lay,
                               cudaStream_t s, LaunchCounter* lc) {
   if (n <= 0) return cudaSuccess;
-  // rows of the intermediate one tile can need: TH output rows span at most TH*scale + ksize source rows
-  double scale = (double)ty.in_size / ty.out_size;
-  int rows_cap = (int)(TH * (scale > 1.0 ? scale : 1.0)) + ty.ksize + 2;
-  size_t smem = (size_t)rows_cap * TW * 3;
+  // source rows / columns one tile can need: T output samples span at most T*scale + ksize source samples
+  const double sy = (double)ty.in_size / ty.out_size, sx = (double)tx.in_size / tx.out_size;
+  const int rows_cap = (int)(TH * (sy > 1.0 ? sy : 1.0)) + ty.ksize + 2;
+  const int cols_cap = (int)(TW * (sx > 1.0 ? sx : 1.0)) + tx.ksize + 2;
+  const int srcb_cap = ((cols_cap * 3 + 15 + 15) / 16 + 1) * 16;          // + alignment skew, rounded to 16 bytes
+  size_t smem = sizeof(int) * (size_t)(2 * TW + TW * tx.ksize + 2 * TH + TH * ty.ksize);
+  smem = (smem + 15) & ~(size_t)15;
+  smem += (size_t)rows_cap * srcb_cap + (size_t)rows_cap * TW * 3 + 16;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   dim3 grid((tx.out_size + TW - 1) / TW, (ty.out_size + TH - 1) / TH, n);
   cudaError_t e;
@@ -121,13 +183,13 @@ cudaError_t preprocess_frames(const uint8_t* const* frames_dev, int n, int h, in
       e = cudaFuncSetAttribute(preprocess_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    preprocess_kernel<T, 0><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, out, lay);
+    preprocess_kernel<T, 0><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, srcb_cap, out, lay);
   } else {
     if (smem > 48 * 1024) {
       e = cudaFuncSetAttribute(preprocess_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    preprocess_kernel<T, 1><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, out, lay);
+    preprocess_kernel<T, 1><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, srcb_cap, out, lay);
   }
   if (lc) lc->n++;
   return cudaGetLastError();
