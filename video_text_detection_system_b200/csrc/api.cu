@@ -82,6 +82,7 @@ struct vtd_ctx {
   cudaEvent_t ptrs_event = nullptr;
   int cur_h = 0, cur_w = 0, cur_pitch = 0, cur_n = 0, cur_pix = 0;
   ResizeTab tx, ty; int tab_h = -1, tab_w = -1;
+  float* norm_lut = nullptr;            // [3][256] u8 -> normalised fp32
 
   // boxes
   uint8_t* box_work = nullptr; BoxWorkLayout box_lay{};
@@ -98,7 +99,8 @@ struct vtd_ctx {
   void* rnn_out[2] = {nullptr, nullptr};
   void* whh[2] = {nullptr, nullptr};
   float *hbuf = nullptr, *cbuf = nullptr;
-  float* logits = nullptr;              // [rc,T,97]
+  float* logits = nullptr;              // [rc,T,logits_ld]  (97, or 128 when the classifier runs on tcgen05)
+  int logits_ld = 97;
   Op xproj_op[2], fc_op;
   uint8_t* ids_dev = nullptr; int* len_dev = nullptr; float* conf_dev = nullptr;
   // crop-list drop-in staging
@@ -565,13 +567,18 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
     const vtd_tensor *w = sd.get("classifier.weight"), *b = sd.get("classifier.bias");
     if (!w || !b || w->ndim != 2 || w->shape[1] != 2 * H || numel(b) != w->shape[0])
       FAIL(VTD_ERR_WEIGHT, "missing or mis-shaped classifier");
-    fc.Cout = (int)w->shape[0]; fc.Cin = fc.Cin_pad = 2 * H; fc.KH = fc.KW = 1;
-    fc.w.assign(w->data, w->data + numel(w)); fc.b.assign(b->data, b->data + numel(b));
+    if (w->shape[0] != 97) FAIL(VTD_ERR_WEIGHT, "classifier must have 97 outputs (text_recognizer.py:81)");
+    // bf16 tier: pad the 97 classes to 128 zero rows so the GEMM runs on the tcgen05 path; the decode reads 97
+    c->logits_ld = c->bf16_mode ? 128 : 97;
+    fc.Cout = c->logits_ld; fc.Cin = fc.Cin_pad = 2 * H; fc.KH = fc.KW = 1;
+    fc.w.assign((size_t)fc.Cout * 2 * H, 0.f); fc.b.assign(fc.Cout, 0.f);
+    memcpy(fc.w.data(), w->data, sizeof(float) * 97 * 2 * H);
+    memcpy(fc.b.data(), b->data, sizeof(float) * 97);
   }
   Act lo;
   if ((r = add_conv(c, nullptr, fc, B, in, 1, 0, false, nullptr, RES_NONE, true, &lo, &c->fc_op))) return r;
   c->logits = (float*)lo.p;
-  reg_dbg(c, "logits", lo, true, true);
+  c->dbg["logits"] = DebugEntry{lo.p, 97, 1, c->T, dense_layout(1, c->T, c->logits_ld), true, true};
   return VTD_OK;
 }
 
@@ -646,10 +653,10 @@ int preprocess_locked(vtd_ctx* c, const uint8_t* const* frames, int n, int h, in
     c->tab_h = h; c->tab_w = w;
   }
   if (c->bf16_mode)
-    CK(preprocess_frames<bf16>(c->frame_ptrs_dev, n, h, w, dev_pitch, pixfmt, c->tx, c->ty, nullptr, (bf16*)c->pre,
+    CK(preprocess_frames<bf16>(c->frame_ptrs_dev, n, h, w, dev_pitch, pixfmt, c->tx, c->ty, c->norm_lut, (bf16*)c->pre,
                                c->pre_lay, c->stream, &c->lc));
   else
-    CK(preprocess_frames<float>(c->frame_ptrs_dev, n, h, w, dev_pitch, pixfmt, c->tx, c->ty, nullptr, (float*)c->pre,
+    CK(preprocess_frames<float>(c->frame_ptrs_dev, n, h, w, dev_pitch, pixfmt, c->tx, c->ty, c->norm_lut, (float*)c->pre,
                                 c->pre_lay, c->stream, &c->lc));
   c->cur_h = h; c->cur_w = w; c->cur_pitch = dev_pitch; c->cur_n = n; c->cur_pix = pixfmt;
   return VTD_OK;
@@ -679,7 +686,7 @@ int recognize_locked(vtd_ctx* c, int n) {
       CK(crop_resize_records<float>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
                                     c->cfg.max_boxes, first, nc, c->cfg.crop_w, (float*)c->crops, c->crops_lay, c->stream, &c->lc));
     int r = run_crnn(c, nc); if (r) return r;
-    CK(ctc_into_records(c->logits, nc, first, c->T, 97, c->cfg.canonical_ctc, c->offsets, n, c->cfg.max_boxes,
+    CK(ctc_into_records(c->logits, nc, first, c->T, 97, c->logits_ld, c->cfg.canonical_ctc, c->offsets, n, c->cfg.max_boxes,
                         c->records, c->stream, &c->lc));
   }
   return VTD_OK;
@@ -787,6 +794,10 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   cudaMemcpy(c->store_ptrs_dev, c->frame_ptrs_pinned, sizeof(void*) * B, cudaMemcpyHostToDevice);
   c->frame_ptrs_dev = c->store_ptrs_dev;
   cudaMemset(c->counts, 0, sizeof(int) * B);
+  if ((r = dalloc(c, &c->norm_lut, 768 * sizeof(float)))) return fail(r);
+  if (build_normalize_lut(c->norm_lut, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    c->err = "normalisation table kernel failed"; return fail(VTD_ERR_CUDA);
+  }
   if (c->use_win) {   // zero-bordered stem inputs: 4 px left/right + 3 rows top/bottom (7x7 s2), 1 px + 1 row (3x3)
     c->pre_lay = padded_layout(dh, dw, 4, 3, 3, 4, 4);
     c->crops_lay = padded_layout(32, cfg->crop_w, 8, 1, 1, 1, 3);
@@ -1020,12 +1031,12 @@ int vtd_recognize_crops(vtd_ctx* c, const uint8_t* const* crops, const int* h, c
       CK(crop_resize_list<float>(c->list_ptrs, c->list_meta, c->list_meta + c->rc, c->list_meta + 2 * c->rc, nc,
                                  c->cfg.crop_w, (float*)c->crops, c->crops_lay, c->stream, &c->lc));
     int r = run_crnn(c, nc); if (r) return r;
-    CK(ctc_greedy(c->logits, nc, T, 97, 0, c->cfg.canonical_ctc, c->ids_dev, VTD_IDS_STRIDE, c->len_dev, c->conf_dev,
+    CK(ctc_greedy(c->logits, nc, T, 97, c->logits_ld, 0, c->cfg.canonical_ctc, c->ids_dev, VTD_IDS_STRIDE, c->len_dev, c->conf_dev,
                   c->stream, &c->lc));
     if (ids_out) CK(cudaMemcpyAsync(ids_out + (size_t)first * VTD_IDS_STRIDE, c->ids_dev, (size_t)nc * VTD_IDS_STRIDE, cudaMemcpyDeviceToHost, c->stream));
     if (len_out) CK(cudaMemcpyAsync(len_out + first, c->len_dev, (size_t)nc * 4, cudaMemcpyDeviceToHost, c->stream));
     if (conf_out) CK(cudaMemcpyAsync(conf_out + first, c->conf_dev, (size_t)nc * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (logits_out) CK(cudaMemcpyAsync(logits_out + (size_t)first * T * 97, c->logits, (size_t)nc * T * 97 * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (logits_out) CK(cudaMemcpy2DAsync(logits_out + (size_t)first * T * 97, 97 * 4, c->logits, (size_t)c->logits_ld * 4, 97 * 4, (size_t)nc * T, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
   return VTD_OK;
@@ -1050,7 +1061,7 @@ int vtd_crnn_forward(vtd_ctx* c, const float* x, int n, float* logits_host) {
     if (c->bf16_mode) CK(nchw_f32_to_nhwc<bf16>(c->stage_f32, (bf16*)c->crops, nc, 3, 32, cw, c->crops_lay, c->stream, &c->lc));
     else CK(nchw_f32_to_nhwc<float>(c->stage_f32, (float*)c->crops, nc, 3, 32, cw, c->crops_lay, c->stream, &c->lc));
     int r = run_crnn(c, nc); if (r) return r;
-    CK(cudaMemcpyAsync(logits_host + (size_t)first * T * 97, c->logits, (size_t)nc * T * 97 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpy2DAsync(logits_host + (size_t)first * T * 97, 97 * 4, c->logits, (size_t)c->logits_ld * 4, 97 * 4, (size_t)nc * T, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
   return VTD_OK;
@@ -1071,7 +1082,7 @@ int vtd_ctc_decode(vtd_ctx* c, const float* x, int B, int T, int V, int is_prob,
   auto cleanup = [&]() { cudaFree(dx); cudaFree(dids); cudaFree(dlen); cudaFree(dconf); };
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { cleanup(); FAIL(VTD_ERR_CUDA, "cudaMalloc failed in vtd_ctc_decode"); }
   cudaError_t e = cudaMemcpyAsync(dx, x, ne * 4, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess) e = ctc_greedy(dx, B, T, V, is_prob, c->cfg.canonical_ctc, dids, VTD_IDS_STRIDE, dlen, dconf, c->stream, &c->lc);
+  if (e == cudaSuccess) e = ctc_greedy(dx, B, T, V, V, is_prob, c->cfg.canonical_ctc, dids, VTD_IDS_STRIDE, dlen, dconf, c->stream, &c->lc);
   if (e == cudaSuccess && ids_out) e = cudaMemcpyAsync(ids_out, dids, (size_t)B * VTD_IDS_STRIDE, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess && len_out) e = cudaMemcpyAsync(len_out, dlen, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream);
   if (e == cudaSuccess && conf_out) e = cudaMemcpyAsync(conf_out, dconf, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream);

@@ -230,127 +230,145 @@ struct GeoParams {
   int pool_words;           // per-plane scratch pool size, 4-byte words
 };
 
-__global__ void geometry_kernel(const uint8_t* __restrict__ mask, CompArrays ca, CandArrays cd, GeoParams gp,
-                                int* __restrict__ pool, int* __restrict__ pool_used, TmpBox* __restrict__ tmp,
-                                int* __restrict__ overflow) {
+// One WARP per candidate.  The candidate's bounding box of the mask (+1 px border) is staged in shared memory, so
+// the inherently sequential outer-border trace runs against ~25-cycle shared-memory probes instead of L2 round
+// trips; per-row extremes come from the label plane in parallel (lanes stride over x); lane 0 then runs the hull /
+// rotating-calipers arithmetic (O(#rows), scratch in shared memory), and the whole warp reduces the mean
+// probability of the resulting box.  Components too large for the per-warp budget fall back to global scratch.
+constexpr int GW = 4;                    // candidates (warps) per CTA
+constexpr int GSMEM = 16 * 1024;         // shared-memory bytes per candidate
+
+__global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __restrict__ mask,
+                                                           const int* __restrict__ labels,
+                                                           const float* __restrict__ prob, CompArrays ca, CandArrays cd,
+                                                           GeoParams gp, int* __restrict__ pool,
+                                                           int* __restrict__ pool_used, TmpBox* __restrict__ tmp,
+                                                           int* __restrict__ overflow) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.y;
   const int nc = min(cd.count[f], cd.kc);
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * GW + warp;
   if (c >= nc) return;
   TmpBox& tb = tmp[(size_t)f * cd.kc + c];
-  tb.valid = 0;
+  if (lane == 0) tb.valid = 0;
   const int s = cd.slot[(size_t)f * cd.kc + c];
   const size_t o = (size_t)f * ca.cap + s;
   const int start = ca.start[o];
-  const int x0 = start % gp.mw, y0 = start / gp.mw;
-  const int nrows = ca.ymax[o] - y0 + 1;
-  const int need = 12 * nrows + 16;
-  const int off = atomicAdd(pool_used + f, need);
-  if (off + need > gp.pool_words) { atomicExch(overflow, 1); return; }
-  int* base = pool + (size_t)f * gp.pool_words + off;
-  int* rowmin = base;
-  int* rowmax = base + nrows;
-  Pt* hull = reinterpret_cast<Pt*>(base + 2 * nrows);
-  float* fl = reinterpret_cast<float*>(base + 2 * nrows + 2 * (2 * nrows + 2));
-  for (int r = 0; r < nrows; ++r) { rowmin[r] = 1 << 30; rowmax[r] = -1; }
-
-  const uint8_t* m = mask + (size_t)f * gp.mh * gp.mw;
   const int mw = gp.mw, mh = gp.mh;
-  auto fg = [&](int x, int y) -> bool {
-    return (unsigned)x < (unsigned)mw && (unsigned)y < (unsigned)mh && m[y * mw + x] != 0;
-  };
-  // border trace: area and row extremes (every hull vertex is a border pixel)
-  long long area2;
-  {
-    const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-    const int dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
-    int sdir = 4, s_end = 4, x1, y1;
-    do { sdir = (sdir - 1) & 7; x1 = x0 + dx[sdir]; y1 = y0 + dy[sdir]; } while (!fg(x1, y1) && sdir != s_end);
-    rowmin[0] = x0; rowmax[0] = x0;
-    if (sdir == s_end) return;              // isolated pixel (cannot pass the bbox filter, but be safe)
-    area2 = 0;
-    int x3 = x0, y3 = y0;
-    const long long max_steps = 8LL * mw * mh;
-    long long steps = 0;
-    for (;;) {
-      int x4, y4;
-      for (;;) { ++sdir; x4 = x3 + dx[sdir & 7]; y4 = y3 + dy[sdir & 7]; if (fg(x4, y4)) break; }
-      sdir &= 7;
-      area2 += (long long)x3 * y4 - (long long)x4 * y3;
-      int r = y4 - y0;
-      if (r >= 0 && r < nrows) { if (x4 < rowmin[r]) rowmin[r] = x4; if (x4 > rowmax[r]) rowmax[r] = x4; }
-      ++steps;
-      if ((x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) || steps >= max_steps) break;
-      x3 = x4; y3 = y4;
-      sdir = (sdir + 4) & 7;
+  const int x0 = start % mw, y0 = start / mw;
+  const int xmin = ca.xmin[o], xmax = ca.xmax[o];
+  const int nrows = ca.ymax[o] - y0 + 1;
+  const int rw = xmax - xmin + 3, rh = nrows + 2;          // staged region incl. 1 px border
+  const int bx0 = xmin - 1, by0 = y0 - 1;
+  const int mask_bytes = (rw * rh + 15) & ~15;
+  const int scratch_words = 12 * nrows + 16;
+  const bool use_smem = mask_bytes + 4 * scratch_words <= GSMEM;
+  uint8_t* sm_mask = gsm + warp * GSMEM;
+  int* scr;
+  if (use_smem) {
+    scr = reinterpret_cast<int*>(sm_mask + mask_bytes);
+  } else {
+    int off = 0;
+    if (lane == 0) off = atomicAdd(pool_used + f, scratch_words);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off + scratch_words > gp.pool_words) { if (lane == 0) atomicExch(overflow, 1); return; }
+    scr = pool + (size_t)f * gp.pool_words + off;
+  }
+  int* rowmin = scr;
+  int* rowmax = scr + nrows;
+  Pt* hull = reinterpret_cast<Pt*>(scr + 2 * nrows);
+  float* fl = reinterpret_cast<float*>(scr + 2 * nrows + 2 * (2 * nrows + 2));
+  const uint8_t* m = mask + (size_t)f * mh * mw;
+  const int* L = labels + (size_t)f * mh * mw;
+
+  if (use_smem) {
+    for (int i = lane; i < rw * rh; i += 32) {
+      const int yy = i / rw, xx = i - yy * rw;
+      const int gx = bx0 + xx, gy = by0 + yy;
+      sm_mask[i] = ((unsigned)gx < (unsigned)mw && (unsigned)gy < (unsigned)mh) ? m[gy * mw + gx] : (uint8_t)0;
     }
   }
-  if (area2 < 0) area2 = -area2;
-  if (area2 < 200) return;                  // cv2.contourArea(contour) < 100 -> skip (text_detector.py:150)
-  // rows the outer border never visits cannot exist inside [y0, ymax] of an 8-connected component, but a
-  // row may be visited only by the border of a *different* lobe; the extremes above are over the whole
-  // outer border, which is what the hull needs.
-  for (int r = 0; r < nrows; ++r)
-    if (rowmax[r] < 0) { rowmin[r] = rowmin[r > 0 ? r - 1 : 0]; rowmax[r] = rowmax[r > 0 ? r - 1 : 0]; }
-  int nh = hull_from_rows(rowmin, rowmax, y0, nrows, hull);
-  if (nh < 3) return;
-  RotRect rr = min_area_rect(hull, nh, fl, fl + nh, fl + 2 * nh);
-  unclip_rect(rr, gp.unclip);
-  PtF bp[4];
-  box_points(rr, bp);
-  int xs[4], ys[4];
+  // per-row extremes of THIS component (label == raster index of its first pixel)
+  for (int r = 0; r < nrows; ++r) {
+    int lo = 1 << 30, hi = -1;
+    const int* row = L + (size_t)(y0 + r) * mw;
+    for (int x = xmin + lane; x <= xmax; x += 32)
+      if (row[x] == start) { lo = min(lo, x); hi = max(hi, x); }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {             // np.int0: truncation toward zero (text_detector.py:155)
-    xs[k] = (int)bp[k].x; ys[k] = (int)bp[k].y;
-    tb.poly[2 * k] = xs[k]; tb.poly[2 * k + 1] = ys[k];
+    for (int d = 16; d > 0; d >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if (lane == 0) { rowmin[r] = lo; rowmax[r] = hi; }
   }
-  int bx1 = min(min(xs[0], xs[1]), min(xs[2], xs[3])), bx2 = max(max(xs[0], xs[1]), max(xs[2], xs[3]));
-  int by1 = min(min(ys[0], ys[1]), min(ys[2], ys[3])), by2 = max(max(ys[0], ys[1]), max(ys[2], ys[3]));
-  bx1 = max(0, bx1); by1 = max(0, by1);                       // :160
-  bx2 = min(gp.clip_w, bx2); by2 = min(gp.clip_h, by2);       // :161
-  int X1 = (int)((double)((long long)bx1 * gp.orig_w) / (double)gp.clip_w);   // :163-166
-  int Y1 = (int)((double)((long long)by1 * gp.orig_h) / (double)gp.clip_h);
-  int X2 = (int)((double)((long long)bx2 * gp.orig_w) / (double)gp.clip_w);
-  int Y2 = (int)((double)((long long)by2 * gp.orig_h) / (double)gp.clip_h);
-  if (!(X2 - X1 > 10 && Y2 - Y1 > 10)) return;                // :168
-  tb.bbox[0] = X1; tb.bbox[1] = Y1; tb.bbox[2] = X2; tb.bbox[3] = Y2;
-  // :169-170  prob_map[y1*640//oh : y2*640//oh, x1*640//ow : x2*640//ow]  (numpy slice clamps to the plane)
-  long long cy0 = (long long)Y1 * gp.clip_h / gp.orig_h, cy1 = (long long)Y2 * gp.clip_h / gp.orig_h;
-  long long cx0 = (long long)X1 * gp.clip_w / gp.orig_w, cx1 = (long long)X2 * gp.clip_w / gp.orig_w;
-  tb.cy0 = (int)min(cy0, (long long)mh); tb.cy1 = (int)min(cy1, (long long)mh);
-  tb.cx0 = (int)min(cx0, (long long)mw); tb.cx1 = (int)min(cx1, (long long)mw);
-  tb.start = start;
-  tb.conf = 0.f;
-  tb.valid = 1;
-}
+  __syncwarp();
 
-// ---- 9. mean probability inside the box: one warp per candidate
-__global__ void confidence_kernel(const float* __restrict__ prob, CandArrays cd, GeoParams gp,
-                                  TmpBox* __restrict__ tmp) {
-  const int f = blockIdx.y;
-  const int nc = min(cd.count[f], cd.kc);
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= nc) return;
-  TmpBox& tb = tmp[(size_t)f * cd.kc + c];
-  if (!tb.valid) return;
-  const int h = tb.cy1 - tb.cy0, w = tb.cx1 - tb.cx0;
+  int ok = 0;
+  if (lane == 0) {
+    do {
+      auto fg_s = [&](int x, int y) -> bool { return sm_mask[(y - by0) * rw + (x - bx0)] != 0; };
+      auto fg_g = [&](int x, int y) -> bool {
+        return (unsigned)x < (unsigned)mw && (unsigned)y < (unsigned)mh && m[y * mw + x] != 0;
+      };
+      const long long max_steps = 8LL * mw * mh;
+      long long area2 = use_smem ? trace_outer_area2(fg_s, x0, y0, max_steps, nullptr)
+                                 : trace_outer_area2(fg_g, x0, y0, max_steps, nullptr);
+      if (area2 < 0) area2 = -area2;
+      if (area2 < 200) break;                  // cv2.contourArea(contour) < 100 -> skip (text_detector.py:150)
+      int nh = hull_from_rows(rowmin, rowmax, y0, nrows, hull);
+      if (nh < 3) break;
+      RotRect rr = min_area_rect(hull, nh, fl, fl + nh, fl + 2 * nh);
+      unclip_rect(rr, gp.unclip);
+      PtF bp[4];
+      box_points(rr, bp);
+      int xs[4], ys[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {             // np.int0: truncation toward zero (text_detector.py:155)
+        xs[k] = (int)bp[k].x; ys[k] = (int)bp[k].y;
+        tb.poly[2 * k] = xs[k]; tb.poly[2 * k + 1] = ys[k];
+      }
+      int bx1 = min(min(xs[0], xs[1]), min(xs[2], xs[3])), bx2 = max(max(xs[0], xs[1]), max(xs[2], xs[3]));
+      int by1 = min(min(ys[0], ys[1]), min(ys[2], ys[3])), by2 = max(max(ys[0], ys[1]), max(ys[2], ys[3]));
+      bx1 = max(0, bx1); by1 = max(0, by1);                       // :160
+      bx2 = min(gp.clip_w, bx2); by2 = min(gp.clip_h, by2);       // :161
+      int X1 = (int)((double)((long long)bx1 * gp.orig_w) / (double)gp.clip_w);   // :163-166
+      int Y1 = (int)((double)((long long)by1 * gp.orig_h) / (double)gp.clip_h);
+      int X2 = (int)((double)((long long)bx2 * gp.orig_w) / (double)gp.clip_w);
+      int Y2 = (int)((double)((long long)by2 * gp.orig_h) / (double)gp.clip_h);
+      if (!(X2 - X1 > 10 && Y2 - Y1 > 10)) break;                 // :168
+      tb.bbox[0] = X1; tb.bbox[1] = Y1; tb.bbox[2] = X2; tb.bbox[3] = Y2;
+      // :169-170  prob_map[y1*640//oh : y2*640//oh, x1*640//ow : x2*640//ow]  (numpy slice clamps to the plane)
+      long long cy0 = (long long)Y1 * gp.clip_h / gp.orig_h, cy1 = (long long)Y2 * gp.clip_h / gp.orig_h;
+      long long cx0 = (long long)X1 * gp.clip_w / gp.orig_w, cx1 = (long long)X2 * gp.clip_w / gp.orig_w;
+      tb.cy0 = (int)min(cy0, (long long)mh); tb.cy1 = (int)min(cy1, (long long)mh);
+      tb.cx0 = (int)min(cx0, (long long)mw); tb.cx1 = (int)min(cx1, (long long)mw);
+      tb.start = start;
+      ok = 1;
+    } while (false);
+  }
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok) return;
+  // mean probability inside the box (np.mean of the slice; empty slice -> nan)
+  const int cy0 = __shfl_sync(0xffffffffu, tb.cy0, 0), cy1 = __shfl_sync(0xffffffffu, tb.cy1, 0);
+  const int cx0 = __shfl_sync(0xffffffffu, tb.cx0, 0), cx1 = __shfl_sync(0xffffffffu, tb.cx1, 0);
+  const int h = cy1 - cy0, w = cx1 - cx0;
   float res;
   if (h <= 0 || w <= 0) {
-    res = __int_as_float(0x7fc00000);        // np.mean of an empty slice is nan
+    res = __int_as_float(0x7fc00000);
   } else {
-    const float* p = prob + (size_t)f * gp.mh * gp.mw;
+    const float* p = prob + (size_t)f * mh * mw;
     double acc = 0.0;
-    for (int y = tb.cy0; y < tb.cy1; ++y) {
+    for (int y = cy0; y < cy1; ++y) {
       float rs = 0.f;
-      for (int x = tb.cx0 + lane; x < tb.cx1; x += 32) rs += p[(size_t)y * gp.mw + x];
+      for (int x = cx0 + lane; x < cx1; x += 32) rs += p[(size_t)y * mw + x];
       acc += (double)rs;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     res = (float)(acc / ((double)h * (double)w));
   }
-  if (lane == 0) tb.conf = res;
+  if (lane == 0) { tb.conf = res; __threadfence_block(); tb.valid = 1; }
 }
 
 // ---- 10. order by raster start, keep kmax, write records.  One CTA per plane.
@@ -456,10 +474,16 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
   run_extents_kernel<<<dim3(gx, n), 256, 0, s>>>(mask, labels, slot_plane, ca, mh, mw);
   select_kernel<<<dim3(min(cdiv(lay.cap, 256), 148), n), 256, 0, s>>>(ca, cd, mw);
   GeoParams gp{mh, mw, p.clip_h, p.clip_w, p.orig_h, p.orig_w, p.unclip, lay.pool_words};
-  geometry_kernel<<<dim3(cdiv(lay.kc, 32), n), 32, 0, s>>>(mask, ca, cd, gp, pool, pool_used, tmp, overflow);
-  confidence_kernel<<<dim3(cdiv((long long)lay.kc * 32, 128), n), 128, 0, s>>>(prob, cd, gp, tmp);
+  static bool geo_attr = false;
+  if (!geo_attr) {
+    cudaError_t ge = cudaFuncSetAttribute(geometry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW * GSMEM);
+    if (ge != cudaSuccess) return ge;
+    geo_attr = true;
+  }
+  geometry_kernel<<<dim3(cdiv(lay.kc, GW), n), GW * 32, GW * GSMEM, s>>>(mask, labels, prob, ca, cd, gp, pool, pool_used,
+                                                                        tmp, overflow);
   pack_kernel<<<n, 256, 0, s>>>(cd, tmp, reinterpret_cast<vtd_record*>(records), counts, p.kmax, overflow);
-  if (lc) lc->n += (mh > 1 ? 10 : 9);
+  if (lc) lc->n += (mh > 1 ? 9 : 8);
   return cudaGetLastError();
 }
 

@@ -75,8 +75,10 @@ inline OutLayout padded_layout(int H, int W, int cpp, int pt, int pb, int pl, in
 }
 template <typename T>
 cudaError_t preprocess_frames(const uint8_t* const* frames_dev /*device array of n pointers*/, int n, int h, int w,
-                              int pitch, int pixfmt, const ResizeTab& tx, const ResizeTab& ty, uint8_t* tmp_u8,
-                              T* out /*4 channels per pixel*/, OutLayout lay, cudaStream_t s, LaunchCounter* lc);
+                              int pitch, int pixfmt, const ResizeTab& tx, const ResizeTab& ty,
+                              const float* lut /*[3][256], build_normalize_lut*/, T* out /*4 channels per pixel*/,
+                              OutLayout lay, cudaStream_t s, LaunchCounter* lc);
+cudaError_t build_normalize_lut(float* lut_dev /*768 floats*/, cudaStream_t s);
 
 // ---- fused DB head tail ----------------------------------------------------------------------------
 struct HeadTailWeights {     // both branches; fp32
@@ -129,10 +131,10 @@ cudaError_t bilstm_layer(const float* xproj, const WT* whh, T* out, float* hbuf,
                          int H, cudaStream_t s, LaunchCounter* lc);
 
 // ---- CTC --------------------------------------------------------------------------------------------------
-cudaError_t ctc_greedy(const float* x /*[B,T,V]*/, int B, int T, int V, int is_prob, int canonical,
+cudaError_t ctc_greedy(const float* x /*[B,T,ld], V <= ld*/, int B, int T, int V, int ld, int is_prob, int canonical,
                        uint8_t* ids /*[B][ids_stride]*/, int ids_stride, int* lens, float* conf, cudaStream_t s,
                        LaunchCounter* lc);
-cudaError_t ctc_into_records(const float* logits, int n_crops, int first_crop, int T, int V, int canonical,
+cudaError_t ctc_into_records(const float* logits, int n_crops, int first_crop, int T, int V, int ld, int canonical,
                              const int* offsets, int n, int kmax, void* records, cudaStream_t s, LaunchCounter* lc);
 
 // ---- layout helpers ----------------------------------------------------------------------------------------

@@ -75,7 +75,7 @@ __device__ __forceinline__ void collapse(const int* ids_t, const float* pm_t, in
   *conf_out = len > 0 ? (float)(csum / (double)len) : 0.f;
 }
 
-__global__ void __launch_bounds__(128) ctc_kernel(const float* __restrict__ x, int B, int T, int V, int is_prob,
+__global__ void __launch_bounds__(128) ctc_kernel(const float* __restrict__ x, int B, int T, int V, int ld, int is_prob,
                                                   int canonical, uint8_t* __restrict__ ids, int ids_stride,
                                                   int* __restrict__ lens, float* __restrict__ conf) {
   __shared__ int s_idx[4][MAXT];
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) ctc_kernel(const float* __restrict__ x, i
   if (b >= B) return;
   for (int t = 0; t < T; ++t) {
     int bi; float pm;
-    row_argmax(x + ((size_t)b * T + t) * V, V, is_prob, lane, &bi, &pm);
+    row_argmax(x + ((size_t)b * T + t) * ld, V, is_prob, lane, &bi, &pm);
     if (lane == 0) { s_idx[wid][t] = bi; s_pm[wid][t] = pm; }
   }
   __syncwarp();
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) ctc_kernel(const float* __restrict__ x, i
 
 // same, but the result lands in the vtd_record of the crop (crop ci of the chunk <-> record via offsets)
 __global__ void __launch_bounds__(128) ctc_records_kernel(const float* __restrict__ x, int n_crops, int first_crop,
-                                                          int T, int V, int canonical,
+                                                          int T, int V, int ld, int canonical,
                                                           const int* __restrict__ offsets, int n, int kmax,
                                                           vtd_record* __restrict__ records) {
   __shared__ int s_idx[4][MAXT];
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(128) ctc_records_kernel(const float* __restric
   if (b >= n_crops) return;
   for (int t = 0; t < T; ++t) {
     int bi; float pm;
-    row_argmax(x + ((size_t)b * T + t) * V, V, 0, lane, &bi, &pm);
+    row_argmax(x + ((size_t)b * T + t) * ld, V, 0, lane, &bi, &pm);
     if (lane == 0) { s_idx[wid][t] = bi; s_pm[wid][t] = pm; }
   }
   __syncwarp();
@@ -122,20 +122,20 @@ __global__ void __launch_bounds__(128) ctc_records_kernel(const float* __restric
 
 }  // namespace
 
-cudaError_t ctc_greedy(const float* x, int B, int T, int V, int is_prob, int canonical, uint8_t* ids, int ids_stride,
-                       int* lens, float* conf, cudaStream_t s, LaunchCounter* lc) {
+cudaError_t ctc_greedy(const float* x, int B, int T, int V, int ld, int is_prob, int canonical, uint8_t* ids,
+                       int ids_stride, int* lens, float* conf, cudaStream_t s, LaunchCounter* lc) {
   if (B <= 0) return cudaSuccess;
   if (T > MAXT || T <= 0 || V <= 1) return cudaErrorInvalidValue;
-  ctc_kernel<<<(B + 3) / 4, 128, 0, s>>>(x, B, T, V, is_prob, canonical, ids, ids_stride, lens, conf);
+  ctc_kernel<<<(B + 3) / 4, 128, 0, s>>>(x, B, T, V, ld, is_prob, canonical, ids, ids_stride, lens, conf);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
 
-cudaError_t ctc_into_records(const float* logits, int n_crops, int first_crop, int T, int V, int canonical,
+cudaError_t ctc_into_records(const float* logits, int n_crops, int first_crop, int T, int V, int ld, int canonical,
                              const int* offsets, int n, int kmax, void* records, cudaStream_t s, LaunchCounter* lc) {
   if (n_crops <= 0) return cudaSuccess;
   if (T > MAXT || T <= 0) return cudaErrorInvalidValue;
-  ctc_records_kernel<<<(n_crops + 3) / 4, 128, 0, s>>>(logits, n_crops, first_crop, T, V, canonical, offsets, n, kmax,
+  ctc_records_kernel<<<(n_crops + 3) / 4, 128, 0, s>>>(logits, n_crops, first_crop, T, V, ld, canonical, offsets, n, kmax,
                                                       reinterpret_cast<vtd_record*>(records));
   if (lc) lc->n++;
   return cudaGetLastError();

@@ -45,7 +45,8 @@ __device__ __forceinline__ int nv12_bgr(const uint8_t* f, int h, int pitch, int 
 template <typename T, int PIX>
 __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __restrict__ frames, int h, int w,
                                                         int pitch, ResizeTab tx, ResizeTab ty, int rows_cap,
-                                                        int srcb_cap, T* __restrict__ out, OutLayout lay) {
+                                                        int srcb_cap, const float* __restrict__ lut_g,
+                                                        T* __restrict__ out, OutLayout lay) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int ksx = tx.ksize, ksy = ty.ksize;
   int* sx_lo = reinterpret_cast<int*>(smem);
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
   int* sy_lo = sx_k + TW * ksx;
   int* sy_cnt = sy_lo + TH;
   int* sy_k = sy_cnt + TH;
-  uint8_t* src = reinterpret_cast<uint8_t*>(sy_k + TH * ksy);
+  float* lut = reinterpret_cast<float*>(sy_k + TH * ksy);          // [3][256]: u8 -> (x/255 - mean)/std, IEEE fp32
+  uint8_t* src = reinterpret_cast<uint8_t*>(lut + 768);
   uint8_t* tmp = src + (size_t)rows_cap * srcb_cap;
 
   const uint8_t* __restrict__ f = frames[blockIdx.z];
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
   for (int i = tid; i < tw * ksx; i += NT) sx_k[i] = tx.kk[(size_t)ox0 * ksx + i];
   for (int i = tid; i < th; i += NT) { sy_lo[i] = ty.lo[oy0 + i]; sy_cnt[i] = ty.cnt[oy0 + i]; }
   for (int i = tid; i < th * ksy; i += NT) sy_k[i] = ty.kk[(size_t)oy0 * ksy + i];
+  for (int i = tid; i < 768; i += NT) lut[i] = __ldg(lut_g + i);
   const int r0 = ty.lo[oy0];
   const int r1 = ty.lo[oy0 + th - 1] + ty.cnt[oy0 + th - 1];       // exclusive (lo is non-decreasing)
   const int rows = min(r1 - r0, rows_cap);
@@ -110,61 +113,69 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
   }
   __syncthreads();
 
-  // ---- horizontal pass: items = rows x tw x 3
-  for (int it = tid; it < rows * tw * 3; it += NT) {
-    const int c = it % 3;
-    const int qx = it / 3;
-    const int xo = qx % tw, r = qx / tw;
-    const int lo = sx_lo[xo], cnt = sx_cnt[xo];
-    const int* kk = sx_k + xo * ksx;
+  // ---- horizontal pass: one item = (source row, output column), all three channels; warps walk rows, lanes columns
+  for (int r = tid >> 5; r < rows; r += NT / 32) {
     int skew = 0;
-    if (PIX == 0) {
-      const uint8_t* row = f + (size_t)(r0 + r) * pitch;
-      skew = (int)((reinterpret_cast<size_t>(row) + c0 * 3) & 15);
+    if (PIX == 0) skew = (int)((reinterpret_cast<size_t>(f + (size_t)(r0 + r) * pitch) + c0 * 3) & 15);
+    const uint8_t* rowp = src + (size_t)r * srcb_cap + skew - c0 * 3;
+    for (int xo = tid & 31; xo < tw; xo += 32) {
+      const int lo = sx_lo[xo], cnt = sx_cnt[xo];
+      const int* kk = sx_k + xo * ksx;
+      const uint8_t* p = rowp + lo * 3;
+      int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+      for (int j = 0; j < cnt; ++j) {
+        const int k = kk[j];
+        a0 += (int)p[j * 3] * k; a1 += (int)p[j * 3 + 1] * k; a2 += (int)p[j * 3 + 2] * k;
+      }
+      uint8_t* t = tmp + (r * TW + xo) * 3;
+      t[0] = (uint8_t)clip8(a0 >> 22); t[1] = (uint8_t)clip8(a1 >> 22); t[2] = (uint8_t)clip8(a2 >> 22);
     }
-    const uint8_t* p = src + (size_t)r * srcb_cap + skew + (lo - c0) * 3 + c;
-    int acc = 1 << 21;
-    for (int j = 0; j < cnt; ++j) acc += (int)p[j * 3] * kk[j];
-    tmp[(r * TW + xo) * 3 + c] = (uint8_t)clip8(acc >> 22);
   }
   __syncthreads();
 
-  // ---- vertical pass + normalise: items = th x tw pixels
-  for (int it = tid; it < th * tw; it += NT) {
-    const int xo = it % tw, yo = it / tw;
+  // ---- vertical pass + normalise: items = th x TW pixels
+  for (int it = tid; it < th * TW; it += NT) {
+    const int xo = it & (TW - 1), yo = it / TW;
+    if (xo >= tw) continue;
     const int oy = oy0 + yo;
     const int lo = sy_lo[yo] - r0, cnt = sy_cnt[yo];
     const int* kk = sy_k + yo * ksy;
     int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+    const uint8_t* p = tmp + (lo * TW + xo) * 3;
     for (int j = 0; j < cnt; ++j) {
-      const uint8_t* p = tmp + ((lo + j) * TW + xo) * 3;
       const int k = kk[j];
       a0 += (int)p[0] * k; a1 += (int)p[1] * k; a2 += (int)p[2] * k;
+      p += TW * 3;
     }
-    // source order is B,G,R; the network wants R,G,B (cvtColor at text_detector.py:120)
-    float b = (float)clip8(a0 >> 22), g = (float)clip8(a1 >> 22), r = (float)clip8(a2 >> 22);
-    // ToTensor: x/255 (fp32 divide); Normalize: (x-mean)/std (fp32 subtract, fp32 divide) -- IEEE, no fast-math
-    float v[4];
-    v[0] = __fdiv_rn(__fsub_rn(__fdiv_rn(r, 255.0f), 0.485f), 0.229f);
-    v[1] = __fdiv_rn(__fsub_rn(__fdiv_rn(g, 255.0f), 0.456f), 0.224f);
-    v[2] = __fdiv_rn(__fsub_rn(__fdiv_rn(b, 255.0f), 0.406f), 0.225f);
-    v[3] = 0.f;
+    // source order is B,G,R; the network wants R,G,B (cvtColor at text_detector.py:120).  The table holds, per
+    // channel, ToTensor (x/255) followed by Normalize ((x-mean)/std) evaluated with IEEE fp32 ops (see lut kernel).
+    const float vr = lut[clip8(a2 >> 22)], vg = lut[256 + clip8(a1 >> 22)], vb = lut[512 + clip8(a0 >> 22)];
     size_t o = (size_t)(lay.offset + blockIdx.z * lay.img_pitch + oy * lay.row_pitch + (long long)(ox0 + xo) * 4);
     if (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(vr, vg, vb, 0.f);
     } else {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(vr, vg), p1 = __floats2bfloat162_rn(vb, 0.f);
       uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + o) = u;
     }
   }
 }
 
+__global__ void normalize_lut_kernel(float* __restrict__ lut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 768) return;
+  const int c = i >> 8;
+  const float x = (float)(i & 255);
+  const float mean = c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+  const float sd = c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+  lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn(x, 255.0f), mean), sd);
+}
+
 }  // namespace
 
 template <typename T>
 cudaError_t preprocess_frames(const uint8_t* const* frames_dev, int n, int h, int w, int pitch, int pixfmt,
-                              const ResizeTab& tx, const ResizeTab& ty, uint8_t* /*tmp_u8*/, T* out, OutLayout lay,
+                              const ResizeTab& tx, const ResizeTab& ty, const float* lut, T* out, OutLayout lay,
                               cudaStream_t s, LaunchCounter* lc) {
   if (n <= 0) return cudaSuccess;
   // source rows / columns one tile can need: T output samples span at most T*scale + ksize source samples
@@ -173,7 +184,7 @@ cudaError_t preprocess_frames(const uint8_t* const* frames_dev, int n, int h, in
   const int cols_cap = (int)(TW * (sx > 1.0 ? sx : 1.0)) + tx.ksize + 2;
   const int srcb_cap = ((cols_cap * 3 + 15 + 15) / 16 + 1) * 16;          // + alignment skew, rounded to 16 bytes
   size_t smem = sizeof(int) * (size_t)(2 * TW + TW * tx.ksize + 2 * TH + TH * ty.ksize);
-  smem = (smem + 15) & ~(size_t)15;
+  smem = ((smem + 15) & ~(size_t)15) + 768 * sizeof(float);
   smem += (size_t)rows_cap * srcb_cap + (size_t)rows_cap * TW * 3 + 16;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   dim3 grid((tx.out_size + TW - 1) / TW, (ty.out_size + TH - 1) / TH, n);
@@ -183,21 +194,26 @@ cudaError_t preprocess_frames(const uint8_t* const* frames_dev, int n, int h, in
       e = cudaFuncSetAttribute(preprocess_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    preprocess_kernel<T, 0><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, srcb_cap, out, lay);
+    preprocess_kernel<T, 0><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, srcb_cap, lut, out, lay);
   } else {
     if (smem > 48 * 1024) {
       e = cudaFuncSetAttribute(preprocess_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    preprocess_kernel<T, 1><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, srcb_cap, out, lay);
+    preprocess_kernel<T, 1><<<grid, NT, smem, s>>>(frames_dev, h, w, pitch, tx, ty, rows_cap, srcb_cap, lut, out, lay);
   }
   if (lc) lc->n++;
   return cudaGetLastError();
 }
 
 template cudaError_t preprocess_frames<float>(const uint8_t* const*, int, int, int, int, int, const ResizeTab&,
-                                              const ResizeTab&, uint8_t*, float*, OutLayout, cudaStream_t, LaunchCounter*);
+                                              const ResizeTab&, const float*, float*, OutLayout, cudaStream_t, LaunchCounter*);
 template cudaError_t preprocess_frames<bf16>(const uint8_t* const*, int, int, int, int, int, const ResizeTab&,
-                                             const ResizeTab&, uint8_t*, bf16*, OutLayout, cudaStream_t, LaunchCounter*);
+                                             const ResizeTab&, const float*, bf16*, OutLayout, cudaStream_t, LaunchCounter*);
+
+cudaError_t build_normalize_lut(float* lut_dev, cudaStream_t s) {
+  normalize_lut_kernel<<<3, 256, 0, s>>>(lut_dev);
+  return cudaGetLastError();
+}
 
 }  // namespace vtd
