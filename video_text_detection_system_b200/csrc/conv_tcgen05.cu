@@ -67,6 +67,7 @@ struct TcParams {
   const float* bias;
   const bf16* res;
   void* out;
+  int stages, bres;           // operand ring depth; 1 = all weight K-slices stay resident in shared memory
   // MODE_WIN
   int nr, sdiv;               // filter rows (= K steps), row phases (= conv stride)
   // MODE_DBHEAD
@@ -199,9 +200,14 @@ struct TcCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * ROWB;
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = MODE == MODE_WIN ? 12 : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr int MAX_STAGES = 16;
+  static constexpr int TAIL_BYTES = 8 * (2 * MAX_STAGES + 6) + 16 + (MODE == MODE_DBHEAD ? 4096 : 0);   // barriers, TMEM slot, head consts
+  // dynamic shared memory for a given ring depth / resident-weight size
+  static constexpr int smem_bytes(int stages, int bres_bytes) {
+    return stages * (bres_bytes ? A_BYTES : STAGE_BYTES) + bres_bytes + 1024 /*alignment slack*/ + TAIL_BYTES;
+  }
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/ +
-                                    (MODE == MODE_DBHEAD ? 4096 : 0) /*head constants*/;
+
 };
 
 
@@ -334,6 +340,18 @@ __device__ __forceinline__ void epilogue_dbhead(const TcParams& p, const float* 
   }
 }
 
+// pull this thread's input-projection and cell-state lines towards L2 while the MMAs of the step run
+__device__ __forceinline__ void lstm_prefetch(const TcParams& p, int half, int b, int nb) {
+  if (b >= p.lstm_B) return;
+  const int dir = nb >> 2, jt = nb & 3;
+  const int t = dir == 0 ? p.lstm_step : p.lstm_T - 1 - p.lstm_step;
+  const float* xp = p.xproj + (((size_t)b * p.lstm_T + t) * 2 + dir) * 1024 + jt * 256 + half * 32;
+  const float* cs = p.cbuf + ((size_t)dir * p.lstm_Bcap + b) * 256 + jt * 64 + half * 32;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + g * 64));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(cs));
+}
+
 // MODE_LSTM: gates -> cell update.  Tile columns = [i(64) | f(64) | g(64) | o(64)] of hidden units jt*64..+63.
 __device__ __forceinline__ void epilogue_lstm(const TcParams& p, uint32_t tmem_acc, int q, int half, int b, int nb) {
   const int dir = nb >> 2, jt = nb & 3;
@@ -400,13 +418,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t ring = (raw + 1023u) & ~1023u;
   uint8_t* ring_ptr = smem_raw + (ring - raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + Cfg::STAGES * Cfg::STAGE_BYTES);
-  const uint32_t full0 = smem_u32(bars);                       // [STAGES]
-  const uint32_t empty0 = full0 + 8 * Cfg::STAGES;             // [STAGES]
-  const uint32_t tfull0 = empty0 + 8 * Cfg::STAGES;            // [2]
+  const int stages = p.stages;
+  const uint32_t stage_bytes = p.bres ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
+  const int ksteps_all = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
+  const uint32_t bres0 = ring + stages * stage_bytes;                       // resident weight K-slices (if p.bres)
+  const uint32_t bres_bytes = p.bres ? (uint32_t)ksteps_all * Cfg::B_STAGE_BYTES : 0u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + stages * stage_bytes + bres_bytes);
+  const uint32_t full0 = smem_u32(bars);                       // [MAX_STAGES]
+  const uint32_t empty0 = full0 + 8 * Cfg::MAX_STAGES;         // [MAX_STAGES]
+  const uint32_t tfull0 = empty0 + 8 * Cfg::MAX_STAGES;        // [2]
   const uint32_t tempty0 = tfull0 + 16;                        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
-  float* head_s = reinterpret_cast<float*>(bars + 2 * Cfg::STAGES + 6);   // MODE_DBHEAD: [2 heads][256 b1 + 256 w2]
+  const uint32_t bfull = tempty0 + 16;                         // [1] resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::MAX_STAGES + 5);
+  float* head_s = reinterpret_cast<float*>(bars + 2 * Cfg::MAX_STAGES + 6);   // MODE_DBHEAD: [2 heads][256 b1 + 256 w2]
   if constexpr (MODE == MODE_DBHEAD) {
     for (int i = threadIdx.x; i < 2 * 512; i += NUM_THREADS) {
       const int hd = i >> 9, r = i & 511;
@@ -417,8 +441,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
+    mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
@@ -433,6 +458,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream; global
+  // memory written by that kernel is only touched below.  (No-ops when launched without the attribute.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int BW = 1 << p.lw, BH = 1 << p.lh;
   const int BNt = BLOCK_M >> (p.lw + p.lh);
@@ -443,6 +472,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (p.bres && blockIdx.x < p.total_tiles) {      // weights once per CTA (n_blocks == 1)
+        mbar_expect_tx(bfull, bres_bytes);
+        for (int ks = 0; ks < ksteps_all; ++ks)
+          tma_load_2d(bres0 + ks * Cfg::B_STAGE_BYTES, &maps.b, bfull, ks * (ROWB / 2), 0);
+      }
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         long long t = tile;
         const int nb = (int)(t % p.n_blocks); t /= p.n_blocks;
@@ -452,12 +486,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         if (MODE == MODE_WIN) {
           for (int r = 0; r < p.nr; ++r) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
+            const uint32_t sa = ring + stage * stage_bytes;
             const uint32_t fb = full0 + 8 * stage;
-            mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+            mbar_expect_tx(fb, stage_bytes);
             tma_load_5d(sa, &maps.a[0], fb, 0, x0, r % p.sdiv, y0 + r / p.sdiv, n0);
-            tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, r * 32, nb * BLOCK_N);
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            if (!p.bres) tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, r * 32, nb * BLOCK_N);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         } else {
           for (int r = 0; r < p.KH; ++r) {
@@ -474,12 +508,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
               const int kbase = (r * p.KW + s) * p.Cin;
               for (int kc = 0; kc < kchunks; ++kc) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
+                const uint32_t sa = ring + stage * stage_bytes;
                 const uint32_t fb = full0 + 8 * stage;
-                mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+                mbar_expect_tx(fb, stage_bytes);
                 tma_load_4d(sa, &maps.a[mi], fb, coff + kc * BLOCK_K, x0 + xo, y0 + yo, n0);
-                tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, kbase + kc * BLOCK_K, nb * BLOCK_N);
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                if (!p.bres) tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, kbase + kc * BLOCK_K, nb * BLOCK_N);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
               }
             }
           }
@@ -492,6 +526,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       const uint32_t idesc = umma_idesc(BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       long long it = 0;
+      if (p.bres && blockIdx.x < p.total_tiles) mbar_wait(bfull, 0);
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int as = (int)(it & 1);
         mbar_wait(tempty0 + 8 * as, (uint32_t)((it >> 1) & 1) ^ 1);
@@ -500,13 +535,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full0 + 8 * stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = ring + stage * Cfg::STAGE_BYTES;
-          const uint64_t ad = umma_desc<ROWB>(sa), bd = umma_desc<ROWB>(sa + Cfg::A_BYTES);
+          const uint32_t sa = ring + stage * stage_bytes;
+          const uint64_t ad = umma_desc<ROWB>(sa);
+          const uint64_t bd = umma_desc<ROWB>(p.bres ? bres0 + ks * Cfg::B_STAGE_BYTES : sa + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < ROWB / 32; ++k)
             umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ks | k) ? 1u : 0u);
           umma_commit(empty0 + 8 * stage);              // frees the slot when these MMAs have read it
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull0 + 8 * as);                   // accumulator complete
       }
@@ -533,6 +569,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         epilogue_dbhead(p, head_s + nb * 512, ex.b2[nb], ex.thr, nb, tmem_acc, q, half, valid, n, oy, ox);
       } else if constexpr (MODE == MODE_LSTM) {
+        lstm_prefetch(p, half, ox, nb);
         mbar_wait(tfull_bar, parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         epilogue_lstm(p, tmem_acc, q, half, ox, nb);
@@ -630,7 +667,10 @@ struct TcPlan {
   HeadConsts hc;
   int block_n;
   int mode;
+  int smem;
 };
+
+static void plan_finalize(TcPlan* pl);
 
 bool tc_supported(const ConvDesc& d) {
   if (d.Cin % 64 != 0 || d.Cout % 64 != 0) return false;
@@ -679,6 +719,7 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   }
   CUresult r = encode_weights(enc, &pl->maps.b, d.w, (long long)d.KH * d.KW * d.Cin, d.Cout, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
+  plan_finalize(pl);
   return pl;
 }
 
@@ -711,6 +752,7 @@ TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int s
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(window) failed: " + std::to_string((int)r)); }
   r = encode_weights(enc, &pl->maps.b, w, (long long)nr * 32, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
+  plan_finalize(pl);
   return pl;
 }
 
@@ -737,6 +779,7 @@ TcPlan* tc_plan_create_dbhead(const void* feat, int N, int H4, int W4, const voi
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(head feature) failed: " + std::to_string((int)r)); }
   r = encode_weights(enc, &pl->maps.b, w1, 64, 512, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(head weights) failed: " + std::to_string((int)r)); }
+  plan_finalize(pl);
   return pl;
 }
 
@@ -765,24 +808,67 @@ TcPlan* tc_plan_create_lstm(const void* h_prev, void* h_next, int Bcap, const vo
   }
   CUresult r = encode_weights(enc, &pl->maps.b, whh, 256, 2048, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(W_hh) failed: " + std::to_string((int)r)); }
+  plan_finalize(pl);
   return pl;
 }
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
+constexpr int SMEM_BUDGET = 220 * 1024;     // of the 227 KB a CTA may use
+
+// ring depth / resident weights for a plan (called once per plan, after mode, block_n and p are filled)
 template <int BN, int MODE>
-static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, const typename ExtraOf<MODE>::type& ex, cudaStream_t s) {
+static void plan_smem(TcPlan* pl) {
+  using Cfg = TcCfg<BN, MODE>;
+  TcParams& p = pl->p;
+  const int ksteps = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
+  const int bres_bytes = ksteps * Cfg::B_STAGE_BYTES;
+  const bool can_res = (MODE == MODE_CONV || MODE == MODE_WIN) && p.n_blocks == 1 && bres_bytes <= 96 * 1024;
+  p.bres = can_res ? 1 : 0;
+  if (p.bres) {
+    int st = (SMEM_BUDGET - bres_bytes - 1024 - Cfg::TAIL_BYTES) / Cfg::A_BYTES;
+    p.stages = st > Cfg::MAX_STAGES ? Cfg::MAX_STAGES : st;
+  } else {
+    p.stages = Cfg::STAGES;
+  }
+  pl->smem = Cfg::smem_bytes(p.stages, p.bres ? bres_bytes : 0);
+}
+
+static void plan_finalize(TcPlan* pl) {
+  switch (pl->mode) {
+    case MODE_WIN: plan_smem<64, MODE_WIN>(pl); break;
+    case MODE_DBHEAD: plan_smem<256, MODE_DBHEAD>(pl); break;
+    case MODE_LSTM: plan_smem<256, MODE_LSTM>(pl); break;
+    default:
+      if (pl->block_n == 256) plan_smem<256, MODE_CONV>(pl);
+      else if (pl->block_n == 128) plan_smem<128, MODE_CONV>(pl);
+      else plan_smem<64, MODE_CONV>(pl);
+  }
+}
+
+template <int BN, int MODE>
+static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, const typename ExtraOf<MODE>::type& ex, cudaStream_t s,
+                             bool pdl = false) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcCfg<BN, MODE>::SMEM_BYTES);
+                                         227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   const int sms = sm_count();
   const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
-  conv_tc_kernel<BN, MODE><<<grid, NUM_THREADS, TcCfg<BN, MODE>::SMEM_BYTES, s>>>(pl->maps, p, ex);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = (size_t)pl->smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE>, pl->maps, p, ex);
 }
 
 // n_actual: images (MODE_LSTM: sequences) actually present in this call (<= what the plan was built for)
@@ -827,7 +913,7 @@ cudaError_t lstm_step_tcgen05(const TcPlan* pl, int B, int step, cudaStream_t s,
   p.tiles_x = (B + 127) / 128;
   p.total_tiles = (long long)p.tiles_x * p.n_blocks;
   NoExtra none{0};
-  cudaError_t e = launch_tc<256, MODE_LSTM>(pl, p, none, s);
+  cudaError_t e = launch_tc<256, MODE_LSTM>(pl, p, none, s, /*pdl=*/step > 0);
   if (lc) lc->n++;
   return e;
 }
