@@ -40,6 +40,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace vtd {
 
@@ -89,6 +90,16 @@ template <int MODE> struct ExtraOf { typedef NoExtra type; };
 template <> struct ExtraOf<MODE_DBHEAD> { typedef HeadConsts type; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One lane of a CONVERGED warp (elect.sync).  The TMA / MMA role warps stay converged and predicate only the
+// issuing instructions on this: ptxas then emits straight UTMALDG / UTCHMMA sequences.  (Issuing them from a
+// divergent `if (lane == 0)` region made it wrap every such instruction in an ELECT / BRA.U.ANY loop, and the
+// single-thread issue loop -- ~650 cycles per K step -- bounded every layer whose MMAs are short.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -201,12 +212,13 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = MODE == MODE_WIN ? 12 : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int MAX_STAGES = 16;
-  static constexpr int TAIL_BYTES = 8 * (2 * MAX_STAGES + 6) + 16 + (MODE == MODE_DBHEAD ? 4096 : 0);   // barriers, TMEM slot, head consts
+  static constexpr int TAIL_BYTES = 8 * (2 * MAX_STAGES + 10) + 16 + (MODE == MODE_DBHEAD ? 4096 : 0);   // barriers, TMEM slot, head consts
   // dynamic shared memory for a given ring depth / resident-weight size
   static constexpr int smem_bytes(int stages, int bres_bytes) {
     return stages * (bres_bytes ? A_BYTES : STAGE_BYTES) + bres_bytes + 1024 /*alignment slack*/ + TAIL_BYTES;
   }
-  static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
+  static constexpr int ACC = 512 / BLOCK_N > 4 ? 4 : 512 / BLOCK_N;        // accumulator buffers in TMEM: 4 / 4 / 2
+  static constexpr int TMEM_COLS = ACC * BLOCK_N;                          // 256 / 512 / 512: powers of two
 
 };
 
@@ -426,11 +438,11 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + stages * stage_bytes + bres_bytes);
   const uint32_t full0 = smem_u32(bars);                       // [MAX_STAGES]
   const uint32_t empty0 = full0 + 8 * Cfg::MAX_STAGES;         // [MAX_STAGES]
-  const uint32_t tfull0 = empty0 + 8 * Cfg::MAX_STAGES;        // [2]
-  const uint32_t tempty0 = tfull0 + 16;                        // [2]
-  const uint32_t bfull = tempty0 + 16;                         // [1] resident weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::MAX_STAGES + 5);
-  float* head_s = reinterpret_cast<float*>(bars + 2 * Cfg::MAX_STAGES + 6);   // MODE_DBHEAD: [2 heads][256 b1 + 256 w2]
+  const uint32_t tfull0 = empty0 + 8 * Cfg::MAX_STAGES;        // [4]
+  const uint32_t tempty0 = tfull0 + 32;                        // [4]
+  const uint32_t bfull = tempty0 + 32;                         // [1] resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::MAX_STAGES + 9);
+  float* head_s = reinterpret_cast<float*>(bars + 2 * Cfg::MAX_STAGES + 10);   // MODE_DBHEAD: [2 heads][256 b1 + 256 w2]
   if constexpr (MODE == MODE_DBHEAD) {
     for (int i = threadIdx.x; i < 2 * 512; i += NUM_THREADS) {
       const int hd = i >> 9, r = i & 511;
@@ -442,7 +454,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
+    for (int i = 0; i < Cfg::ACC; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
     mbar_init(bfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
@@ -469,13 +481,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const int ksteps = MODE == MODE_WIN ? p.nr : p.KH * p.KW * kchunks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       if (p.bres && blockIdx.x < p.total_tiles) {      // weights once per CTA (n_blocks == 1)
-        mbar_expect_tx(bfull, bres_bytes);
-        for (int ks = 0; ks < ksteps_all; ++ks)
-          tma_load_2d(bres0 + ks * Cfg::B_STAGE_BYTES, &maps.b, bfull, ks * (ROWB / 2), 0);
+        if (elect_one()) {
+          mbar_expect_tx(bfull, bres_bytes);
+          for (int ks = 0; ks < ksteps_all; ++ks)
+            tma_load_2d(bres0 + ks * Cfg::B_STAGE_BYTES, &maps.b, bfull, ks * (ROWB / 2), 0);
+        }
+        __syncwarp();
       }
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         long long t = tile;
@@ -486,11 +501,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         if (MODE == MODE_WIN) {
           for (int r = 0; r < p.nr; ++r) {
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            const uint32_t sa = ring + stage * stage_bytes;
-            const uint32_t fb = full0 + 8 * stage;
-            mbar_expect_tx(fb, stage_bytes);
-            tma_load_5d(sa, &maps.a[0], fb, 0, x0, r % p.sdiv, y0 + r / p.sdiv, n0);
-            if (!p.bres) tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, r * 32, nb * BLOCK_N);
+            if (elect_one()) {
+              const uint32_t sa = ring + stage * stage_bytes;
+              const uint32_t fb = full0 + 8 * stage;
+              mbar_expect_tx(fb, stage_bytes);
+              tma_load_5d(sa, &maps.a[0], fb, 0, x0, r % p.sdiv, y0 + r / p.sdiv, n0);
+              if (!p.bres) tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, r * 32, nb * BLOCK_N);
+            }
+            __syncwarp();
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -508,11 +526,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
               const int kbase = (r * p.KW + s) * p.Cin;
               for (int kc = 0; kc < kchunks; ++kc) {
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                const uint32_t sa = ring + stage * stage_bytes;
-                const uint32_t fb = full0 + 8 * stage;
-                mbar_expect_tx(fb, stage_bytes);
-                tma_load_4d(sa, &maps.a[mi], fb, coff + kc * BLOCK_K, x0 + xo, y0 + yo, n0);
-                if (!p.bres) tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, kbase + kc * BLOCK_K, nb * BLOCK_N);
+                if (elect_one()) {
+                  const uint32_t sa = ring + stage * stage_bytes;
+                  const uint32_t fb = full0 + 8 * stage;
+                  mbar_expect_tx(fb, stage_bytes);
+                  tma_load_4d(sa, &maps.a[mi], fb, coff + kc * BLOCK_K, x0 + xo, y0 + yo, n0);
+                  if (!p.bres) tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, kbase + kc * BLOCK_K, nb * BLOCK_N);
+                }
+                __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1; }
               }
             }
@@ -521,30 +542,42 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc(BLOCK_N);
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    {
+      // SPLIT > 1 issues each K=16 step as SPLIT narrower MMAs into independent column ranges of the accumulator.
+      // Measured on B200 (profiles/r01_ncu_notes.md): it is SLOWER (256->256 3x3: 0.836 -> 0.914 ms) -- an MMA with
+      // M=128 costs ~128 cycles whatever its N (the A operand is re-read from shared memory per instruction), so
+      // fewer, wider instructions win.  Kept as a knob; 1 = one MMA of the full tile width.
+      constexpr int SPLIT = 1;
+      constexpr int SUBN = BLOCK_N / SPLIT;
+      const uint32_t idesc = umma_idesc(SUBN);
       int stage = 0; uint32_t phase = 0;
       long long it = 0;
       if (p.bres && blockIdx.x < p.total_tiles) mbar_wait(bfull, 0);
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = (int)(it & 1);
-        mbar_wait(tempty0 + 8 * as, (uint32_t)((it >> 1) & 1) ^ 1);
+        const int as = (int)(it % Cfg::ACC);
+        mbar_wait(tempty0 + 8 * as, (uint32_t)((it / Cfg::ACC) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full0 + 8 * stage, phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = ring + stage * stage_bytes;
-          const uint64_t ad = umma_desc<ROWB>(sa);
-          const uint64_t bd = umma_desc<ROWB>(p.bres ? bres0 + ks * Cfg::B_STAGE_BYTES : sa + Cfg::A_BYTES);
+          if (elect_one()) {
+            const uint32_t sa = ring + stage * stage_bytes;
+            const uint64_t ad = umma_desc<ROWB>(sa);
+            const uint64_t bd = umma_desc<ROWB>(p.bres ? bres0 + ks * Cfg::B_STAGE_BYTES : sa + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < ROWB / 32; ++k)
-            umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ks | k) ? 1u : 0u);
-          umma_commit(empty0 + 8 * stage);              // frees the slot when these MMAs have read it
+            for (int k = 0; k < ROWB / 32; ++k)
+#pragma unroll
+              for (int j = 0; j < SPLIT; ++j)      // sub-tile j: B rows j*SUBN.. (SUBN*ROWB bytes further), D columns j*SUBN..
+                umma_f16(d_tmem + (uint32_t)(j * SUBN), ad + (uint64_t)(k * 2),
+                         bd + (uint64_t)(k * 2 + ((j * SUBN * ROWB) >> 4)), idesc, (ks | k) ? 1u : 0u);
+            umma_commit(empty0 + 8 * stage);            // frees the slot when these MMAs have read it
+            if (ks == ksteps - 1) umma_commit(tfull0 + 8 * as);   // accumulator complete
+          }
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull0 + 8 * as);                   // accumulator complete
       }
     }
   } else {
@@ -561,9 +594,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
       const int ox = tx * BW + xx, oy = ty * BH + yy, n = (int)t * BNt + nn;
       const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
-      const int as = (int)(it & 1);
+      const int as = (int)(it % Cfg::ACC);
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
-      const uint32_t tfull_bar = tfull0 + 8 * as, parity = (uint32_t)((it >> 1) & 1);
+      const uint32_t tfull_bar = tfull0 + 8 * as, parity = (uint32_t)((it / Cfg::ACC) & 1);
       if constexpr (MODE == MODE_DBHEAD) {
         mbar_wait(tfull_bar, parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -823,13 +856,18 @@ static void plan_smem(TcPlan* pl) {
   TcParams& p = pl->p;
   const int ksteps = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
   const int bres_bytes = ksteps * Cfg::B_STAGE_BYTES;
-  const bool can_res = (MODE == MODE_CONV || MODE == MODE_WIN) && p.n_blocks == 1 && bres_bytes <= 96 * 1024;
+  const bool can_res = (MODE == MODE_CONV || MODE == MODE_WIN) && p.n_blocks == 1 && bres_bytes <= 96 * 1024 &&
+                       !getenv("VTD_NO_BRES");
   p.bres = can_res ? 1 : 0;
   if (p.bres) {
     int st = (SMEM_BUDGET - bres_bytes - 1024 - Cfg::TAIL_BYTES) / Cfg::A_BYTES;
     p.stages = st > Cfg::MAX_STAGES ? Cfg::MAX_STAGES : st;
   } else {
     p.stages = Cfg::STAGES;
+  }
+  if (const char* e = getenv("VTD_TC_STAGES")) {          // tuning aid: cap the ring depth
+    int cap = atoi(e);
+    if (cap >= 2 && cap < p.stages) p.stages = cap;
   }
   pl->smem = Cfg::smem_bytes(p.stages, p.bres ? bres_bytes : 0);
 }
