@@ -1,0 +1,168 @@
+"""GPU tests of the reference-facing Python surface and of the less common entry points (NV12 ingest, ResNet50,
+4K, crop chunking, concurrent callers).  The oracle (oracle/port.py) is the checker."""
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def port():
+    from oracle import port as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def E():
+    from video_text_detection_system_b200 import _lib
+    return _lib
+
+
+def _nv12_from_bgr(bgr):
+    import cv2
+    h, w = bgr.shape[:2]
+    i420 = cv2.cvtColor(bgr, cv2.COLOR_BGR2YUV_I420)
+    nv12 = np.empty((h * 3 // 2, w), np.uint8)
+    nv12[:h] = i420[:h]
+    u = i420[h:h + h // 4].reshape(h // 2, w // 2)
+    v = i420[h + h // 4:].reshape(h // 2, w // 2)
+    nv12[h:, 0::2] = u
+    nv12[h:, 1::2] = v
+    return nv12
+
+
+def test_nv12_preprocess_matches_cv2_then_reference_transform(E, port):
+    import ctypes as C
+    import cv2
+    h, w, dh, dw = 360, 640, 256, 448
+    rng = np.random.default_rng(3)
+    frames = [_nv12_from_bgr(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)),
+              rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8)]          # second: arbitrary YUV values
+    eng = E.Engine(det_h=dh, det_w=dw, max_batch=2, max_src_h=h, max_src_w=w)
+    ptrs = (C.c_void_p * 2)(*[f.ctypes.data for f in frames])
+    eng._check(eng.lib.vtd_preprocess(eng.handle, C.cast(ptrs, C.POINTER(C.c_void_p)), 2, h, w, w, E.VTD_PIX_NV12, 0))
+    x = eng.debug_tensor("input", 2)
+    for i, f in enumerate(frames):
+        bgr = cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12)
+        assert np.array_equal(x[i], port.preprocess(bgr, dh, dw)[0].numpy())
+
+
+def test_resnet50_bf16_maps_vs_oracle(E, port):
+    net = port.build_dbnet("resnet50", seed=4)
+    h, w = 192, 256
+    x = np.random.default_rng(1).standard_normal((2, 3, h, w)).astype(np.float32)
+    eng = E.Engine(backbone=50, det_h=h, det_w=w, max_batch=2, dtype="bf16")
+    eng.load_detector(net.state_dict())
+    p, t = eng.dbnet_forward(x)
+    with torch.no_grad():
+        ref = port.dbnet_forward(net, torch.from_numpy(x), return_feats=True)
+    # Random-init ResNet50 with randomised BN statistics has pre-sigmoid logits of std ~30 (94 % of the pixels are
+    # saturated), so a 1 % bf16 error in a logit that crosses zero moves the probability by far more than 1e-2.  The
+    # meaningful bf16 check here is relative error before the sigmoid, plus the share of pixels inside 1e-2.
+    p2 = eng.debug_tensor("p2", 2)
+    rp2 = ref["p2"].numpy()
+    assert np.abs(p2 - rp2).max() <= 0.03 * np.abs(rp2).max()
+    assert (np.abs(p - ref["probability"].numpy()) <= 1e-2).mean() >= 0.90
+    assert (np.abs(t - ref["threshold"].numpy()) <= 1e-2).mean() >= 0.90
+
+
+def test_4k_resnet50_bf16_runs_and_agrees_with_fp32_tier(E, port):
+    """BASELINE config 5 shape: 2160x3840 -> 2176x3840, DBNet-ResNet50, bf16.  Oracle-free (a CPU forward at this
+    size takes minutes): the two tiers of the library must agree within the bf16 tolerance."""
+    net = port.build_dbnet("resnet50", seed=0)
+    frames = port.synthetic_frames(1, 2160, 3840, seed=9)
+    outs = {}
+    for dtype in ("fp32", "bf16"):
+        eng = E.Engine(backbone=50, det_h=2176, det_w=3840, max_batch=1, dtype=dtype, max_src_h=2160, max_src_w=3840)
+        eng.load_detector(net.state_dict())
+        eng.preprocess(list(frames))
+        eng.detect_maps(1, 0.5)
+        outs[dtype] = eng.read_maps(1)
+        eng.close()
+    assert np.isfinite(outs["bf16"][0]).all()
+    # logits of the random-init ResNet50 are mostly saturated (see test_resnet50_bf16_maps_vs_oracle)
+    assert (np.abs(outs["fp32"][0] - outs["bf16"][0]) <= 1e-2).mean() >= 0.90
+    assert (np.abs(outs["fp32"][1] - outs["bf16"][1]) <= 1e-2).mean() >= 0.90
+
+
+def test_more_crops_than_one_chunk(E, port):
+    net = port.build_crnn(seed=0)
+    eng = E.Engine(det_h=32, det_w=32, crop_w=128, max_batch=1, max_boxes=64, max_src_h=32, max_src_w=32)   # chunk = 64
+    eng.load_recognizer(net.state_dict())
+    rng = np.random.default_rng(2)
+    crops = [rng.integers(0, 256, (rng.integers(12, 40), rng.integers(20, 150), 3), dtype=np.uint8) for _ in range(150)]
+    ids, lens, conf, logits = eng.recognize_crops(crops, want_logits=True)
+    ref, ref_logits = port.recognize_batch(net, crops, return_logits=True)
+    assert np.abs(logits - ref_logits.numpy()).max() <= 5e-3
+    agree = sum(ids[i, :lens[i]].tolist() == ref[i]["ids"] for i in range(len(crops)))
+    assert agree >= 0.95 * len(crops)          # 1-LSB resize differences may flip a near-tie argmax
+
+
+def test_text_detector_detect_vs_oracle_and_threads(port):
+    from video_text_detection_system_b200 import TextDetector
+    sd = port.build_dbnet("resnet18", seed=0).state_dict()
+    D = TextDetector(backbone="resnet18", pretrained=False, det_size=(320, 480))
+    D.model.load_state_dict(sd)
+    net = port.build_dbnet("resnet18", seed=0)
+    import cv2
+    frames = []
+    for i in range(4):
+        f = np.zeros((360, 540, 3), np.uint8)
+        cv2.putText(f, "FRAME %d" % i, (30, 120 + 40 * i), cv2.FONT_HERSHEY_SIMPLEX, 2, (255, 255, 255), 5)
+        frames.append(f)
+    want = [port.detect(net, f, 0.5, 320, 480) for f in frames]
+    got = [None] * 4
+
+    def work(i):
+        got[i] = D.detect(frames[i], 0.5)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]     # the reference's 4 executor threads
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for g, w_ in zip(got, want):
+        assert sorted(tuple(d["bbox"]) for d in g) == sorted(tuple(d["bbox"]) for d in w_)
+        for d in g:
+            assert isinstance(d["confidence"], float) and all(isinstance(v, int) for v in d["bbox"])
+    # patched forward (reference tests/test_models.py:30-37): arbitrary map size, post-process only
+    from unittest.mock import patch
+    with patch.object(D.model, "forward", return_value={"probability": torch.rand(1, 1, 160, 160),
+                                                        "threshold": torch.rand(1, 1, 160, 160)}):
+        out = D.detect(frames[0])
+    assert isinstance(out, list)
+    pm = np.random.default_rng(0).random((160, 160))
+    got_pp = D._post_process(pm, 640, 480, 0.5)
+    want_pp = port.post_process(pm.astype(np.float32), 640, 480, 0.5, 320, 480)
+    assert sorted(tuple(d["bbox"]) for d in got_pp) == sorted(tuple(d["bbox"]) for d in want_pp)
+
+
+def test_pipeline_fused_path_vs_oracle(port):
+    from video_text_detection_system_b200 import VideoTextPipeline
+    P = VideoTextPipeline(use_transformer_ocr=False, backbone="resnet18", pretrained=False, det_size=(256, 1280))
+    det, rec = port.build_dbnet("resnet18", seed=0), port.build_crnn(seed=0)
+    P.detector.model.load_state_dict(det.state_dict())
+    P.recognizer.model.load_state_dict(rec.state_dict())
+    import cv2
+    frames = []
+    for i in range(3):
+        f = np.full((288, 1440, 3), 30, np.uint8)
+        cv2.putText(f, "HELLO WORLD %d" % i, (40, 200), cv2.FONT_HERSHEY_SIMPLEX, 4, (255, 255, 255), 9)
+        frames.append(f)
+    got = P.detect_and_recognize(frames)
+    for f, regions in zip(frames, got):
+        want = port.process_frame(det, rec, f, 0.5, 256, 1280, 128, per_crop=False)
+        assert sorted(tuple(r["bbox"]) for r in regions) == sorted(tuple(r["bbox"]) for r in want)
+        for r in regions:
+            assert set(r) == {"bbox", "text", "detection_confidence", "recognition_confidence", "polygon"}
+    single = P.process_single_frame(frames[0])
+    assert [r["bbox"] for r in single["detections"]] == [r["bbox"] for r in got[0]]
+    assert all("polygon" not in r for r in single["detections"])
+    # recogniser surface
+    crop = frames[0][100:220, 40:700]
+    r1 = P.recognizer.recognize(crop)
+    w1 = port.recognize_batch(rec, [crop])[0]
+    assert r1["text"] == w1["text"] and r1["confidence"] == pytest.approx(w1["confidence"], abs=2e-3)
