@@ -65,12 +65,12 @@ class TextDetector:
             raise
 
     # ---- engine plumbing
-    def _engine_for(self, src_h: int, src_w: int, max_batch: int = 1, crop_w: int = 128) -> Engine:
+    def _engine_for(self, src_h: int, src_w: int, max_batch: int = 1, crop_w: int = 128, slot: int = 0) -> Engine:
         mh = max(2160, src_h)
         mw = max(3840, src_w)
         return self.model.get_engine(self.det_h, self.det_w, max_batch=max_batch, max_boxes=self.max_boxes,
                                      crop_w=crop_w, max_src_h=mh, max_src_w=mw, device=self.device,
-                                     unclip_ratio=self.unclip_ratio)
+                                     unclip_ratio=self.unclip_ratio, slot=slot)
 
     def _forward_is_patched(self) -> bool:
         return "forward" in vars(self.model)

@@ -160,10 +160,12 @@ class DBNet(nn.Module, _EngineOwner):
 
     def get_engine(self, det_h: int, det_w: int, dtype: Optional[str] = None, max_batch: int = 1,
                    max_boxes: int = 256, crop_w: int = 128, max_src_h: int = 2160, max_src_w: int = 3840,
-                   device=None, unclip_ratio: float = 1.0) -> Engine:
+                   device=None, unclip_ratio: float = 1.0, slot: int = 0) -> Engine:
+        """`slot` distinguishes otherwise identical contexts: the pipeline keeps several batches in flight, each on
+        its own context (own stream, own buffers)."""
         dtype = dtype or self.dtype_tier
         key = (det_h, det_w, dtype, max_batch, max_boxes, crop_w, max_src_h, max_src_w, _device_index(device),
-               float(unclip_ratio))
+               float(unclip_ratio), int(slot))
         with self._engine_lock:
             hit = self._engines.get(key)
             if hit is not None:

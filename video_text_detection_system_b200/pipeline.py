@@ -37,7 +37,10 @@ class VideoTextPipeline:
         self.confidence_threshold = confidence_threshold
         self.batch_size = batch_size
         self.executor = ThreadPoolExecutor(max_workers=4)
-        self._rec_version = None
+        # batches kept in flight by process_video: each runs on its own context/stream from an executor thread, so
+        # the host->device copy and the latency-bound stages of one batch overlap the convolutions of the other
+        self.inflight = int(engine_kwargs.get("inflight", 2))
+        self._slot_locks = {}
 
     # ---- fused batch path -----------------------------------------------------------------------------
     def _patched(self) -> bool:
@@ -46,21 +49,23 @@ class VideoTextPipeline:
         return ("detect" in vars(self.detector) or "recognize" in vars(self.recognizer)
                 or self.detector._forward_is_patched() or self.recognizer._forward_is_patched())
 
-    def _engine(self, src_h: int, src_w: int, n: int):
+    def _engine(self, src_h: int, src_w: int, n: int, slot: int = 0):
         cap = max(int(self.batch_size), n, 1)
-        eng = self.detector._engine_for(src_h, src_w, max_batch=cap, crop_w=self.recognizer.crop_w)
-        if not eng.rec_loaded:
-            self.recognizer.model._check_supported()
-            eng.load_recognizer(self.recognizer.model.state_dict())
-        return eng
+        with self.detector._lock:
+            eng = self.detector._engine_for(src_h, src_w, max_batch=cap, crop_w=self.recognizer.crop_w, slot=slot)
+            if not eng.rec_loaded:
+                self.recognizer.model._check_supported()
+                eng.load_recognizer(self.recognizer.model.state_dict())
+            lock = self._slot_locks.setdefault(slot, __import__("threading").Lock())
+        return eng, lock
 
-    def detect_and_recognize(self, frames: List[np.ndarray]) -> List[List[Dict[str, Any]]]:
+    def detect_and_recognize(self, frames: List[np.ndarray], slot: int = 0) -> List[List[Dict[str, Any]]]:
         """One fused device pass over same-sized BGR frames -> per-frame text regions."""
         if not frames:
             return []
         h, w = frames[0].shape[:2]
-        eng = self._engine(h, w, len(frames))
-        with self.detector._lock:
+        eng, lock = self._engine(h, w, len(frames), slot)
+        with lock:
             rec, cnt = eng.run_batch(frames, thr=self.confidence_threshold, recognize=True)
         out = []
         for i in range(len(frames)):
@@ -82,17 +87,32 @@ class VideoTextPipeline:
             total_frames = video_info.get("frame_count", 0)
             batch_frames: List[np.ndarray] = []
             batch_numbers: List[Tuple] = []
+            pending: List[Tuple[Any, int]] = []      # (task, frames in it), oldest first; results stay in frame order
+            next_slot = 0
+
+            async def retire():
+                nonlocal frame_count
+                task, n = pending.pop(0)
+                all_results.extend(await task)
+                frame_count += n
+                if progress_callback:
+                    progress = frame_count / total_frames if total_frames > 0 else 0
+                    await progress_callback(progress, frame_count, total_frames)
+
             async for frame, frame_number, timestamp in frames:
                 batch_frames.append(frame)
                 batch_numbers.append((frame_number, timestamp))
                 if len(batch_frames) >= self.batch_size:
-                    all_results.extend(await self._process_frame_batch(batch_frames, batch_numbers, output_dir))
-                    frame_count += len(batch_frames)
+                    task = asyncio.ensure_future(self._process_frame_batch(list(batch_frames), list(batch_numbers),
+                                                                           output_dir, slot=next_slot))
+                    pending.append((task, len(batch_frames)))
+                    next_slot = (next_slot + 1) % max(1, self.inflight)
                     batch_frames.clear()
                     batch_numbers.clear()
-                    if progress_callback:
-                        progress = frame_count / total_frames if total_frames > 0 else 0
-                        await progress_callback(progress, frame_count, total_frames)
+                    while len(pending) >= max(1, self.inflight):
+                        await retire()
+            while pending:
+                await retire()
             if batch_frames:
                 all_results.extend(await self._process_frame_batch(batch_frames, batch_numbers, output_dir))
                 frame_count += len(batch_frames)
@@ -103,13 +123,13 @@ class VideoTextPipeline:
             logger.error(f"Video processing failed: {e}")
             return {"status": "failed", "error": str(e), "results": []}
 
-    async def _process_frame_batch(self, frames: List[np.ndarray], frame_info: List[Tuple], output_dir: str
-                                   ) -> List[Dict]:
+    async def _process_frame_batch(self, frames: List[np.ndarray], frame_info: List[Tuple], output_dir: str,
+                                   slot: int = 0) -> List[Dict]:
         loop = asyncio.get_event_loop()
         same = all(isinstance(f, np.ndarray) and f.ndim == 3 and f.shape == frames[0].shape and f.dtype == np.uint8
                    for f in frames)
         if same and not self._patched():
-            per_frame = await loop.run_in_executor(self.executor, self.detect_and_recognize, list(frames))
+            per_frame = await loop.run_in_executor(self.executor, self.detect_and_recognize, list(frames), slot)
             return [{"frame_number": fn, "timestamp": ts, "detections": regions}
                     for (fn, ts), regions in zip(frame_info, per_frame)]
         # reference control flow (pipeliine.py:96-139): honours patched detect()/recognize()
