@@ -65,7 +65,9 @@ struct vtd_ctx {
   bool use_win = false, use_tchead = false, use_tclstm = false;   // tcgen05 stems / head tail / LSTM (bf16 tier)
   OutLayout pre_lay{}, crops_lay{};
   TcPlan* head_plan = nullptr;
-  TcPlan* lstm_plan[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [layer][step parity]
+  TcPlan* lstm_plan[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [layer][step parity] (step-wise variant)
+  LstmPlan* plstm[2] = {nullptr, nullptr};   // persistent clustered variant (default)
+  bool use_plstm = false;
   bf16* h16 = nullptr;                  // [2 ping-pong][2 dirs][rc][256]
   void* pre = nullptr;                  // [B,dh,dw,4]  (bf16 + use_win: zero-bordered [B,dh+6,dw+8,4])
   void* head_feat = nullptr;            // [B,dh/4,dw/4,128]
@@ -551,7 +553,13 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
     reg_dbg(c, l == 0 ? "rnn0" : "rnn1", in, false, true);
   }
   if ((r = dalloc(c, &c->hbuf, (size_t)2 * 2 * B * H * 4)) || (r = dalloc(c, &c->cbuf, (size_t)2 * B * H * 4))) return r;
-  if (c->use_tclstm) {
+  if (c->use_tclstm && c->use_plstm) {
+    for (int l = 0; l < 2; ++l) {
+      std::string e;
+      c->plstm[l] = lstm_plan_create(c->whh[l], &e);
+      if (!c->plstm[l]) FAIL(VTD_ERR_CUDA, "persistent LSTM plan: %s", e.c_str());
+    }
+  } else if (c->use_tclstm) {
     if ((r = dalloc(c, &c->h16, (size_t)2 * 2 * B * H * 2))) return r;
     for (int l = 0; l < 2; ++l)
       for (int pp = 0; pp < 2; ++pp) {
@@ -589,7 +597,9 @@ int run_crnn(vtd_ctx* c, int nc) {
     // the second layer's xproj reuses its own buffer (allocated by add_conv)
     { int r2 = run_op_prof(c, c->xproj_op[l], nc); if (r2) return r2; }
     const float* xp = (const float*)c->xproj_op[l].d.out;
-    if (c->use_tclstm) {
+    if (c->use_tclstm && c->use_plstm) {
+      CK(bilstm_layer_tcgen05(c->plstm[l], xp, c->rnn_out[l], nc, c->T, c->stream, &c->lc));
+    } else if (c->use_tclstm) {
       CK(cudaMemsetAsync(c->h16, 0, (size_t)2 * c->rc * 256 * 2, c->stream));          // h_0 = 0 (parity 0)
       CK(cudaMemsetAsync(c->cbuf, 0, (size_t)2 * c->rc * 256 * 4, c->stream));         // c_0 = 0
       for (int step = 0; step < c->T; ++step) CK(lstm_step_tcgen05(c->lstm_plan[l][step & 1], nc, step, c->stream, &c->lc));
@@ -755,6 +765,7 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   c->use_win = c->bf16_mode && !getenv("VTD_NO_WIN");
   c->use_tchead = c->bf16_mode && !getenv("VTD_NO_TCHEAD");
   c->use_tclstm = c->bf16_mode && !getenv("VTD_NO_TCLSTM");
+  c->use_plstm = c->use_tclstm && !getenv("VTD_NO_PLSTM");
   long long want = (long long)cfg->max_batch * cfg->max_boxes;
   c->rc = (int)(want < 1024 ? want : 1024);
   auto fail = [&](int code) { g_create_error = c->err; vtd_destroy(c); *out = nullptr; return code; };
@@ -822,6 +833,7 @@ void vtd_destroy(vtd_ctx* c) {
   for (int l = 0; l < 2; ++l) if (c->xproj_op[l].plan) tc_plan_destroy(c->xproj_op[l].plan);
   if (c->fc_op.plan) tc_plan_destroy(c->fc_op.plan);
   if (c->head_plan) tc_plan_destroy(c->head_plan);
+  for (int l = 0; l < 2; ++l) if (c->plstm[l]) lstm_plan_destroy(c->plstm[l]);
   for (int l = 0; l < 2; ++l) for (int pp = 0; pp < 2; ++pp) if (c->lstm_plan[l][pp]) tc_plan_destroy(c->lstm_plan[l][pp]);
   for (void* p : c->allocs) cudaFree(p);
   for (ResizeTab* t : {&c->tx, &c->ty}) if (t->lo) { cudaFree(t->lo); cudaFree(t->cnt); cudaFree(t->kk); }

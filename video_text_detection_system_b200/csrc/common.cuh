@@ -50,6 +50,13 @@ TcPlan* tc_plan_create_lstm(const void* h_prev, void* h_next, int Bcap, const vo
 cudaError_t dbhead_tcgen05(TcPlan* pl, int n, float thr, const float* logit_bias, cudaStream_t s, LaunchCounter* lc);
 cudaError_t lstm_step_tcgen05(const TcPlan* pl, int B, int step, cudaStream_t s, LaunchCounter* lc);
 void tc_plan_destroy(TcPlan*);
+
+// persistent clustered BiLSTM layer (lstm_tcgen05.cu): one launch = all T steps of both directions
+struct LstmPlan;
+LstmPlan* lstm_plan_create(const void* whh /*[2*1024][256] bf16, rows (dir, unit tile, gate, unit)*/, std::string* err);
+void lstm_plan_destroy(LstmPlan*);
+cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const float* xproj, void* seq_out, int B, int T, cudaStream_t s,
+                                 LaunchCounter* lc);
 cudaError_t conv_tcgen05(const TcPlan* p, int n_actual, cudaStream_t s, LaunchCounter* lc);
 bool tc_supported(const ConvDesc& d);
 
