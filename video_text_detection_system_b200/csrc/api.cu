@@ -545,7 +545,8 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
         }
     }
     Act xo;
-    if ((r = add_conv(c, nullptr, xp, B, in, 1, 0, false, nullptr, RES_NONE, true, &xo, &c->xproj_op[l]))) return r;
+    if ((r = add_conv(c, nullptr, xp, B, in, 1, 0, false, nullptr, RES_NONE, /*out_f32=*/!c->use_plstm, &xo, &c->xproj_op[l])))
+      return r;
     if (l == 0) c->xproj = (float*)xo.p;
     if ((r = upload_act_type(c, whh, &c->whh[l]))) return r;
     if ((r = dev_alloc(c, &c->rnn_out[l], (size_t)B * c->T * 2 * H * c->esz))) return r;
@@ -598,7 +599,7 @@ int run_crnn(vtd_ctx* c, int nc) {
     { int r2 = run_op_prof(c, c->xproj_op[l], nc); if (r2) return r2; }
     const float* xp = (const float*)c->xproj_op[l].d.out;
     if (c->use_tclstm && c->use_plstm) {
-      CK(bilstm_layer_tcgen05(c->plstm[l], xp, c->rnn_out[l], nc, c->T, c->stream, &c->lc));
+      CK(bilstm_layer_tcgen05(c->plstm[l], c->xproj_op[l].d.out, c->rnn_out[l], nc, c->T, c->stream, &c->lc));
     } else if (c->use_tclstm) {
       CK(cudaMemsetAsync(c->h16, 0, (size_t)2 * c->rc * 256 * 2, c->stream));          // h_0 = 0 (parity 0)
       CK(cudaMemsetAsync(c->cbuf, 0, (size_t)2 * c->rc * 256 * 4, c->stream));         // c_0 = 0

@@ -55,7 +55,7 @@ void tc_plan_destroy(TcPlan*);
 struct LstmPlan;
 LstmPlan* lstm_plan_create(const void* whh /*[2*1024][256] bf16, rows (dir, unit tile, gate, unit)*/, std::string* err);
 void lstm_plan_destroy(LstmPlan*);
-cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const float* xproj, void* seq_out, int B, int T, cudaStream_t s,
+cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*[B][T][2][1024] bf16*/, void* seq_out, int B, int T, cudaStream_t s,
                                  LaunchCounter* lc);
 cudaError_t conv_tcgen05(const TcPlan* p, int n_actual, cudaStream_t s, LaunchCounter* lc);
 bool tc_supported(const ConvDesc& d);

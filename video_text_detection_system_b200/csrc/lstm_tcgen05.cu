@@ -14,8 +14,12 @@
 //     between steps, and there is no TMA on the recurrent path;
 //   * the cell state c stays in registers (each epilogue thread owns one sequence x 32 units for all timesteps).
 // Per step: 16 tcgen05.mma (128 x 256 x 16) into TMEM -> epilogue warps add xproj, apply the gates, write h (DSMEM)
-// and the layer output (global) -> two cluster barriers order "all MMAs have read h_{t-1}" before "h_t is written"
-// before "next MMAs".  Latency per step is a few microseconds instead of one kernel launch per step.
+// and the layer output (global).  Ordering is carried by mbarriers only: a multicast tcgen05.commit tells all four
+// CTAs "my MMAs no longer read h_{t-1}" (afree, 4 arrivals); h_t travels with st.async, whose bytes complete the
+// transaction count of the destination CTA's hready barrier, which that CTA's MMA warp waits on (expect_tx 64 KB).
+// No fences, no cluster-wide barriers inside the loop.  (Earlier versions: barrier.cluster pairs -- 12.7 us/step;
+// st.shared::cluster + release/acquire.cluster mbarrier ops -- 10 us/step, MEMBAR.ALL.GPU on every arrive and
+// CCTL.IVALL on every poll.)
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string>
@@ -31,7 +35,7 @@ constexpr int L_A_BYTES = 4 * 128 * 128;       // 4 K-chunks x 128 rows x 128 B
 constexpr int L_SMEM = L_W_BYTES + L_A_BYTES + 1024 + 64;
 
 struct LstmParams {
-  const float* xproj;     // [B][T][2][1024]
+  const bf16* xproj;      // [B][T][2][1024] bf16
   bf16* seq_out;          // [B][T][512]
   int B, T;
 };
@@ -43,8 +47,37 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {      // release at cluster scope
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope, bounded
+  uint32_t done = 0;
+  long long t0 = 0;
+  int spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 64) t0 = clock64();
+    if (spins > 64 && (clock64() - t0) > 4000000000LL) __trap();
+  }
+}
+// tcgen05.commit that arrives on the barrier at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// 16-byte store into (possibly remote) shared memory of the cluster through the ASYNC proxy, completing 16 bytes of
+// the transaction count of the mbarrier `mbar` in the same destination CTA.  No fences on either side: the consumer's
+// mbarrier wait orders the data before its tcgen05.mma reads.
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar)
                : "memory");
 }
 
@@ -58,7 +91,9 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
   const uint32_t abuf = base + L_W_BYTES;               // [4][128 rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + L_W_BYTES + L_A_BYTES);
   const uint32_t wfull = smem_u32(bars), tfull = wfull + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const uint32_t afree = wfull + 16;      // 4 arrivals: the MMAs of a step have completed in every CTA of the cluster
+  const uint32_t hready = wfull + 24;     // 1 arrival (own MMA thread, expect_tx 64 KB) + the st.async bytes of h_t from all 4 CTAs
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x;                            // == rank in cluster: hidden units 64*jt ..
@@ -68,6 +103,8 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
   if (warp == 0 && lane == 0) {
     mbar_init(wfull, 1);
     mbar_init(tfull, 1);
+    mbar_init(afree, 4);
+    mbar_init(hready, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whh) : "memory");
   }
@@ -95,13 +132,16 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
         tma_load_2d(wbuf + kc * (256 * 128), &map_whh, wfull, kc * 64, (dir * 4 + jt) * 256);
     }
     __syncwarp();
-    for (int s = 0; s < p.T; ++s) { cluster_arrive(); cluster_wait(); cluster_arrive(); cluster_wait(); }
   } else if (warp == 1) {
     // ---- MMA issuer
     const uint32_t idesc = umma_idesc(256);
     mbar_wait(wfull, 0);
     for (int s = 0; s < p.T; ++s) {
-      asm volatile("fence.proxy.async;" ::: "memory");
+      if (s > 0) {                                      // h_{s-1} of all 256 units (64 KB, written by st.async) has landed here
+        if (elect_one()) mbar_expect_tx(hready, L_A_BYTES);
+        __syncwarp();
+        mbar_wait(hready, (uint32_t)((s - 1) & 1));
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
 #pragma unroll
@@ -110,11 +150,10 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(tmem_acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
         }
-        umma_commit(tfull);
+        umma_commit(tfull);                       // accumulators of this step ready (own epilogue)
+        umma_commit_multicast(afree, 0xF);        // ... and this CTA no longer reads h_{s-1} (tell all four CTAs)
       }
       __syncwarp();
-      cluster_arrive(); cluster_wait();                 // #1: every CTA's MMAs of this step have completed
-      cluster_arrive(); cluster_wait();                 // #2: h_t has landed in every CTA
     }
   } else {
     // ---- epilogue: gates, cell update, h exchange
@@ -133,72 +172,72 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
 #pragma unroll
       for (int r = 0; r < 4; ++r) dst[r] = map_to_cta(row, (uint32_t)r);
     }
+    uint32_t hrdy[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) hrdy[r] = map_to_cta(hready, (uint32_t)r);
     for (int s = 0; s < p.T; ++s) {
       const int t = dir == 0 ? s : p.T - 1 - s;
-      const float* __restrict__ xp = p.xproj + (((size_t)bb * p.T + t) * 2 + dir) * 1024 + jt * 256 + half * 32;
+      const bf16* __restrict__ xp = p.xproj + (((size_t)bb * p.T + t) * 2 + dir) * 1024 + jt * 256 + half * 32;
       bf16* __restrict__ so = p.seq_out + ((size_t)bb * p.T + t) * 512 + dir * 256 + jt * 64 + half * 32;
-      if (valid) {
+      // input projection of this step: 4 gates x 32 units bf16 = 16 x 16 bytes, requested BEFORE the accumulator wait so
+      // the L2/DRAM latency overlaps the MMAs (loading them chunk by chunk inside the gate loop cost 8 exposed round
+      // trips per step: long_scoreboard was 49 % of the stalls)
+      uint4 xr[4][4];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + g * 64));
-      }
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          xr[g][j] = valid ? __ldg(reinterpret_cast<const uint4*>(xp + g * 64) + j) : make_uint4(0u, 0u, 0u, 0u);
       mbar_wait(tfull, (uint32_t)(s & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      cluster_arrive();                                 // #1 (own MMAs are complete)
       uint4 hw[4];
 #pragma unroll
-      for (int qq = 0; qq < 2; ++qq) {                  // 16 hidden units at a time
-        uint32_t vi[16], vf[16], vg[16], vo[16];
-        const uint32_t tb = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32 + qq * 16);
-        tmem_ld16(tb, vi); tmem_ld16(tb + 64, vf); tmem_ld16(tb + 128, vg); tmem_ld16(tb + 192, vo);
+      for (int j = 0; j < 4; ++j) {                     // 8 hidden units at a time
+        uint32_t vi[8], vf[8], vg[8], vo[8];
+        const uint32_t tb = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32 + j * 8);
+        tmem_ld8(tb, vi); tmem_ld8(tb + 64, vf); tmem_ld8(tb + 128, vg); tmem_ld8(tb + 192, vo);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float hv[16];
+        const __nv_bfloat162* xi2 = reinterpret_cast<const __nv_bfloat162*>(&xr[0][j]);
+        const __nv_bfloat162* xf2 = reinterpret_cast<const __nv_bfloat162*>(&xr[1][j]);
+        const __nv_bfloat162* xg2 = reinterpret_cast<const __nv_bfloat162*>(&xr[2][j]);
+        const __nv_bfloat162* xo2 = reinterpret_cast<const __nv_bfloat162*>(&xr[3][j]);
+        float hv[8];
 #pragma unroll
-        for (int u4 = 0; u4 < 16; u4 += 4) {
-          const int u = qq * 16 + u4;
-          float4 xi = make_float4(0.f, 0.f, 0.f, 0.f), xf = xi, xg = xi, xo = xi;
-          if (valid) {
-            xi = __ldg(reinterpret_cast<const float4*>(xp + u));
-            xf = __ldg(reinterpret_cast<const float4*>(xp + 64 + u));
-            xg = __ldg(reinterpret_cast<const float4*>(xp + 128 + u));
-            xo = __ldg(reinterpret_cast<const float4*>(xp + 192 + u));
-          }
-          const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
-          const float xgv[4] = {xg.x, xg.y, xg.z, xg.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const float2 xi = __bfloat1622float2(xi2[e2]), xf = __bfloat1622float2(xf2[e2]);
+          const float2 xg = __bfloat1622float2(xg2[e2]), xo = __bfloat1622float2(xo2[e2]);
+          const float xiv[2] = {xi.x, xi.y}, xfv[2] = {xf.x, xf.y}, xgv[2] = {xg.x, xg.y}, xov[2] = {xo.x, xo.y};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float gi = __uint_as_float(vi[u4 + e]) + xiv[e], gf = __uint_as_float(vf[u4 + e]) + xfv[e];
-            const float gg = __uint_as_float(vg[u4 + e]) + xgv[e], go = __uint_as_float(vo[u4 + e]) + xov[e];
-            const float cn = fast_sigmoid(gf) * c[u + e] + fast_sigmoid(gi) * fast_tanh(gg);
-            c[u + e] = cn;
-            hv[u4 + e] = valid ? fast_sigmoid(go) * fast_tanh(cn) : 0.f;
+          for (int e = 0; e < 2; ++e) {
+            const int u = e2 * 2 + e;
+            const float gi = __uint_as_float(vi[u]) + xiv[e], gf = __uint_as_float(vf[u]) + xfv[e];
+            const float gg = __uint_as_float(vg[u]) + xgv[e], go = __uint_as_float(vo[u]) + xov[e];
+            const float cn = sigmoid_approx(gf) * c[j * 8 + u] + sigmoid_approx(gi) * tanh_approx(gg);
+            c[j * 8 + u] = cn;
+            hv[u] = valid ? sigmoid_approx(go) * tanh_approx(cn) : 0.f;
           }
         }
-#pragma unroll
-        for (int w2 = 0; w2 < 2; ++w2) {
-          __nv_bfloat162 a0 = __floats2bfloat162_rn(hv[8 * w2 + 0], hv[8 * w2 + 1]);
-          __nv_bfloat162 a1 = __floats2bfloat162_rn(hv[8 * w2 + 2], hv[8 * w2 + 3]);
-          __nv_bfloat162 a2 = __floats2bfloat162_rn(hv[8 * w2 + 4], hv[8 * w2 + 5]);
-          __nv_bfloat162 a3 = __floats2bfloat162_rn(hv[8 * w2 + 6], hv[8 * w2 + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&a0); u.y = *reinterpret_cast<uint32_t*>(&a1);
-          u.z = *reinterpret_cast<uint32_t*>(&a2); u.w = *reinterpret_cast<uint32_t*>(&a3);
-          hw[qq * 2 + w2] = u;
-        }
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(hv[0], hv[1]), a1 = __floats2bfloat162_rn(hv[2], hv[3]);
+        __nv_bfloat162 a2 = __floats2bfloat162_rn(hv[4], hv[5]), a3 = __floats2bfloat162_rn(hv[6], hv[7]);
+        uint4 u4;
+        u4.x = *reinterpret_cast<uint32_t*>(&a0); u4.y = *reinterpret_cast<uint32_t*>(&a1);
+        u4.z = *reinterpret_cast<uint32_t*>(&a2); u4.w = *reinterpret_cast<uint32_t*>(&a3);
+        hw[j] = u4;
       }
-      if (valid) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (s + 1 < p.T) {
+        mbar_wait(afree, (uint32_t)(s & 1));            // nobody's MMAs still read h_{s-1}
+        // h_s slice -> A operand of all 4 CTAs: 16-byte chunk j of the row goes to physical chunk j ^ (row & 7)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st_async_v4(dst[r] + ((uint32_t)((half * 4 + j) ^ (m & 7)) << 4), hw[j], hrdy[r]);
+      }
+      if (valid) {                                      // layer output (global) after the exchange: off the critical path
         uint4* sp = reinterpret_cast<uint4*>(so);
 #pragma unroll
         for (int j = 0; j < 4; ++j) sp[j] = hw[j];
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      cluster_wait();                                   // #1: nobody's MMAs still read h_{t-1}
-      // h_t slice -> A operand of all 4 CTAs: 16-byte chunk j of the row goes to physical chunk j ^ (row & 7)
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) st_cluster_v4(dst[r] + ((uint32_t)((half * 4 + j) ^ (m & 7)) << 4), hw[j]);
-      asm volatile("fence.proxy.async;" ::: "memory");
-      cluster_arrive(); cluster_wait();                 // #2
     }
   }
 
@@ -239,7 +278,7 @@ LstmPlan* lstm_plan_create(const void* whh /*[2*1024][256] bf16, rows (dir, unit
 
 void lstm_plan_destroy(LstmPlan* p) { delete p; }
 
-cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const float* xproj, void* seq_out, int B, int T, cudaStream_t s,
+cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*bf16*/, void* seq_out, int B, int T, cudaStream_t s,
                                  LaunchCounter* lc) {
   if (B <= 0 || T <= 0) return cudaSuccess;
   static bool attr_done = false;
@@ -249,7 +288,7 @@ cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const float* xproj, void* s
     attr_done = true;
   }
   LstmParams p;
-  p.xproj = xproj; p.seq_out = reinterpret_cast<bf16*>(seq_out); p.B = B; p.T = T;
+  p.xproj = reinterpret_cast<const bf16*>(xproj); p.seq_out = reinterpret_cast<bf16*>(seq_out); p.B = B; p.T = T;
   dim3 grid(4, 2, (B + 127) / 128);
   bilstm_persistent_kernel<<<grid, L_THREADS, L_SMEM, s>>>(pl->map_whh, p);
   if (lc) lc->n++;
