@@ -386,16 +386,21 @@ class Engine:
 
 
 def records_to_detections(rec_row: np.ndarray, count: int, with_text: bool) -> List[Dict]:
-    """vtd_record rows of one frame -> the reference's detection dicts (plain Python scalars)."""
-    out = []
-    for r in rec_row[:count]:
-        d = {"bbox": [int(v) for v in r["bbox"]],
-             "confidence": float(r["det_conf"]),
-             "polygon": [[int(r["polygon"][2 * k]), int(r["polygon"][2 * k + 1])] for k in range(4)]}
-        if with_text:
-            ln = int(r["len"])
-            d["ids"] = [int(v) for v in r["ids"][:min(ln, 36)]]
+    """vtd_record rows of one frame -> the reference's detection dicts (plain Python scalars).  Field extraction is
+    vectorised (one .tolist() per field), so assembling ~50 dicts per frame costs microseconds, not milliseconds."""
+    r = rec_row[:count]
+    if count <= 0:
+        return []
+    bbox = r["bbox"].tolist()
+    conf = r["det_conf"].astype(np.float64).tolist()
+    poly = r["polygon"].reshape(count, 4, 2).tolist()
+    out = [{"bbox": bbox[i], "confidence": conf[i], "polygon": poly[i]} for i in range(count)]
+    if with_text:
+        lens = np.minimum(r["len"], 36).tolist()
+        ids = r["ids"].tolist()
+        rconf = r["rec_conf"].astype(np.float64).tolist()
+        for i, d in enumerate(out):
+            d["ids"] = ids[i][:lens[i]]
             d["text"] = ids_to_text(d["ids"])
-            d["recognition_confidence"] = float(r["rec_conf"])
-        out.append(d)
+            d["recognition_confidence"] = rconf[i]
     return out

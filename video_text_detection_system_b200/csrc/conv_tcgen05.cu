@@ -70,6 +70,7 @@ struct TcParams {
   const bf16* res;
   void* out;
   int stages, bres;           // operand ring depth; 1 = all weight K-slices stay resident in shared memory
+  int ts;                     // 1 = operand A is staged smem -> TMEM (tcgen05.cp) and the MMAs use the TS form
   // MODE_WIN
   int nr, sdiv;               // filter rows (= K steps), row phases (= conv stride)
   // MODE_DBHEAD
@@ -364,6 +365,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
 
   const int BW = 1 << p.lw, BH = 1 << p.lh;
   const int BNt = BLOCK_M >> (p.lw + p.lh);
+  const int acc_n = p.ts ? 2 : Cfg::ACC;                 // TS mode keeps columns [2*BLOCK_N, 2*BLOCK_N+64) for operand A
   const int kchunks = p.Cin / BLOCK_K;
   const int ksteps = MODE == MODE_WIN ? p.nr : p.KH * p.KW * kchunks;
 
@@ -442,8 +444,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       long long it = 0;
       if (p.bres && blockIdx.x < p.total_tiles) mbar_wait(bfull, 0);
       for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = (int)(it % Cfg::ACC);
-        mbar_wait(tempty0 + 8 * as, (uint32_t)((it / Cfg::ACC) & 1) ^ 1);
+        const int as = (int)(it % acc_n);
+        mbar_wait(tempty0 + 8 * as, (uint32_t)((it / acc_n) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -453,6 +455,17 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
             const uint32_t sa = ring + stage * stage_bytes;
             const uint64_t ad = umma_desc<ROWB>(sa);
             const uint64_t bd = umma_desc<ROWB>(p.bres ? bres0 + ks * Cfg::B_STAGE_BYTES : sa + Cfg::A_BYTES);
+            if (MODE == MODE_CONV && BLOCK_N <= 128 && p.ts) {
+              // operand A through tensor memory: an SS-form MMA with M=128 re-reads its 4 KB A slab from shared
+              // memory at ~32 B/cycle (~128 cycles per instruction whatever N is); tcgen05.cp moves the slab once at
+              // full shared-memory bandwidth and the TS-form MMAs then run at N/2 cycles.
+              const uint32_t a_t = tmem_base + (uint32_t)(2 * BLOCK_N) + (uint32_t)((ks & 1) * 32);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) tmem_cp_128x256b(a_t + (uint32_t)(k * 8), ad + (uint64_t)(k * 2));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(d_tmem, a_t + (uint32_t)(k * 8), bd + (uint64_t)(k * 2), idesc, (ks | k) ? 1u : 0u);
+            } else
 #pragma unroll
             for (int k = 0; k < ROWB / 32; ++k)
 #pragma unroll
@@ -481,9 +494,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
       const int ox = tx * BW + xx, oy = ty * BH + yy, n = (int)t * BNt + nn;
       const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
-      const int as = (int)(it % Cfg::ACC);
+      const int as = (int)(it % acc_n);
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
-      const uint32_t tfull_bar = tfull0 + 8 * as, parity = (uint32_t)((it / Cfg::ACC) & 1);
+      const uint32_t tfull_bar = tfull0 + 8 * as, parity = (uint32_t)((it / acc_n) & 1);
       if constexpr (MODE == MODE_DBHEAD) {
         mbar_wait(tfull_bar, parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -755,6 +768,7 @@ static void plan_smem(TcPlan* pl) {
     int cap = atoi(e);
     if (cap >= 2 && cap < p.stages) p.stages = cap;
   }
+  p.ts = (MODE == MODE_CONV && BN <= 128 && getenv("VTD_TS")) ? 1 : 0;
   pl->smem = Cfg::smem_bytes(p.stages, p.bres ? bres_bytes : 0);
 }
 

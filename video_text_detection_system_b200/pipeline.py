@@ -39,7 +39,7 @@ class VideoTextPipeline:
         self.executor = ThreadPoolExecutor(max_workers=4)
         # batches kept in flight by process_video: each runs on its own context/stream from an executor thread, so
         # the host->device copy and the latency-bound stages of one batch overlap the convolutions of the other
-        self.inflight = int(engine_kwargs.get("inflight", 2))
+        self.inflight = int(engine_kwargs.get("inflight", 3))
         self._slot_locks = {}
 
     # ---- fused batch path -----------------------------------------------------------------------------
