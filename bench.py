@@ -221,7 +221,24 @@ def main():
         engines[w].run_batch_raw(ptrs_of(host_pool.data_ptr(), i), B, SRC_H, SRC_W, SRC_W * 3, False, 0.5, True,
                                  bias.data_ptr(), host_rec[w].data_ptr(), host_cnt[w].data_ptr())
 
-    # worker threads: ctypes releases the GIL inside the library, so NW batches really are in flight
+    # worker threads: ctypes releases the GIL inside the library, so NW batches really are in flight.  With N>1 GPUs
+    # every step ends with the gather of its records to rank 0 (NCCL); collectives must be issued in the same order
+    # on every rank, so the workers take turns in step order (a condition variable), which still lets the next
+    # batches run while a gather is in flight.
+    gather_cv = threading.Condition()
+    gather_next = [0]
+
+    def gather_in_order(w, i):
+        with gather_cv:
+            while gather_next[0] != i:
+                gather_cv.wait()
+            main_stream.wait_stream(streams[w])
+            with torch.cuda.stream(main_stream):
+                parallel.gather_records(rec_t[w], cnt_t[w], 0)
+            streams[w].wait_stream(main_stream)
+            gather_next[0] = i + 1
+            gather_cv.notify_all()
+
     class Worker(threading.Thread):
         def __init__(self, w):
             super().__init__(daemon=True)
@@ -237,6 +254,8 @@ def main():
                 try:
                     for i in steps:
                         fn(self.w, i)
+                        if world > 1:
+                            gather_in_order(self.w, i)
                     self.done.put(None)
                 except Exception as ex:      # surface failures in the main thread
                     self.done.put(ex)
@@ -246,30 +265,15 @@ def main():
         wk.start()
 
     def run_steps(fn, first, count, nw=None):
-        """`count` steps starting at index `first`, dealt round-robin to the in-flight contexts.  With N>1 GPUs the
-        records of every round are gathered to rank 0 (NCCL) before the next round starts."""
+        """`count` steps starting at index `first`, dealt round-robin to the in-flight contexts."""
         nw = nw or NW
-        if world == 1:
-            for w in range(nw):
-                workers[w].q.put((fn, list(range(first + w, first + count, nw))))
-            for w in range(nw):
-                r = workers[w].done.get()
-                if r is not None:
-                    raise r
-            return
-        for r0 in range(first, first + count, nw):
-            act = [w for w in range(nw) if r0 + w < first + count]
-            for w in act:
-                workers[w].q.put((fn, [r0 + w]))
-            for w in act:
-                r = workers[w].done.get()
-                if r is not None:
-                    raise r
-            for w in act:
-                main_stream.wait_stream(streams[w])
-                parallel.gather_records(rec_t[w], cnt_t[w], 0)
-            for w in act:
-                streams[w].wait_stream(main_stream)
+        gather_next[0] = first
+        for w in range(nw):
+            workers[w].q.put((fn, list(range(first + w, first + count, nw))))
+        for w in range(nw):
+            r = workers[w].done.get()
+            if r is not None:
+                raise r
 
     def timed(fn, steps, warmup, profile=False, nw=None):
         run_steps(fn, 0, warmup, nw)
