@@ -48,6 +48,20 @@ def peaks():
     return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
 
 
+def top_kernel_traffic(op):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_top_kernel_ncu.json), when it is the same layer; else None."""
+    p = os.path.join(ROOT, "profiles", "r01_top_kernel_ncu.json")
+    try:
+        d = json.load(open(p))
+        if (op["H"], op["W"], op["Cin"], op["Cout"], op["KH"]) == (184, 328, 256, 256, 3):
+            return {"bytes_per_launch": d["dram_bytes_per_launch"], "algorithmic_bytes_per_launch":
+                    d["algorithmic_bytes_per_launch"], "source": "profiles/r01_top_kernel_ncu.json"}
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (pynvml; same counters as nvidia-smi)."""
 
@@ -350,7 +364,8 @@ def main():
         ach = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM) %dx%d %d->%d k%d" %
                 (top["H"], top["W"], top["Cin"], top["Cout"], top["KH"]),
-                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+                "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                "traffic": top_kernel_traffic(top),
                 "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "ms_per_launch": per_launch_ms, "gflop_per_launch": per_launch_flops / 1e9,
                 "all_tc_convs": {"tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None,
