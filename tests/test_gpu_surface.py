@@ -166,3 +166,28 @@ def test_pipeline_fused_path_vs_oracle(port):
     r1 = P.recognizer.recognize(crop)
     w1 = port.recognize_batch(rec, [crop])[0]
     assert r1["text"] == w1["text"] and r1["confidence"] == pytest.approx(w1["confidence"], abs=2e-3)
+
+
+def test_nv12_run_batch_equals_bgr_run_batch(E, port):
+    """Decoder-surface ingest: the whole path on NV12 frames -- preprocess AND the crop gather read
+    the NV12 planes directly -- gives the very records it gives on cv2.cvtColor(COLOR_YUV2BGR_NV12) of those frames."""
+    import cv2
+    h, w, dh, dw, n = 180, 360, 160, 320, 2
+    det, rec = port.build_dbnet("resnet18", seed=0), port.build_crnn(seed=0)
+    rng = np.random.default_rng(11)
+    nv12 = [_nv12_from_bgr(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)),
+            rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8)]
+    bgr = [cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12) for f in nv12]
+    bias = torch.from_numpy(port.planted_logit_bias(n, dh, dw, seed=2, boxes=4)).cuda()
+    out = {}
+    for name, frames, pix in (("nv12", nv12, E.VTD_PIX_NV12), ("bgr", bgr, E.VTD_PIX_BGR)):
+        eng = E.Engine(det_h=dh, det_w=dw, max_batch=n, max_boxes=32, max_src_h=h, max_src_w=w)
+        eng.load_detector(det.state_dict())
+        eng.load_recognizer(rec.state_dict())
+        out[name] = eng.run_batch(frames, thr=0.5, recognize=True, logit_bias_dev=bias.data_ptr(), pixfmt=pix)
+        eng.close()
+    assert out["bgr"][1].sum() > 0
+    assert np.array_equal(out["nv12"][1], out["bgr"][1])
+    for i in range(n):
+        k = out["bgr"][1][i]
+        assert out["nv12"][0][i, :k].tobytes() == out["bgr"][0][i, :k].tobytes()

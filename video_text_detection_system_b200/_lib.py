@@ -207,11 +207,23 @@ class Engine:
 
     # ---- helpers
     @staticmethod
-    def _frame_ptrs(frames) -> Tuple[C.Array, int, int, int, list]:
-        """frames: sequence of HxWx3 uint8 arrays (same shape) or an [n,H,W,3] array."""
+    def _frame_ptrs(frames, pixfmt: int = VTD_PIX_BGR) -> Tuple[C.Array, int, int, int, list]:
+        """frames: sequence of HxWx3 uint8 arrays (same shape) or an [n,H,W,3] array; NV12: (H*3/2)xW uint8 planes."""
         keep = []
         ptrs = (C.c_void_p * len(frames))()
         h = w = pitch = None
+        if pixfmt == VTD_PIX_NV12:
+            for i, f in enumerate(frames):
+                if not isinstance(f, np.ndarray) or f.dtype != np.uint8 or f.ndim != 2 or f.shape[0] % 3 or f.shape[1] % 2:
+                    raise ValueError("NV12 frames must be (H*3/2)xW uint8 arrays with even H and W")
+                f = np.ascontiguousarray(f)
+                if h is None:
+                    h, w, pitch = f.shape[0] * 2 // 3, f.shape[1], f.strides[0]
+                elif (f.shape[0] * 2 // 3, f.shape[1]) != (h, w):
+                    raise ValueError("all frames of a batch must have the same size")
+                keep.append(f)
+                ptrs[i] = f.ctypes.data
+            return ptrs, h, w, pitch, keep
         for i, f in enumerate(frames):
             if not isinstance(f, np.ndarray) or f.dtype != np.uint8 or f.ndim != 3 or f.shape[2] != 3:
                 raise ValueError("frames must be HxWx3 uint8 arrays")
@@ -231,7 +243,7 @@ class Engine:
 
     # ---- stages
     def preprocess(self, frames, pixfmt: int = VTD_PIX_BGR):
-        ptrs, h, w, pitch, keep = self._frame_ptrs(frames)
+        ptrs, h, w, pitch, keep = self._frame_ptrs(frames, pixfmt)
         self._check(self.lib.vtd_preprocess(self._h, C.cast(ptrs, _u8pp), len(frames), h, w, pitch, pixfmt, 0))
         self.sync()
 
@@ -288,7 +300,7 @@ class Engine:
 
     def run_batch(self, frames, thr: float = 0.5, recognize: bool = True, logit_bias_dev: int = 0,
                   pixfmt: int = VTD_PIX_BGR, read: bool = True):
-        ptrs, h, w, pitch, keep = self._frame_ptrs(frames)
+        ptrs, h, w, pitch, keep = self._frame_ptrs(frames, pixfmt)
         n = len(frames)
         rec = np.zeros((n, self.max_boxes), RECORD_DTYPE) if read else None
         cnt = np.zeros(n, np.int32) if read else None

@@ -683,7 +683,6 @@ int extract_locked(vtd_ctx* c, int n, int orig_h, int orig_w) {
 }
 
 int recognize_locked(vtd_ctx* c, int n) {
-  if (c->cur_pix != VTD_PIX_BGR) FAIL(VTD_ERR_STATE, "crops are taken from BGR frames; the current batch is NV12");
   CK(scan_counts(c->counts, n, c->offsets, c->stream, &c->lc));
   CK(cudaMemcpyAsync(c->pinned_int, c->offsets + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -692,10 +691,12 @@ int recognize_locked(vtd_ctx* c, int n) {
     const int nc = total - first < c->rc ? total - first : c->rc;
     if (c->bf16_mode)
       CK(crop_resize_records<bf16>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
-                                   c->cfg.max_boxes, first, nc, c->cfg.crop_w, (bf16*)c->crops, c->crops_lay, c->stream, &c->lc));
+                                   c->cfg.max_boxes, first, nc, c->cfg.crop_w, c->cur_pix == VTD_PIX_NV12, (bf16*)c->crops, c->crops_lay,
+                                   c->stream, &c->lc));
     else
       CK(crop_resize_records<float>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
-                                    c->cfg.max_boxes, first, nc, c->cfg.crop_w, (float*)c->crops, c->crops_lay, c->stream, &c->lc));
+                                    c->cfg.max_boxes, first, nc, c->cfg.crop_w, c->cur_pix == VTD_PIX_NV12, (float*)c->crops, c->crops_lay,
+                                    c->stream, &c->lc));
     int r = run_crnn(c, nc); if (r) return r;
     CK(ctc_into_records(c->logits, nc, first, c->T, 97, c->logits_ld, c->cfg.canonical_ctc, c->offsets, n, c->cfg.max_boxes,
                         c->records, c->stream, &c->lc));

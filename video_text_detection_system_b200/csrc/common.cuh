@@ -125,7 +125,8 @@ cudaError_t scan_counts(const int* counts, int n, int* offsets /*[n+1]*/, cudaSt
 template <typename T>
 cudaError_t crop_resize_records(const uint8_t* const* frames_dev, int src_h, int src_w, int pitch,
                                 const void* records, const int* offsets, int n, int kmax, int first_crop,
-                                int n_crops, int crop_w, T* out, OutLayout lay, cudaStream_t s, LaunchCounter* lc);
+                                int n_crops, int crop_w, int nv12 /*frames are NV12, converted on the fly*/, T* out,
+                                OutLayout lay, cudaStream_t s, LaunchCounter* lc);
 template <typename T>
 cudaError_t crop_resize_list(const uint8_t* const* crops_dev, const int* h, const int* w, const int* pitch,
                              int n_crops, int crop_w, T* out, OutLayout lay, cudaStream_t s, LaunchCounter* lc);

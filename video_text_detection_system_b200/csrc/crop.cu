@@ -54,10 +54,23 @@ template <> __device__ __forceinline__ void store_px<bf16>(bf16* o, float b, flo
   }
 }
 
-template <typename T>
+// BT.601 limited-range NV12 -> B,G,R (cv2.cvtColor COLOR_YUV2BGR_NV12 fixed point, bit-exact): the decoder-surface
+// ingest path crops straight from the NV12 frame, which equals converting the frame first and cropping after.
+__device__ __forceinline__ int nv12_px(const uint8_t* __restrict__ f, int frame_h, int pitch, int y, int x, int c) {
+  int Y = f[(size_t)y * pitch + x];
+  const uint8_t* uv = f + (size_t)frame_h * pitch + (size_t)(y >> 1) * pitch + (x & ~1);
+  int u = (int)uv[0] - 128, v = (int)uv[1] - 128;
+  int yy = max(0, Y - 16) * 1220542;
+  int val = c == 2 ? (yy + (1 << 19) + 1673527 * v) >> 20
+                   : (c == 1 ? (yy + (1 << 19) - 852492 * v - 409993 * u) >> 20 : (yy + (1 << 19) + 2116026 * u) >> 20);
+  return val < 0 ? 0 : (val > 255 ? 255 : val);
+}
+
+// NV12 = true: `src` is the whole frame (frame_h rows of Y then UV), (x0,y0) the crop origin
+template <typename T, bool NV12>
 __device__ void resize_one(const uint8_t* __restrict__ src, int pitch, int h, int w, int crop_w,
                            T* __restrict__ out /*pixel (0,0) of this crop*/, OutLayout lay, Tap* xt /*smem [crop_w]*/,
-                           Tap* yt /*smem [CH]*/) {
+                           Tap* yt /*smem [CH]*/, int frame_h = 0, int x0 = 0, int y0 = 0) {
   for (int i = threadIdx.x; i < crop_w; i += blockDim.x) xt[i] = cv_tap(i, w, crop_w);
   for (int i = threadIdx.x; i < CH; i += blockDim.x) yt[i] = cv_tap(i, h, CH);
   __syncthreads();
@@ -69,8 +82,15 @@ __device__ void resize_one(const uint8_t* __restrict__ src, int pitch, int h, in
     float v[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      int h0 = (int)r0[tx.s0 * 3 + c] * tx.a0 + (int)r0[tx.s1 * 3 + c] * tx.a1;
-      int h1 = (int)r1[tx.s0 * 3 + c] * tx.a0 + (int)r1[tx.s1 * 3 + c] * tx.a1;
+      int p00, p01, p10, p11;
+      if (NV12) {
+        p00 = nv12_px(src, frame_h, pitch, y0 + ty.s0, x0 + tx.s0, c); p01 = nv12_px(src, frame_h, pitch, y0 + ty.s0, x0 + tx.s1, c);
+        p10 = nv12_px(src, frame_h, pitch, y0 + ty.s1, x0 + tx.s0, c); p11 = nv12_px(src, frame_h, pitch, y0 + ty.s1, x0 + tx.s1, c);
+      } else {
+        p00 = r0[tx.s0 * 3 + c]; p01 = r0[tx.s1 * 3 + c]; p10 = r1[tx.s0 * 3 + c]; p11 = r1[tx.s1 * 3 + c];
+      }
+      int h0 = p00 * tx.a0 + p01 * tx.a1;
+      int h1 = p10 * tx.a0 + p11 * tx.a1;
       int o = (((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
       o = o < 0 ? 0 : (o > 255 ? 255 : o);
       v[c] = __fdiv_rn((float)o, 255.0f);                      // .float() / 255.0
@@ -80,7 +100,7 @@ __device__ void resize_one(const uint8_t* __restrict__ src, int pitch, int h, in
 }
 
 // records: [n][kmax]; offsets: [n+1] exclusive prefix of counts; one CTA per crop.
-template <typename T>
+template <typename T, bool NV12>
 __global__ void __launch_bounds__(256) crop_records_kernel(const uint8_t* const* __restrict__ frames, int src_h,
                                                            int src_w, int pitch,
                                                            const vtd_record* __restrict__ records,
@@ -103,8 +123,12 @@ __global__ void __launch_bounds__(256) crop_records_kernel(const uint8_t* const*
       store_px<T>(o + (i / crop_w) * lay.row_pitch + (long long)(i % crop_w) * lay.cpp, 0.f, 0.f, 0.f, lay.cpp);
     return;
   }
-  const uint8_t* src = frames[f] + (size_t)y1 * pitch + (size_t)x1 * 3;
-  resize_one<T>(src, pitch, h, w, crop_w, o, lay, taps, taps + crop_w);
+  if (NV12) {
+    resize_one<T, true>(frames[f], pitch, h, w, crop_w, o, lay, taps, taps + crop_w, src_h, x1, y1);
+  } else {
+    const uint8_t* src = frames[f] + (size_t)y1 * pitch + (size_t)x1 * 3;
+    resize_one<T, false>(src, pitch, h, w, crop_w, o, lay, taps, taps + crop_w);
+  }
 }
 
 template <typename T>
@@ -114,8 +138,8 @@ __global__ void __launch_bounds__(256) crop_list_kernel(const uint8_t* const* __
                                                         T* __restrict__ out, OutLayout lay) {
   extern __shared__ Tap taps[];
   const int ci = blockIdx.x;
-  resize_one<T>(crops[ci], pitches[ci], hs[ci], ws[ci], crop_w, out + lay.offset + ci * lay.img_pitch, lay, taps,
-                taps + crop_w);
+  resize_one<T, false>(crops[ci], pitches[ci], hs[ci], ws[ci], crop_w, out + lay.offset + ci * lay.img_pitch, lay, taps,
+                       taps + crop_w);
 }
 
 __global__ void scan_counts_kernel(const int* __restrict__ counts, int n, int* __restrict__ offsets) {
@@ -137,12 +161,18 @@ cudaError_t scan_counts(const int* counts, int n, int* offsets, cudaStream_t s, 
 template <typename T>
 cudaError_t crop_resize_records(const uint8_t* const* frames_dev, int src_h, int src_w, int pitch,
                                 const void* records, const int* offsets, int n, int kmax, int first_crop,
-                                int n_crops, int crop_w, T* out, OutLayout lay, cudaStream_t s, LaunchCounter* lc) {
+                                int n_crops, int crop_w, int nv12, T* out, OutLayout lay, cudaStream_t s,
+                                LaunchCounter* lc) {
   if (n_crops <= 0) return cudaSuccess;
   size_t smem = sizeof(Tap) * (crop_w + CH);
-  crop_records_kernel<T><<<n_crops, 256, smem, s>>>(frames_dev, src_h, src_w, pitch,
-                                                    reinterpret_cast<const vtd_record*>(records), offsets, n, kmax,
-                                                    first_crop, crop_w, out, lay);
+  if (nv12)
+    crop_records_kernel<T, true><<<n_crops, 256, smem, s>>>(frames_dev, src_h, src_w, pitch,
+                                                            reinterpret_cast<const vtd_record*>(records), offsets, n,
+                                                            kmax, first_crop, crop_w, out, lay);
+  else
+    crop_records_kernel<T, false><<<n_crops, 256, smem, s>>>(frames_dev, src_h, src_w, pitch,
+                                                             reinterpret_cast<const vtd_record*>(records), offsets, n,
+                                                             kmax, first_crop, crop_w, out, lay);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
@@ -159,7 +189,8 @@ cudaError_t crop_resize_list(const uint8_t* const* crops_dev, const int* h, cons
 
 #define INST(T)                                                                                                  \
   template cudaError_t crop_resize_records<T>(const uint8_t* const*, int, int, int, const void*, const int*, int, \
-                                              int, int, int, int, T*, OutLayout, cudaStream_t, LaunchCounter*);  \
+                                              int, int, int, int, int, T*, OutLayout, cudaStream_t,              \
+                                              LaunchCounter*);                                                   \
   template cudaError_t crop_resize_list<T>(const uint8_t* const*, const int*, const int*, const int*, int, int,  \
                                            T*, OutLayout, cudaStream_t, LaunchCounter*);
 INST(float)
