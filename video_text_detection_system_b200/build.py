@@ -50,7 +50,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def run(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("VTD_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (s, r.stdout, r.stderr))

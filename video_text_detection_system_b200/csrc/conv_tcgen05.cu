@@ -42,6 +42,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace vtd {
 
@@ -55,6 +56,8 @@ constexpr int NUM_EPI_WARPS = 8;
 struct alignas(64) TcMaps {
   CUtensorMap a[4];     // activation maps; [0] only for stride 1, [py*2+px] for stride 2
   CUtensorMap b;        // weights
+  CUtensorMap o;        // output (TMA-store epilogue): box = one epilogue warp's 32 pixels x 128 bytes of channels
+  CUtensorMap r;        // residual (TMA-store epilogue with p.res_tma): the source pixels of that box
 };
 
 enum { MODE_CONV = 0, MODE_WIN = 1, MODE_DBHEAD = 2, MODE_LSTM = 3 };
@@ -64,13 +67,18 @@ struct TcParams {
   int KH, KW, stride, pad;
   int lw, lh;                 // log2(BW), log2(BH); BN = 128 >> (lw+lh)
   int tiles_x, tiles_y, tiles_n, n_blocks;
-  long long total_tiles;
+  int total_tiles;
   int relu, res_mode, out_f32;
   const float* bias;
   const bf16* res;
   void* out;
   int stages, bres;           // operand ring depth; 1 = all weight K-slices stay resident in shared memory
-  int ts;                     // 1 = operand A is staged smem -> TMEM (tcgen05.cp) and the MMAs use the TS form
+  int epi_tma;                // 1 = epilogue stages 32 px x 128 B per warp in shared memory and leaves with a TMA store
+  int res_tma;                // 1 = the residual of each warp's box arrives by TMA into shared memory, one item ahead
+  int res_bytes;              // bytes of one residual box
+  int kps;                    // K steps per ring slot: one full/empty handshake (and one tcgen05.commit) per kps steps
+  long long* timers;          // VTD_TIMERS builds: [grid][3 roles][total, wait, wait2] cycles
+  int dbg;                    // VTD_DBG timing experiments (results are wrong): 1 no A loads, 2 no MMAs, 4 no stores
   // MODE_WIN
   int nr, sdiv;               // filter rows (= K steps), row phases (= conv stride)
   // MODE_DBHEAD
@@ -88,6 +96,18 @@ struct HeadConsts {            // DB head tail constants, passed in the kernel p
   float pad_;
 };
 struct NoExtra { int unused; };
+
+// -DVTD_TIMERS (dev builds only): per-role wait/total cycle counters, printed per launch by launch_tc()
+#ifdef VTD_TIMERS
+#define TMR_DECL long long tmr_wait = 0, tmr_wait2 = 0; const long long tmr_t0 = clock64();
+#define TMR_WAIT(acc, stmt) { const long long _a = clock64(); stmt; acc += clock64() - _a; }
+#define TMR_STORE(role) if (lane == 0 && p.timers) { long long* o = p.timers + ((size_t)blockIdx.x * 3 + role) * 3; \
+    o[0] = clock64() - tmr_t0; o[1] = tmr_wait; o[2] = tmr_wait2; }
+#else
+#define TMR_DECL
+#define TMR_WAIT(acc, stmt) { stmt; }
+#define TMR_STORE(role)
+#endif
 template <int MODE> struct ExtraOf { typedef NoExtra type; };
 template <> struct ExtraOf<MODE_DBHEAD> { typedef HeadConsts type; };
 
@@ -100,7 +120,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = MODE == MODE_WIN ? 12 : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
   static constexpr int MAX_STAGES = 16;
-  static constexpr int TAIL_BYTES = 8 * (2 * MAX_STAGES + 10) + 16 + (MODE == MODE_DBHEAD ? 4096 : 0);   // barriers, TMEM slot, head consts
+  static constexpr int TAIL_BYTES = 8 * (2 * MAX_STAGES + 18) + 16 + (MODE == MODE_DBHEAD ? 4096 : 0);   // barriers, TMEM slot, head consts
   // dynamic shared memory for a given ring depth / resident-weight size
   static constexpr int smem_bytes(int stages, int bres_bytes) {
     return stages * (bres_bytes ? A_BYTES : STAGE_BYTES) + bres_bytes + 1024 /*alignment slack*/ + TAIL_BYTES;
@@ -122,7 +142,8 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
   constexpr int NCH = BLOCK_N / 64;                  // 32-column chunks per warp
   const int cbase = half * (BLOCK_N / 2);
   uint4 rv[NCH][4];
-  const bool has_res = p.res_mode != RES_NONE;
+  const bool has_res = p.res_mode != RES_NONE && !(p.dbg & 12);
+  if (p.dbg & 4) valid = false;
   if (has_res && valid) {
     const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + nb * BLOCK_N + cbase);
 #pragma unroll
@@ -184,6 +205,86 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
         }
       }
     }
+  }
+}
+
+// MODE_CONV / MODE_WIN with p.epi_tma: the same arithmetic, but the tile leaves through shared memory and TMA stores.
+// Per-thread stores write 16 bytes per lane at a pixel stride (32 sectors touched per warp instruction, half of each
+// used); here a warp packs its 32 pixels x 128 bytes of channels (64 bf16 or 32 fp32: one "group") into a 4 KB
+// 128B-swizzled staging block and one lane issues cp.async.bulk.tensor: full 128-byte rows, out-of-range pixels are
+// clipped by the tensor map, and the store drains while the warp converts the next group.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUtensorMap* omap, uint32_t stg, uint32_t tmem_acc,
+                                                   int q, int lane, int g, bool use_res, const uint4 (&rv)[8], int nb, int cx,
+                                                   int cy, int cn) {
+  const int gcols = p.out_f32 ? 32 : 64;                 // accumulator columns per 128-byte group
+  const uint32_t row = stg + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  const int c0 = g * gcols;                              // first column of the group inside the tile
+  const int co = nb * BLOCK_N + c0;
+  uint4 o[8];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    if (p.out_f32 && hh == 1) break;
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + hh * 32), v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + co + hh * 32 + j));
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+      }
+    }
+    if (use_res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[hh * 4 + j]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 r2 = __bfloat1622float2(h[e]);
+          f[j * 8 + e * 2] += r2.x; f[j * 8 + e * 2 + 1] += r2.y;
+        }
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (p.out_f32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                          __float_as_uint(f[4 * j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+        o[hh * 4 + j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                   *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+      }
+    }
+  }
+  if (p.dbg & 4) return;
+  // the previous store of this warp must have finished READING the staging block before it is overwritten
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)j ^ sw) << 4)), "r"(o[j].x), "r"(o[j].y),
+                 "r"(o[j].z), "r"(o[j].w) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(omap), "r"(stg),
+                 "r"(co), "r"(cx), "r"(cy), "r"(cn) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
 }
 
@@ -307,7 +408,7 @@ __device__ __forceinline__ void epilogue_lstm(const TcParams& p, uint32_t tmem_a
   }
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int KPS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
                const __grid_constant__ typename ExtraOf<MODE>::type ex) {
@@ -319,18 +420,23 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const uint32_t ring = (raw + 1023u) & ~1023u;
   uint8_t* ring_ptr = smem_raw + (ring - raw);
   const int stages = p.stages;
-  const uint32_t stage_bytes = p.bres ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
+  constexpr int kps = KPS;                       // K steps per ring slot (host: ksteps % KPS == 0)
+  const uint32_t step_bytes = p.bres ? Cfg::A_BYTES : Cfg::STAGE_BYTES;      // bytes one K step brings in
+  const uint32_t stage_bytes = (uint32_t)kps * step_bytes;                   // slot = kps A slabs, then kps B slabs
   const int ksteps_all = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
   const uint32_t bres0 = ring + stages * stage_bytes;                       // resident weight K-slices (if p.bres)
   const uint32_t bres_bytes = p.bres ? (uint32_t)ksteps_all * Cfg::B_STAGE_BYTES : 0u;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + stages * stage_bytes + bres_bytes);
+  const uint32_t stg_bytes = (p.epi_tma ? (uint32_t)NUM_EPI_WARPS * 4096u : 0u) + (p.res_tma ? (uint32_t)NUM_EPI_WARPS * 4096u : 0u);
+  const uint32_t stg0 = bres0 + bres_bytes;                                  // 4 KB of store staging per epilogue warp
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + stages * stage_bytes + bres_bytes + stg_bytes);
   const uint32_t full0 = smem_u32(bars);                       // [MAX_STAGES]
   const uint32_t empty0 = full0 + 8 * Cfg::MAX_STAGES;         // [MAX_STAGES]
   const uint32_t tfull0 = empty0 + 8 * Cfg::MAX_STAGES;        // [4]
   const uint32_t tempty0 = tfull0 + 32;                        // [4]
   const uint32_t bfull = tempty0 + 32;                         // [1] resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::MAX_STAGES + 9);
-  float* head_s = reinterpret_cast<float*>(bars + 2 * Cfg::MAX_STAGES + 10);   // MODE_DBHEAD: [2 heads][256 b1 + 256 w2]
+  const uint32_t rbar0 = bfull + 16;                           // [8] residual box landed, one per epilogue warp
+  float* head_s = reinterpret_cast<float*>(bars + 2 * Cfg::MAX_STAGES + 18);   // MODE_DBHEAD: [2 heads][256 b1 + 256 w2]
   if constexpr (MODE == MODE_DBHEAD) {
     for (int i = threadIdx.x; i < 2 * 512; i += NUM_THREADS) {
       const int hd = i >> 9, r = i & 511;
@@ -342,8 +448,13 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < Cfg::ACC; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
+    // BLOCK_N = 64 with the TMA-store epilogue: the two halves of the epilogue take alternate tiles (4 arrivals each)
+    const uint32_t epi_arrivals = (BLOCK_N == 64 && p.epi_tma) ? NUM_EPI_WARPS / 2 : NUM_EPI_WARPS;
+    for (int i = 0; i < Cfg::ACC; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, epi_arrivals); }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.o) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.r) : "memory");
     mbar_init(bfull, 1);
+    for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(rbar0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
@@ -365,138 +476,216 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
 
   const int BW = 1 << p.lw, BH = 1 << p.lh;
   const int BNt = BLOCK_M >> (p.lw + p.lh);
-  const int acc_n = p.ts ? 2 : Cfg::ACC;                 // TS mode keeps columns [2*BLOCK_N, 2*BLOCK_N+64) for operand A
+  constexpr int acc_n = Cfg::ACC;
   const int kchunks = p.Cin / BLOCK_K;
   const int ksteps = MODE == MODE_WIN ? p.nr : p.KH * p.KW * kchunks;
+  const int total_tiles = p.total_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
-    {
-      int stage = 0; uint32_t phase = 0;
-      if (p.bres && blockIdx.x < p.total_tiles) {      // weights once per CTA (n_blocks == 1)
-        if (elect_one()) {
-          mbar_expect_tx(bfull, bres_bytes);
-          for (int ks = 0; ks < ksteps_all; ++ks)
-            tma_load_2d(bres0 + ks * Cfg::B_STAGE_BYTES, &maps.b, bfull, ks * (ROWB / 2), 0);
-        }
-        __syncwarp();
+    // One ring slot holds kps K steps: the per-slot handshake (empty wait, expect_tx, the consumer's full wait and
+    // tcgen05.commit) costs a few hundred cycles whatever the slot holds (profiles/micro/handshake.cu), which is more
+    // than the MMAs of ONE K step take on the narrow layers.
+    int stage = 0; uint32_t phase = 0;
+    TMR_DECL
+    if (p.bres && (int)blockIdx.x < total_tiles) {      // weights once per CTA (n_blocks == 1)
+      if (elect_one()) {
+        mbar_expect_tx(bfull, bres_bytes);
+        for (int ks = 0; ks < ksteps_all; ++ks)
+          tma_load_2d(bres0 + ks * Cfg::B_STAGE_BYTES, &maps.b, bfull, ks * (ROWB / 2), 0);
       }
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        long long t = tile;
-        const int nb = (int)(t % p.n_blocks); t /= p.n_blocks;
-        const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
-        const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
-        const int x0 = tx * BW, y0 = ty * BH, n0 = (int)t * BNt;
-        if (MODE == MODE_WIN) {
-          for (int r = 0; r < p.nr; ++r) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            if (elect_one()) {
-              const uint32_t sa = ring + stage * stage_bytes;
-              const uint32_t fb = full0 + 8 * stage;
-              mbar_expect_tx(fb, stage_bytes);
-              tma_load_5d(sa, &maps.a[0], fb, 0, x0, r % p.sdiv, y0 + r / p.sdiv, n0);
-              if (!p.bres) tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, r * 32, nb * BLOCK_N);
-            }
-            __syncwarp();
-            if (++stage == stages) { stage = 0; phase ^= 1; }
+      __syncwarp();
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int nb = t % p.n_blocks; t /= p.n_blocks;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int x0 = tx * BW, y0 = ty * BH, n0 = t * BNt;
+      int r = 0, sx = 0, kc = 0;                          // filter row, filter column, 64-channel chunk of the next K step
+      for (int ks0 = 0; ks0 < ksteps; ks0 += kps) {
+        constexpr int nk = kps;
+        TMR_WAIT(tmr_wait, mbar_wait(empty0 + 8 * stage, phase ^ 1))
+        if (elect_one()) {
+          const uint32_t sa = ring + stage * stage_bytes;
+          const uint32_t sb = sa + (uint32_t)kps * Cfg::A_BYTES;
+          const uint32_t fb = full0 + 8 * stage;
+          if (p.dbg & 1) {
+            if (p.bres) mbar_arrive(fb); else mbar_expect_tx(fb, (uint32_t)nk * Cfg::B_STAGE_BYTES);
+          } else {
+            mbar_expect_tx(fb, (uint32_t)nk * step_bytes);
           }
-        } else {
-          for (int r = 0; r < p.KH; ++r) {
-            for (int s = 0; s < p.KW; ++s) {
+#pragma unroll
+          for (int j = 0; j < nk; ++j) {
+            if (MODE == MODE_WIN) {
+              if (!(p.dbg & 1)) tma_load_5d(sa + j * Cfg::A_BYTES, &maps.a[0], fb, 0, x0, r % p.sdiv, y0 + r / p.sdiv, n0);
+              if (!p.bres) tma_load_2d(sb + j * Cfg::B_STAGE_BYTES, &maps.b, fb, r * 32, nb * BLOCK_N);
+              ++r;
+            } else {
               int mi = 0, xo, yo, coff = 0;
               if (MODE == MODE_DBHEAD) { xo = yo = 0; coff = nb * 64; }
               else if (MODE == MODE_LSTM) { xo = yo = 0; mi = nb >> 2; }
-              else if (p.stride == 1) { xo = s - p.pad; yo = r - p.pad; }
+              else if (p.stride == 1) { xo = sx - p.pad; yo = r - p.pad; }
               else {
-                const int tyy = r - p.pad, txx = s - p.pad;
+                const int tyy = r - p.pad, txx = sx - p.pad;
                 const int py = tyy & 1, px = txx & 1;
                 mi = py * 2 + px; yo = (tyy - py) / 2; xo = (txx - px) / 2;
               }
-              const int kbase = (r * p.KW + s) * p.Cin;
-              for (int kc = 0; kc < kchunks; ++kc) {
-                mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                if (elect_one()) {
-                  const uint32_t sa = ring + stage * stage_bytes;
-                  const uint32_t fb = full0 + 8 * stage;
-                  mbar_expect_tx(fb, stage_bytes);
-                  tma_load_4d(sa, &maps.a[mi], fb, coff + kc * BLOCK_K, x0 + xo, y0 + yo, n0);
-                  if (!p.bres) tma_load_2d(sa + Cfg::A_BYTES, &maps.b, fb, kbase + kc * BLOCK_K, nb * BLOCK_N);
-                }
-                __syncwarp();
-                if (++stage == stages) { stage = 0; phase ^= 1; }
-              }
+              if (!(p.dbg & 1)) tma_load_4d(sa + j * Cfg::A_BYTES, &maps.a[mi], fb, coff + kc * BLOCK_K, x0 + xo, y0 + yo, n0);
+              if (!p.bres)
+                tma_load_2d(sb + j * Cfg::B_STAGE_BYTES, &maps.b, fb, (r * p.KW + sx) * p.Cin + kc * BLOCK_K, nb * BLOCK_N);
+              if (++kc == kchunks) { kc = 0; if (++sx == p.KW) { sx = 0; ++r; } }
             }
           }
         }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
     }
+    TMR_STORE(0)
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-    {
-      // SPLIT > 1 issues each K=16 step as SPLIT narrower MMAs into independent column ranges of the accumulator.
-      // Measured on B200 (profiles/r01_ncu_notes.md): it is SLOWER (256->256 3x3: 0.836 -> 0.914 ms) -- an MMA with
-      // M=128 costs ~128 cycles whatever its N (the A operand is re-read from shared memory per instruction), so
-      // fewer, wider instructions win.  Kept as a knob; 1 = one MMA of the full tile width.
-      constexpr int SPLIT = 1;
-      constexpr int SUBN = BLOCK_N / SPLIT;
-      const uint32_t idesc = umma_idesc(SUBN);
-      int stage = 0; uint32_t phase = 0;
-      long long it = 0;
-      if (p.bres && blockIdx.x < p.total_tiles) mbar_wait(bfull, 0);
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int as = (int)(it % acc_n);
-        mbar_wait(tempty0 + 8 * as, (uint32_t)((it / acc_n) & 1) ^ 1);
+    const uint32_t idesc = umma_idesc(BLOCK_N);
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    TMR_DECL
+    if (p.bres && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TMR_WAIT(tmr_wait2, mbar_wait(tempty0 + 8 * as, aphase ^ 1))
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+      for (int ks0 = 0; ks0 < ksteps; ks0 += kps) {
+        constexpr int nk = kps;
+        TMR_WAIT(tmr_wait, mbar_wait(full0 + 8 * stage, phase))
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
-        for (int ks = 0; ks < ksteps; ++ks) {
-          mbar_wait(full0 + 8 * stage, phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (elect_one()) {
-            const uint32_t sa = ring + stage * stage_bytes;
-            const uint64_t ad = umma_desc<ROWB>(sa);
-            const uint64_t bd = umma_desc<ROWB>(p.bres ? bres0 + ks * Cfg::B_STAGE_BYTES : sa + Cfg::A_BYTES);
-            if (MODE == MODE_CONV && BLOCK_N <= 128 && p.ts) {
-              // operand A through tensor memory: an SS-form MMA with M=128 re-reads its 4 KB A slab from shared
-              // memory at ~32 B/cycle (~128 cycles per instruction whatever N is); tcgen05.cp moves the slab once at
-              // full shared-memory bandwidth and the TS-form MMAs then run at N/2 cycles.
-              const uint32_t a_t = tmem_base + (uint32_t)(2 * BLOCK_N) + (uint32_t)((ks & 1) * 32);
+        if (elect_one()) {
+          const uint32_t sa = ring + stage * stage_bytes;
+          const uint32_t sb = sa + (uint32_t)kps * Cfg::A_BYTES;
+          if (!(p.dbg & 2)) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) tmem_cp_128x256b(a_t + (uint32_t)(k * 8), ad + (uint64_t)(k * 2));
+            for (int j = 0; j < nk; ++j) {
+              const uint64_t ad = umma_desc<ROWB>(sa + j * Cfg::A_BYTES);
+              const uint64_t bd = umma_desc<ROWB>(p.bres ? bres0 + (ks0 + j) * Cfg::B_STAGE_BYTES : sb + j * Cfg::B_STAGE_BYTES);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16_ts(d_tmem, a_t + (uint32_t)(k * 8), bd + (uint64_t)(k * 2), idesc, (ks | k) ? 1u : 0u);
-            } else
-#pragma unroll
-            for (int k = 0; k < ROWB / 32; ++k)
-#pragma unroll
-              for (int j = 0; j < SPLIT; ++j)      // sub-tile j: B rows j*SUBN.. (SUBN*ROWB bytes further), D columns j*SUBN..
-                umma_f16(d_tmem + (uint32_t)(j * SUBN), ad + (uint64_t)(k * 2),
-                         bd + (uint64_t)(k * 2 + ((j * SUBN * ROWB) >> 4)), idesc, (ks | k) ? 1u : 0u);
-            umma_commit(empty0 + 8 * stage);            // frees the slot when these MMAs have read it
-            if (ks == ksteps - 1) umma_commit(tfull0 + 8 * as);   // accumulator complete
+              for (int k = 0; k < ROWB / 32; ++k)
+                umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ks0 | j | k) ? 1u : 0u);
+            }
           }
-          __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          umma_commit(empty0 + 8 * stage);            // frees the slot when these MMAs have read it
+          if (ks0 + nk >= ksteps) umma_commit(tfull0 + 8 * as);   // accumulator complete
         }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
+      if (++as == acc_n) { as = 0; aphase ^= 1; }
     }
+    TMR_STORE(1)
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;                   // which half of the tile's columns / units / rows
     const int m = q * 32 + lane;                        // row of the tile = pixel
     const int xx = m & (BW - 1), yy = (m >> p.lw) & (BH - 1), nn = m >> (p.lw + p.lh);
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      long long t = tile;
-      const int nb = (int)(t % p.n_blocks); t /= p.n_blocks;
-      const int tx = (int)(t % p.tiles_x); t /= p.tiles_x;
-      const int ty = (int)(t % p.tiles_y); t /= p.tiles_y;
-      const int ox = tx * BW + xx, oy = ty * BH + yy, n = (int)t * BNt + nn;
+    if ((MODE == MODE_CONV || MODE == MODE_WIN) && p.epi_tma) {
+      // ---- TMA-store epilogue.  Work items = (tile, 128-byte channel group); N = 64 tiles have one group, so the two
+      // halves take alternate tiles; wider tiles split their groups between the halves.  The residual of the NEXT work
+      // item (next group, or the first group of this warp's next tile) is requested before the current one is
+      // converted, so its L2/DRAM latency never sits between an accumulator and its store.
+      const int step = (BLOCK_N == 64 ? 2 : 1) * (int)gridDim.x;
+      const int groups = (p.out_f32 ? BLOCK_N * 4 : BLOCK_N * 2) / 128;
+      const int g0 = BLOCK_N == 64 ? 0 : half * (groups / 2), g1 = BLOCK_N == 64 ? groups : g0 + groups / 2;
+      const bool use_res = p.res_mode != RES_NONE && !(p.dbg & 12);
+      const uint32_t stg = stg0 + (uint32_t)(warp - 2) * 4096u;
+      const int m0 = q * 32;                              // first pixel of this warp inside the tile
+      const int gcols = p.out_f32 ? 32 : 64;
+      // residual: per-lane loads (16 B per lane at a pixel stride) cost one L1 tag lookup per lane and instruction; with
+      // p.res_tma the source pixels of the warp's box arrive by TMA (requested one work item ahead) and each lane reads
+      // its 128-byte row from shared memory.
+      const uint32_t rbuf = stg0 + (uint32_t)NUM_EPI_WARPS * 4096u + (uint32_t)(warp - 2) * 4096u;
+      const uint32_t rbar = rbar0 + 8 * (uint32_t)(warp - 2);
+      const int up = p.res_mode == RES_UP2 ? 1 : 0;
+      const int sw_ = BW < 32 ? BW : 32, sh_ = BH < 32 / sw_ ? BH : 32 / sw_;           // the warp's box: sw_ x sh_ x sn_ pixels
+      const int lx = lane & (sw_ - 1), ly = (lane / sw_) & (sh_ - 1), ln = lane / (sw_ * sh_);
+      const int rw = up ? (sw_ > 1 ? sw_ >> 1 : 1) : sw_, rh = up ? (sh_ > 1 ? sh_ >> 1 : 1) : sh_;
+      const int rrow = (ln * rh + (up ? (sh_ > 1 ? ly >> 1 : 0) : ly)) * rw + (up ? lx >> 1 : lx);   // my row of the residual box
+      const uint32_t raddr = rbuf + (uint32_t)rrow * 128u;
+      const uint32_t rsw = (uint32_t)(rrow & 7);
+      uint32_t rphase = 0;
+      auto res_issue = [&](int tile_, int g_) {
+        int t = tile_;
+        const int nb = t % p.n_blocks; t /= p.n_blocks;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int cx = tx * BW + (m0 & (BW - 1)), cy = ty * BH + ((m0 >> p.lw) & (BH - 1)), cn = t * BNt + (m0 >> (p.lw + p.lh));
+        if (lane == 0) {
+          mbar_expect_tx(rbar, (uint32_t)p.res_bytes);
+          tma_load_4d(rbuf, &maps.r, rbar, nb * BLOCK_N + g_ * gcols, cx >> up, cy >> up, cn);
+        }
+      };
+      auto res_load = [&](int tile_, int g_, uint4 (&r)[8]) {
+        int t = tile_;
+        const int nb = t % p.n_blocks; t /= p.n_blocks;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int ox = tx * BW + xx, oy = ty * BH + yy, n = t * BNt + nn;
+        if (ox < p.Wo && oy < p.Ho && n < p.N) {
+          const size_t rpix = p.res_mode == RES_SAME ? ((size_t)n * p.Ho + oy) * p.Wo + ox
+                                                     : ((size_t)n * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + nb * BLOCK_N + g_ * gcols);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = __ldg(rp + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      int tile = blockIdx.x + (BLOCK_N == 64 ? half * (int)gridDim.x : 0);
+      int it = BLOCK_N == 64 ? half : 0;                  // index of `tile` among this CTA's tiles
+      if (use_res && p.res_tma && tile < total_tiles) res_issue(tile, g0);
+      for (; tile < total_tiles; tile += step, it += (BLOCK_N == 64 ? 2 : 1)) {
+        int t = tile;
+        const int nb = t % p.n_blocks; t /= p.n_blocks;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int as = it % acc_n;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
+        uint4 rv[8];
+        if (use_res && !p.res_tma) res_load(tile, g0, rv);
+        mbar_wait(tfull0 + 8 * as, (uint32_t)((it / acc_n) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int g = g0; g < g1; ++g) {
+          if (use_res && p.res_tma) {
+            mbar_wait(rbar, rphase); rphase ^= 1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv[j].x), "=r"(rv[j].y), "=r"(rv[j].z), "=r"(rv[j].w)
+                           : "r"(raddr + (((uint32_t)j ^ rsw) << 4)) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (g + 1 < g1) res_issue(tile, g + 1);
+            else if (tile + step < total_tiles) res_issue(tile + step, g0);
+          } else if (use_res && g > g0) {
+            res_load(tile, g, rv);
+          }
+          epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, tmem_acc, q, lane, g, use_res, rv, nb, tx * BW + (m0 & (BW - 1)),
+                                      ty * BH + ((m0 >> p.lw) & (BH - 1)), t * BNt + (m0 >> (p.lw + p.lh)));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+      }
+    } else {
+    int as = 0; uint32_t aphase = 0;
+    TMR_DECL
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int nb = t % p.n_blocks; t /= p.n_blocks;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int ox = tx * BW + xx, oy = ty * BH + yy, n = t * BNt + nn;
       const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
-      const int as = (int)(it % acc_n);
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
-      const uint32_t tfull_bar = tfull0 + 8 * as, parity = (uint32_t)((it / acc_n) & 1);
+      const uint32_t tfull_bar = tfull0 + 8 * as, parity = aphase;
       if constexpr (MODE == MODE_DBHEAD) {
         mbar_wait(tfull_bar, parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -511,12 +700,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         size_t rpix = 0;
         if (p.res_mode == RES_SAME) rpix = opix;
         else if (p.res_mode == RES_UP2) rpix = ((size_t)n * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
+#ifdef VTD_TIMERS
+        TMR_WAIT(tmr_wait, mbar_wait(tfull_bar, parity))
+#endif
         epilogue_conv<BLOCK_N>(p, tmem_acc, q, half, valid, opix, rpix, nb, tfull_bar, parity);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+      if (++as == acc_n) { as = 0; aphase ^= 1; }
     }
+    }
+    if (p.epi_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    if (warp == 2) { TMR_STORE(2) }
   }
 
   // ---- teardown
@@ -561,6 +757,26 @@ CUresult encode_act4d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int C
   cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bnn};
   cuuint32_t es[4] = {1, 1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// output map of the TMA-store epilogue: box = the 32 consecutive tile rows of one epilogue warp x 128 bytes of channels
+// up = 1: the map covers the half-resolution residual of an upsample-add; the box is the source pixels of the warp's box
+CUresult encode_out(EncodeTiledFn enc, CUtensorMap* m, void* out, int out_f32, int C, int W, int H, int N, int lw, int lh, int up,
+                    int* box_bytes) {
+  const int bw = 1 << lw, bh = 1 << lh;
+  int sw = bw < 32 ? bw : 32;
+  int sh = bh < 32 / sw ? bh : 32 / sw;
+  const int sn = 32 / (sw * sh);
+  if (up) { sw = sw > 1 ? sw / 2 : 1; sh = sh > 1 ? sh / 2 : 1; }
+  if (box_bytes) *box_bytes = sw * sh * sn * 128;
+  const cuuint64_t es = out_f32 ? 4 : 2;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sn};
+  cuuint32_t est[4] = {1, 1, 1, 1};
+  return enc(m, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, est,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
@@ -619,10 +835,14 @@ static void fill_common(TcPlan* pl, int N, int Ho, int Wo, int Cout, int Cin, in
   p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cin = Cin;
   p.KH = p.KW = 1; p.stride = 1; p.pad = 0;
   pick_tile(N, Ho, Wo, &p.lw, &p.lh);
+  if (const char* e = getenv("VTD_TILE")) {               // tuning aid: "lw,lh" for layers at least that large
+    int a = 0, b = 0;
+    if (sscanf(e, "%d,%d", &a, &b) == 2 && a + b <= 7 && (1 << a) <= Wo && (1 << b) <= Ho && (128 >> (a + b)) <= (N > 1 ? N : 1)) { p.lw = a; p.lh = b; }
+  }
   const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
   p.tiles_x = (Wo + bw - 1) / bw; p.tiles_y = (Ho + bh - 1) / bh; p.tiles_n = (N + bnn - 1) / bnn;
   p.n_blocks = Cout / bn;
-  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
   pl->block_n = bn;
 }
 
@@ -651,6 +871,13 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   }
   CUresult r = encode_weights(enc, &pl->maps.b, d.w, (long long)d.KH * d.KW * d.Cin, d.Cout, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
+  r = encode_out(enc, &pl->maps.o, d.out, d.out_f32, d.Cout, d.Wo, d.Ho, d.N, p.lw, p.lh, 0, nullptr);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r)); }
+  if (d.res_mode != RES_NONE && !d.out_f32) {
+    const int up = d.res_mode == RES_UP2 ? 1 : 0;
+    r = encode_out(enc, &pl->maps.r, const_cast<void*>(d.res), 0, d.Cout, d.Wo >> up, d.Ho >> up, d.N, p.lw, p.lh, up, &p.res_bytes);
+    if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(residual) failed: " + std::to_string((int)r)); }
+  }
   plan_finalize(pl);
   return pl;
 }
@@ -684,6 +911,8 @@ TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int s
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(window) failed: " + std::to_string((int)r)); }
   r = encode_weights(enc, &pl->maps.b, w, (long long)nr * 32, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
+  r = encode_out(enc, &pl->maps.o, out, 0, 64, Wo, Ho, N, p.lw, p.lh, 0, nullptr);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r)); }
   plan_finalize(pl);
   return pl;
 }
@@ -729,7 +958,7 @@ TcPlan* tc_plan_create_lstm(const void* h_prev, void* h_next, int Bcap, const vo
   TcParams& p = pl->p;
   p.lw = 7; p.lh = 0;                                   // 128 sequences per tile
   p.tiles_x = (Bcap + 127) / 128; p.tiles_y = 1; p.tiles_n = 1;
-  p.total_tiles = (long long)p.tiles_x * p.n_blocks;
+  p.total_tiles = p.tiles_x * p.n_blocks;
   p.xproj = xproj; p.cbuf = cbuf; p.h_next = reinterpret_cast<bf16*>(h_next); p.seq_out = reinterpret_cast<bf16*>(seq_out);
   p.lstm_T = T; p.lstm_Bcap = Bcap;
   for (int dir = 0; dir < 2; ++dir) {
@@ -746,7 +975,7 @@ TcPlan* tc_plan_create_lstm(const void* h_prev, void* h_next, int Bcap, const vo
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
-constexpr int SMEM_BUDGET = 220 * 1024;     // of the 227 KB a CTA may use
+constexpr int SMEM_TOTAL = 227 * 1024;      // dynamic shared memory a CTA may use
 
 // ring depth / resident weights for a plan (called once per plan, after mode, block_n and p are filled)
 template <int BN, int MODE>
@@ -758,18 +987,53 @@ static void plan_smem(TcPlan* pl) {
   const bool can_res = (MODE == MODE_CONV || MODE == MODE_WIN) && p.n_blocks == 1 && bres_bytes <= 96 * 1024 &&
                        !getenv("VTD_NO_BRES");
   p.bres = can_res ? 1 : 0;
-  if (p.bres) {
-    int st = (SMEM_BUDGET - bres_bytes - 1024 - Cfg::TAIL_BYTES) / Cfg::A_BYTES;
-    p.stages = st > Cfg::MAX_STAGES ? Cfg::MAX_STAGES : st;
-  } else {
-    p.stages = Cfg::STAGES;
+  const int step_bytes = p.bres ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
+  // K steps per ring slot.  A slot handshake costs ~300-500 cycles in the two role warps; the MMAs of one K step take
+  // 4 x max(32, N/2) cycles.  N = 256 hides it with one step per slot; narrower tiles batch up to 3 steps (a divisor of
+  // the step count, at least 3 slots in the ring); the 3-channel stems (2 MMAs per filter row) take the whole filter.
+  int want = MODE == MODE_WIN ? 7 : (BN >= 256 ? 1 : 3);
+  if (MODE == MODE_LSTM || MODE == MODE_DBHEAD) want = 1;
+  if (const char* e = getenv("VTD_KPS")) { int v = atoi(e); if (v >= 1 && BN < 256) want = v; }
+  auto pick = [&](int avail, int* stages_out) {
+    int kps = 1;
+    for (int c = want; c >= 1; --c) {
+      if (MODE == MODE_WIN ? (c != 7 && c != 3 && c != 1) : c > 3) continue;       // instantiated variants
+      if (ksteps % c == 0 && avail / (c * step_bytes) >= (c == 1 ? 2 : 3)) { kps = c; break; }
+    }
+    int st = avail / (kps * step_bytes);
+    if (st > Cfg::MAX_STAGES) st = Cfg::MAX_STAGES;
+    if (!p.bres && kps == 1 && st > Cfg::STAGES) st = Cfg::STAGES;
+    *stages_out = st;
+    return kps;
+  };
+  const int avail = SMEM_TOTAL - (p.bres ? bres_bytes : 0) - 1024 - Cfg::TAIL_BYTES;
+  const int stg_bytes = NUM_EPI_WARPS * 4096;
+  int st_plain = 0, st_tma = 0;
+  const int kps_plain = pick(avail, &st_plain);
+  const int kps_tma = pick(avail - stg_bytes, &st_tma);
+  // the TMA-store epilogue needs 32 KB of staging: take it unless that costs K-step batching or leaves < 3 ring slots
+  // (the resident-weight 64-channel 3x3 layers, where the handshake per K step is the larger cost)
+  bool tma = (MODE == MODE_CONV || MODE == MODE_WIN) && !getenv("VTD_NO_TMA_STORE") && kps_tma == kps_plain &&
+             st_tma >= (st_plain < 3 ? st_plain : 3);
+  if (BN == 256 && tma && st_tma < 4 && st_plain >= 4) tma = false;
+  if (p.out_f32 && p.res_mode != RES_NONE) tma = false;     // (no such layer) residual registers are sized for bf16 groups
+  p.epi_tma = tma ? 1 : 0;
+  p.kps = tma ? kps_tma : kps_plain;
+  p.stages = tma ? st_tma : st_plain;
+  // residual through TMA as well when another 32 KB leave the ring as deep (and the warp's box is at least 2 px wide
+  // for the upsample-add)
+  p.res_tma = 0;
+  if (tma && p.res_mode != RES_NONE && !getenv("VTD_NO_TMA_RES") && (p.res_mode != RES_UP2 || p.lw >= 1)) {
+    int st_r = 0;
+    if (pick(avail - 2 * stg_bytes, &st_r) == p.kps && st_r >= (p.stages < 4 ? p.stages : 4)) { p.res_tma = 1; p.stages = st_r; }
   }
   if (const char* e = getenv("VTD_TC_STAGES")) {          // tuning aid: cap the ring depth
     int cap = atoi(e);
     if (cap >= 2 && cap < p.stages) p.stages = cap;
   }
-  p.ts = (MODE == MODE_CONV && BN <= 128 && getenv("VTD_TS")) ? 1 : 0;
-  pl->smem = Cfg::smem_bytes(p.stages, p.bres ? bres_bytes : 0);
+  p.dbg = getenv("VTD_DBG") ? atoi(getenv("VTD_DBG")) : 0;
+  pl->smem = p.stages * p.kps * step_bytes + (p.bres ? bres_bytes : 0) + (tma ? stg_bytes : 0) + (p.res_tma ? stg_bytes : 0) + 1024 +
+             Cfg::TAIL_BYTES;
 }
 
 static void plan_finalize(TcPlan* pl) {
@@ -784,18 +1048,18 @@ static void plan_finalize(TcPlan* pl) {
   }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int KPS = 1>
 static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, const typename ExtraOf<MODE>::type& ex, cudaStream_t s,
                              bool pdl = false) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   const int sms = sm_count();
-  const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
@@ -806,7 +1070,26 @@ static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, const typename
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE>, pl->maps, p, ex);
+#ifdef VTD_TIMERS
+  if (getenv("VTD_TIMERS")) {
+    static long long* tb = nullptr;
+    if (!tb) cudaMalloc(&tb, 148 * 9 * sizeof(long long));
+    TcParams q = p; q.timers = tb;
+    cudaMemsetAsync(tb, 0, 148 * 9 * sizeof(long long), s);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE, KPS>, pl->maps, q, ex);
+    cudaStreamSynchronize(s);
+    static long long h[148 * 9];
+    cudaMemcpy(h, tb, sizeof(h), cudaMemcpyDeviceToHost);
+    double a[9] = {0};
+    for (int i = 0; i < grid; ++i) for (int j = 0; j < 9; ++j) a[j] += (double)h[i * 9 + j] / grid;
+    const int tiles_cta = (p.total_tiles + grid - 1) / grid;
+    fprintf(stderr, "TMR BN=%d mode=%d kps=%d st=%d %dx%d %d->%d k%d s%d tiles/cta=%d | prod tot %.0f wait_empty %.0f | mma tot %.0f "
+            "wait_full %.0f wait_tempty %.0f | epi tot %.0f wait_tfull %.0f | per tile %.0f\n", BN, MODE, KPS, p.stages, p.Ho, p.Wo,
+            p.Cin, p.Cout, p.KH, p.stride, tiles_cta, a[0], a[1], a[3], a[4], a[5], a[6], a[7], a[3] / tiles_cta);
+    return e;
+  }
+#endif
+  return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MODE, KPS>, pl->maps, p, ex);
 }
 
 // n_actual: images (MODE_LSTM: sequences) actually present in this call (<= what the plan was built for)
@@ -816,14 +1099,22 @@ cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchC
   const int bnn = 128 >> (p.lw + p.lh);
   p.N = n_actual < pl->p.N ? n_actual : pl->p.N;
   p.tiles_n = (p.N + bnn - 1) / bnn;
-  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
   NoExtra none{0};
   cudaError_t e;
-  if (pl->mode == MODE_WIN) e = launch_tc<64, MODE_WIN>(pl, p, none, s);
-  else switch (pl->block_n) {
-    case 256: e = launch_tc<256, MODE_CONV>(pl, p, none, s); break;
-    case 128: e = launch_tc<128, MODE_CONV>(pl, p, none, s); break;
-    default: e = launch_tc<64, MODE_CONV>(pl, p, none, s); break;
+  const int key = pl->mode == MODE_WIN ? 1000 + p.kps : pl->block_n * 10 + p.kps;
+  switch (key) {                                  // the (tile width, K steps per slot) pairs plan_smem() can pick
+    case 1007: e = launch_tc<64, MODE_WIN, 7>(pl, p, none, s); break;
+    case 1003: e = launch_tc<64, MODE_WIN, 3>(pl, p, none, s); break;
+    case 1001: e = launch_tc<64, MODE_WIN, 1>(pl, p, none, s); break;
+    case 2561: e = launch_tc<256, MODE_CONV, 1>(pl, p, none, s); break;
+    case 1281: e = launch_tc<128, MODE_CONV, 1>(pl, p, none, s); break;
+    case 1282: e = launch_tc<128, MODE_CONV, 2>(pl, p, none, s); break;
+    case 1283: e = launch_tc<128, MODE_CONV, 3>(pl, p, none, s); break;
+    case 641: e = launch_tc<64, MODE_CONV, 1>(pl, p, none, s); break;
+    case 642: e = launch_tc<64, MODE_CONV, 2>(pl, p, none, s); break;
+    case 643: e = launch_tc<64, MODE_CONV, 3>(pl, p, none, s); break;
+    default: return cudaErrorInvalidConfiguration;
   }
   if (lc) lc->n++;
   return e;
@@ -835,7 +1126,7 @@ cudaError_t dbhead_tcgen05(TcPlan* pl, int n, float thr, const float* logit_bias
   const int bnn = 128 >> (p.lw + p.lh);
   p.N = n < pl->p.N ? n : pl->p.N;
   p.tiles_n = (p.N + bnn - 1) / bnn;
-  p.total_tiles = (long long)p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
   p.logit_bias = logit_bias;
   pl->hc.thr = thr;
   cudaError_t e = launch_tc<256, MODE_DBHEAD>(pl, p, pl->hc, s);
@@ -849,7 +1140,7 @@ cudaError_t lstm_step_tcgen05(const TcPlan* pl, int B, int step, cudaStream_t s,
   p.lstm_B = B; p.lstm_step = step;
   p.Wo = B;                                              // rows beyond B are masked in the epilogue
   p.tiles_x = (B + 127) / 128;
-  p.total_tiles = (long long)p.tiles_x * p.n_blocks;
+  p.total_tiles = p.tiles_x * p.n_blocks;
   NoExtra none{0};
   cudaError_t e = launch_tc<256, MODE_LSTM>(pl, p, none, s, /*pdl=*/step > 0);
   if (lc) lc->n++;
