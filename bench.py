@@ -313,7 +313,7 @@ def main():
         prof = None
         if profile:
             eng.set_profiling(False)
-            prof = {"detector": eng.op_profile(0), "recogniser": eng.op_profile(1)}
+            prof = {"detector": eng.op_profile(0), "recogniser": eng.op_profile(1), "stages": eng.op_profile(2)}
         if world > 1:
             dist.barrier()
             t = torch.tensor([ms], device=dev, dtype=torch.float64)

@@ -163,7 +163,9 @@ int  vtd_debug_tensor(vtd_ctx* ctx, const char* name, int n, float* host_out, in
 /* ---- measurement: per-launch device times of the conv / pool programs, taken with CUDA events on the
  * launching stream while the normal entry points run (bench.py's roofline figures).  which: 0 detector,
  * 1 recogniser.  info[16] = {kind (0 conv, 1 pool), tensor_core, H, W, Cin, Ho, Wo, Cout, KH, KW, stride,
- * launches timed, 0...}; *ms = summed device time of those launches. */
+ * launches timed, 0...}; *ms = summed device time of those launches.  which = 2: the other stages of the path, one
+ * entry each: info[0] = 2, info[11] = launches timed, info[12] = stage (0 preprocess, 1 DB head tail, 2 box extraction,
+ * 3 crop gather, 4/5 BiLSTM layer 0/1, 6 CTC decode). */
 int  vtd_set_profiling(vtd_ctx* ctx, int on);
 int  vtd_op_count(vtd_ctx* ctx, int which);
 int  vtd_op_info(vtd_ctx* ctx, int which, int idx, int64_t* info, double* ms);

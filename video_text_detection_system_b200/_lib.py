@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libvtd_b200.so")
 
 VTD_FP32, VTD_BF16 = 0, 1
 VTD_PIX_BGR, VTD_PIX_NV12 = 0, 1
+STAGE_NAMES = ("preprocess", "head_tail", "boxes", "crop", "lstm0", "lstm1", "ctc")   # vtd_op_info(which=2)
 VTD_IDS_STRIDE = 64
 
 CHARS = "0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~ "
@@ -386,6 +387,8 @@ class Engine:
             d = {k: int(info[j]) for j, k in enumerate(keys)}
             d["ms"] = float(ms.value)
             d["index"] = i
+            if which == 2:
+                d["name"] = STAGE_NAMES[int(info[12])]
             out.append(d)
         return out
 

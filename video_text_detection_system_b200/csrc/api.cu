@@ -38,6 +38,13 @@ struct Op {
 
 struct Act { void* p = nullptr; int H = 0, W = 0, C = 0; };
 
+// stage-level device timers (vtd_set_profiling): the launches of the path that are not conv/pool ops
+enum { ST_PREPROCESS = 0, ST_HEAD_TAIL, ST_BOXES, ST_CROP, ST_LSTM0, ST_LSTM1, ST_CTC, ST_COUNT };
+struct StageProf {
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double ms = 0.0; long long n = 0; bool pending = false;
+};
+
 struct HostConv {              // folded, repacked host weights [Cout][KH][KW][Cin_pad]
   std::vector<float> w, b;
   int Cout = 0, Cin = 0, Cin_pad = 0, KH = 0, KW = 0;
@@ -52,6 +59,7 @@ struct vtd_ctx {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   LaunchCounter lc;
   bool profiling = false;
+  StageProf stage_prof[ST_COUNT];
   std::vector<void*> allocs;
   size_t esz = 4;                       // activation element size
   bool bf16_mode = false;
@@ -273,6 +281,22 @@ void prof_harvest(Op& op) {
   if (cudaEventElapsedTime(&ms, op.ev0, op.ev1) == cudaSuccess) { op.prof_ms += ms; op.prof_n++; op.prof_pending = false; }
   else cudaGetLastError();   // not ready yet: keep pending, clear the sticky-free error
 }
+
+void stage_harvest(StageProf& sp) {
+  float ms = 0.f;
+  if (sp.pending && cudaEventElapsedTime(&ms, sp.ev0, sp.ev1) == cudaSuccess) { sp.ms += ms; sp.n++; }
+  sp.pending = false;
+}
+struct StageTimer {                      // brackets a stage with CUDA events on the launching stream when profiling is on
+  vtd_ctx* c; StageProf* sp;
+  StageTimer(vtd_ctx* ctx, int id) : c(ctx), sp(ctx->profiling ? &ctx->stage_prof[id] : nullptr) {
+    if (!sp) return;
+    if (!sp->ev0) { cudaEventCreate(&sp->ev0); cudaEventCreate(&sp->ev1); }
+    if (sp->pending) { cudaEventSynchronize(sp->ev1); stage_harvest(*sp); }
+    cudaEventRecord(sp->ev0, c->stream);
+  }
+  ~StageTimer() { if (sp) { cudaEventRecord(sp->ev1, c->stream); sp->pending = true; } }
+};
 
 int run_op_prof(vtd_ctx* c, Op& op, int n) {
   if (!c->profiling) { CK(run_op(c, op, n)); return VTD_OK; }
@@ -598,6 +622,7 @@ int run_crnn(vtd_ctx* c, int nc) {
     // the second layer's xproj reuses its own buffer (allocated by add_conv)
     { int r2 = run_op_prof(c, c->xproj_op[l], nc); if (r2) return r2; }
     const float* xp = (const float*)c->xproj_op[l].d.out;
+    StageTimer st(c, l == 0 ? ST_LSTM0 : ST_LSTM1);
     if (c->use_tclstm && c->use_plstm) {
       CK(bilstm_layer_tcgen05(c->plstm[l], c->xproj_op[l].d.out, c->rnn_out[l], nc, c->T, c->stream, &c->lc));
     } else if (c->use_tclstm) {
@@ -618,6 +643,7 @@ int run_crnn(vtd_ctx* c, int nc) {
 int detect_maps_locked(vtd_ctx* c, int n, float thr, const float* logit_bias) {
   int r = run_prog(c, c->det_prog, n); if (r) return r;
   const int dh = c->cfg.det_h, dw = c->cfg.det_w;
+  StageTimer st(c, ST_HEAD_TAIL);
   if (c->head_plan)
     CK(dbhead_tcgen05(c->head_plan, n, thr, logit_bias, c->stream, &c->lc));
   else if (c->bf16_mode)
@@ -663,6 +689,7 @@ int preprocess_locked(vtd_ctx* c, const uint8_t* const* frames, int n, int h, in
     r = build_tab(c, h, c->cfg.det_h, &c->ty); if (r) return r;
     c->tab_h = h; c->tab_w = w;
   }
+  StageTimer st(c, ST_PREPROCESS);
   if (c->bf16_mode)
     CK(preprocess_frames<bf16>(c->frame_ptrs_dev, n, h, w, dev_pitch, pixfmt, c->tx, c->ty, c->norm_lut, (bf16*)c->pre,
                                c->pre_lay, c->stream, &c->lc));
@@ -678,6 +705,7 @@ int extract_locked(vtd_ctx* c, int n, int orig_h, int orig_w) {
   bp.n = n; bp.n_alloc = c->cfg.max_batch; bp.mh = c->cfg.det_h; bp.mw = c->cfg.det_w;
   bp.clip_h = c->cfg.det_h; bp.clip_w = c->cfg.det_w; bp.orig_h = orig_h; bp.orig_w = orig_w;
   bp.kmax = c->cfg.max_boxes; bp.unclip = c->cfg.unclip_ratio;
+  StageTimer st(c, ST_BOXES);
   CK(extract_boxes(c->prob, c->mask, bp, c->box_work, c->box_lay, c->records, c->counts, c->stream, &c->lc));
   return VTD_OK;
 }
@@ -689,6 +717,8 @@ int recognize_locked(vtd_ctx* c, int n) {
   const int total = c->pinned_int[0];
   for (int first = 0; first < total; first += c->rc) {
     const int nc = total - first < c->rc ? total - first : c->rc;
+    {
+    StageTimer st(c, ST_CROP);
     if (c->bf16_mode)
       CK(crop_resize_records<bf16>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
                                    c->cfg.max_boxes, first, nc, c->cfg.crop_w, c->cur_pix == VTD_PIX_NV12, (bf16*)c->crops, c->crops_lay,
@@ -697,7 +727,9 @@ int recognize_locked(vtd_ctx* c, int n) {
       CK(crop_resize_records<float>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
                                     c->cfg.max_boxes, first, nc, c->cfg.crop_w, c->cur_pix == VTD_PIX_NV12, (float*)c->crops, c->crops_lay,
                                     c->stream, &c->lc));
+    }
     int r = run_crnn(c, nc); if (r) return r;
+    StageTimer st(c, ST_CTC);
     CK(ctc_into_records(c->logits, nc, first, c->T, 97, c->logits_ld, c->cfg.canonical_ctc, c->offsets, n, c->cfg.max_boxes,
                         c->records, c->stream, &c->lc));
   }
@@ -1149,17 +1181,31 @@ int vtd_set_profiling(vtd_ctx* c, int on) {
   CK(cudaStreamSynchronize(c->stream));
   for (int w = 0; w < 2; ++w)
     for (Op* o : prof_ops(c, w)) { prof_harvest(*o); if (on) { o->prof_ms = 0.0; o->prof_n = 0; o->prof_pending = false; } }
+  for (StageProf& sp : c->stage_prof) { stage_harvest(sp); if (on) { sp.ms = 0.0; sp.n = 0; } }
   c->profiling = on != 0;
   return VTD_OK;
 }
 
-int vtd_op_count(vtd_ctx* c, int which) { if (!c) return 0; Guard g(c); return (int)prof_ops(c, which).size(); }
+int vtd_op_count(vtd_ctx* c, int which) {
+  if (!c) return 0;
+  Guard g(c);
+  return which == 2 ? (int)ST_COUNT : (int)prof_ops(c, which).size();
+}
 
 /* info[16]: kind(0 conv,1 pool), tensor_core(0/1), H, W, Cin, Ho, Wo, Cout, KH, KW, stride, launches, 0... ; ms = summed
  * device time of those launches */
 int vtd_op_info(vtd_ctx* c, int which, int idx, int64_t* info, double* ms) {
   if (!c || !info) return VTD_ERR_ARG;
   Guard g(c);
+  if (which == 2) {                       // stages: info[0] = 2, info[12] = stage id (see vtd.h), info[11] = launches
+    if (idx < 0 || idx >= ST_COUNT) FAIL(VTD_ERR_ARG, "stage index out of range");
+    StageProf& sp = c->stage_prof[idx];
+    if (sp.pending) { cudaEventSynchronize(sp.ev1); stage_harvest(sp); }
+    for (int i = 0; i < 16; ++i) info[i] = 0;
+    info[0] = 2; info[11] = sp.n; info[12] = idx;
+    if (ms) *ms = sp.ms;
+    return VTD_OK;
+  }
   std::vector<Op*> v = prof_ops(c, which);
   if (idx < 0 || idx >= (int)v.size()) FAIL(VTD_ERR_ARG, "op index out of range");
   Op& o = *v[idx];

@@ -586,6 +586,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
     const int half = (warp - 2) >> 2;                   // which half of the tile's columns / units / rows
     const int m = q * 32 + lane;                        // row of the tile = pixel
     const int xx = m & (BW - 1), yy = (m >> p.lw) & (BH - 1), nn = m >> (p.lw + p.lh);
+    TMR_DECL
     if ((MODE == MODE_CONV || MODE == MODE_WIN) && p.epi_tma) {
       // ---- TMA-store epilogue.  Work items = (tile, 128-byte channel group); N = 64 tiles have one group, so the two
       // halves take alternate tiles; wider tiles split their groups between the halves.  The residual of the NEXT work
@@ -651,7 +652,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
         uint4 rv[8];
         if (use_res && !p.res_tma) res_load(tile, g0, rv);
-        mbar_wait(tfull0 + 8 * as, (uint32_t)((it / acc_n) & 1));
+        TMR_WAIT(tmr_wait, mbar_wait(tfull0 + 8 * as, (uint32_t)((it / acc_n) & 1)))
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int g = g0; g < g1; ++g) {
           if (use_res && p.res_tma) {
@@ -676,7 +677,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       }
     } else {
     int as = 0; uint32_t aphase = 0;
-    TMR_DECL
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int t = tile;
       const int nb = t % p.n_blocks; t /= p.n_blocks;

@@ -23,21 +23,39 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <string>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace vtd {
 namespace {
 
 using namespace tc;
 
-constexpr int L_THREADS = 320;                 // warp 0: weight loader, warp 1: MMA issuer, warps 2..9: epilogue
+#ifndef VTD_LSTM_PARTS
+#define VTD_LSTM_PARTS 4
+#endif
+constexpr int L_PARTS = VTD_LSTM_PARTS;        // epilogue warps per TMEM lane quarter: each owns 64 / L_PARTS hidden units of a row
+constexpr int L_UPT = 64 / L_PARTS;            // hidden units per epilogue thread
+constexpr int L_CH = L_UPT / 8;                // 16-byte chunks (8 bf16) per thread and gate
+constexpr int L_EPI_THREADS = 128 * L_PARTS;
+constexpr int L_THREADS = 64 + L_EPI_THREADS;  // warp 0: weight loader, warp 1: MMA issuer, then the epilogue warps
 constexpr int L_W_BYTES = 4 * 256 * 128;       // 4 K-chunks x 256 rows x 128 B
 constexpr int L_A_BYTES = 4 * 128 * 128;       // 4 K-chunks x 128 rows x 128 B
 constexpr int L_SMEM = L_W_BYTES + L_A_BYTES + 1024 + 64;
 
+#ifdef VTD_TIMERS
+#define LT_DECL long long lt_a = 0, lt_b = 0, lt_c = 0, lt_d = 0, lt_e = 0, lt_f = 0; const long long lt_t0 = clock64();
+#define LT(acc, stmt) { const long long _a = clock64(); stmt; acc += clock64() - _a; }
+#else
+#define LT_DECL
+#define LT(acc, stmt) { stmt; }
+#endif
 struct LstmParams {
+  long long* timers;
   const bf16* xproj;      // [B][T][2][1024] bf16
   bf16* seq_out;          // [B][T][512]
   int B, T;
+  int rows;               // sequences per cluster: 128, or 64 when that still fits one wave (halves the h exchange per step)
 };
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -98,13 +116,13 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x;                            // == rank in cluster: hidden units 64*jt ..
   const int dir = blockIdx.y;
-  const int b0 = blockIdx.z * 128;
+  const int b0 = blockIdx.z * p.rows;
 
   if (warp == 0 && lane == 0) {
     mbar_init(wfull, 1);
     mbar_init(tfull, 1);
     mbar_init(afree, 4);
-    mbar_init(hready, 1);
+    mbar_init(hready, 2);                               // MMA thread (expect_tx of the 3 remote slices) + own epilogue (local slice)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whh) : "memory");
   }
@@ -136,11 +154,12 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
     // ---- MMA issuer
     const uint32_t idesc = umma_idesc(256);
     mbar_wait(wfull, 0);
+    LT_DECL
     for (int s = 0; s < p.T; ++s) {
       if (s > 0) {                                      // h_{s-1} of all 256 units (64 KB, written by st.async) has landed here
-        if (elect_one()) mbar_expect_tx(hready, L_A_BYTES);
+        if (elect_one()) mbar_expect_tx(hready, 3u * (uint32_t)p.rows * 128u);
         __syncwarp();
-        mbar_wait(hready, (uint32_t)((s - 1) & 1));
+        LT(lt_a, mbar_wait(hready, (uint32_t)((s - 1) & 1)))
       }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
@@ -155,46 +174,69 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
       }
       __syncwarp();
     }
+#ifdef VTD_TIMERS
+    if (lane == 0 && p.timers && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { p.timers[0] = clock64() - lt_t0; p.timers[1] = lt_a; }
+#endif
   } else {
     // ---- epilogue: gates, cell update, h exchange
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, half = (warp - 2) >> 2;   // half = which L_UPT-unit part of the 64 units
     const int m = q * 32 + lane;                        // sequence row inside the tile
     const int b = b0 + m;
     const bool valid = b < p.B;
+    const bool active = q * 32 < p.rows;                // with 64 rows per cluster the upper two lane quarters carry no sequence
+    const uint32_t epi_threads = (uint32_t)(p.rows * L_PARTS);
+    const bool issuer = q == 0 && half == 0 && lane == 0;   // one thread of an always-active warp pushes the slice to the peers
     const int bb = valid ? b : 0;
-    float c[32];
+    float c[L_UPT];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) c[i] = 0.f;
+    for (int i = 0; i < L_UPT; ++i) c[i] = 0.f;
     // remote addresses of this thread's 4 x 16-byte h chunks in every CTA of the cluster
-    uint32_t dst[4];
-    {
-      const uint32_t row = abuf + jt * (128 * 128) + m * 128;      // K-chunk jt, row m (local address)
+    const uint32_t own_chunk = abuf + jt * (128 * 128);             // K-chunk jt of the A operand (local address)
+    const uint32_t own_row = own_chunk + m * 128;
+    uint32_t dst_chunk[4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) dst[r] = map_to_cta(row, (uint32_t)r);
-    }
+    for (int r = 0; r < 4; ++r) dst_chunk[r] = map_to_cta(own_chunk, (uint32_t)r);
     uint32_t hrdy[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) hrdy[r] = map_to_cta(hready, (uint32_t)r);
-    for (int s = 0; s < p.T; ++s) {
+    LT_DECL
+    for (int s = 0; active && s < p.T; ++s) {
       const int t = dir == 0 ? s : p.T - 1 - s;
-      const bf16* __restrict__ xp = p.xproj + (((size_t)bb * p.T + t) * 2 + dir) * 1024 + jt * 256 + half * 32;
-      bf16* __restrict__ so = p.seq_out + ((size_t)bb * p.T + t) * 512 + dir * 256 + jt * 64 + half * 32;
+      const bf16* __restrict__ xp = p.xproj + (((size_t)bb * p.T + t) * 2 + dir) * 1024 + jt * 256 + half * L_UPT;
+      bf16* __restrict__ so = p.seq_out + ((size_t)bb * p.T + t) * 512 + dir * 256 + jt * 64 + half * L_UPT;
       // input projection of this step: 4 gates x 32 units bf16 = 16 x 16 bytes, requested BEFORE the accumulator wait so
       // the L2/DRAM latency overlaps the MMAs (loading them chunk by chunk inside the gate loop cost 8 exposed round
       // trips per step: long_scoreboard was 49 % of the stalls)
-      uint4 xr[4][4];
+#ifdef VTD_TIMERS
+      const long long lt_x0 = clock64();
+#endif
+      uint4 xr[4][L_CH];
 #pragma unroll
       for (int g = 0; g < 4; ++g)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < L_CH; ++j)
           xr[g][j] = valid ? __ldg(reinterpret_cast<const uint4*>(xp + g * 64) + j) : make_uint4(0u, 0u, 0u, 0u);
-      mbar_wait(tfull, (uint32_t)(s & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint4 hw[4];
+      // xproj of one layer is ~100 MB: the rows of the steps after this one are pulled into L2 now, so that the loads
+      // above find them there (DRAM latency is longer than the MMAs of a step; long_scoreboard was the top stall)
+      if (valid && s + 2 < p.T) {
+        const int t2 = dir == 0 ? s + 2 : p.T - 3 - s;
+        const bf16* xn = p.xproj + (((size_t)bb * p.T + t2) * 2 + dir) * 1024 + jt * 256 + half * L_UPT;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {                     // 8 hidden units at a time
+        for (int g = 0; g < 4; ++g) asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + g * 64));
+      }
+#ifdef VTD_TIMERS
+      lt_d += clock64() - lt_x0;
+#endif
+      LT(lt_a, mbar_wait(tfull, (uint32_t)(s & 1)))
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef VTD_TIMERS
+      const long long lt_m0 = clock64();
+#endif
+      uint4 hw[L_CH];
+#pragma unroll
+      for (int j = 0; j < L_CH; ++j) {                  // 8 hidden units at a time
         uint32_t vi[8], vf[8], vg[8], vo[8];
-        const uint32_t tb = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32 + j * 8);
+        const uint32_t tb = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * L_UPT + j * 8);
         tmem_ld8(tb, vi); tmem_ld8(tb + 64, vf); tmem_ld8(tb + 128, vg); tmem_ld8(tb + 192, vo);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const __nv_bfloat162* xi2 = reinterpret_cast<const __nv_bfloat162*>(&xr[0][j]);
@@ -225,20 +267,53 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
         hw[j] = u4;
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#ifdef VTD_TIMERS
+      lt_c += clock64() - lt_m0;
+#endif
       if (s + 1 < p.T) {
-        mbar_wait(afree, (uint32_t)(s & 1));            // nobody's MMAs still read h_{s-1}
+        LT(lt_b, mbar_wait(afree, (uint32_t)(s & 1)))            // nobody's MMAs still read h_{s-1}
         // h_s slice -> A operand of all 4 CTAs: 16-byte chunk j of the row goes to physical chunk j ^ (row & 7)
+#ifdef VTD_TIMERS
+        const long long lt_s0 = clock64();
+#endif
+        // h_s slice: 16-byte chunk c of row m goes to physical chunk c ^ (m & 7) of K-chunk jt of the OWN A buffer; that
+        // K-chunk (128 rows x 128 B = 16 KB, contiguous) is then pushed to the three peers with one bulk DSMEM copy each,
+        // whose bytes complete the peers' hready barriers (16-byte st.async packets moved the same bytes ~3x slower)
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int j = 0; j < L_CH; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(own_row + ((uint32_t)((half * L_CH + j) ^ (m & 7)) << 4)),
+                       "r"(hw[j].x), "r"(hw[j].y), "r"(hw[j].z), "r"(hw[j].w) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");      // all active epilogue warps have written their part
+        if (issuer) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) st_async_v4(dst[r] + ((uint32_t)((half * 4 + j) ^ (m & 7)) << 4), hw[j], hrdy[r]);
+          for (int r = 0; r < 4; ++r)
+            if (r != jt)
+              asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(dst_chunk[r]), "r"(own_chunk), "r"((uint32_t)p.rows * 128u), "r"(hrdy[r]) : "memory");
+          mbar_arrive(hready);                              // own slice is in place (release; the MMA thread's wait acquires)
+        }
+#ifdef VTD_TIMERS
+        lt_e += clock64() - lt_s0;
+#endif
       }
+#ifdef VTD_TIMERS
+      const long long lt_g0 = clock64();
+#endif
       if (valid) {                                      // layer output (global) after the exchange: off the critical path
         uint4* sp = reinterpret_cast<uint4*>(so);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sp[j] = hw[j];
+        for (int j = 0; j < L_CH; ++j) sp[j] = hw[j];
       }
+#ifdef VTD_TIMERS
+      lt_f += clock64() - lt_g0;
+#endif
     }
+#ifdef VTD_TIMERS
+    if (issuer && p.timers && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      p.timers[2] = clock64() - lt_t0; p.timers[3] = lt_a; p.timers[4] = lt_b; p.timers[5] = lt_c; p.timers[6] = lt_d; p.timers[7] = lt_e; p.timers[8] = lt_f;
+    }
+#endif
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -289,7 +364,25 @@ cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*bf16*/,
   }
   LstmParams p;
   p.xproj = reinterpret_cast<const bf16*>(xproj); p.seq_out = reinterpret_cast<bf16*>(seq_out); p.B = B; p.T = T;
-  dim3 grid(4, 2, (B + 127) / 128);
+  p.timers = nullptr;
+  // 64 sequences per cluster when all clusters are still resident at once: the MMA costs the same (M = 128 either way),
+  // the per-step h exchange (DSMEM, ~9 B/cycle/SM measured) and the gate math per CTA halve
+  p.rows = (((B + 63) / 64) * 8 <= tc::sm_count() && !getenv("VTD_LSTM_ROWS128")) ? 64 : 128;
+  dim3 grid(4, 2, (B + p.rows - 1) / p.rows);
+#ifdef VTD_TIMERS
+  if (getenv("VTD_TIMERS")) {
+    static long long* tb = nullptr;
+    if (!tb) cudaMalloc(&tb, 16 * sizeof(long long));
+    p.timers = tb;
+    bilstm_persistent_kernel<<<grid, L_THREADS, L_SMEM, s>>>(pl->map_whh, p);
+    cudaStreamSynchronize(s);
+    long long h[9]; cudaMemcpy(h, tb, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "LSTM B=%d T=%d | mma tot %lld wait_hready %lld | epi tot %lld wait_tfull %lld wait_afree %lld math %lld xload %lld stasync %lld gstore %lld | per step %lld\n",
+            B, T, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[2] / T);
+    if (lc) lc->n++;
+    return cudaGetLastError();
+  }
+#endif
   bilstm_persistent_kernel<<<grid, L_THREADS, L_SMEM, s>>>(pl->map_whh, p);
   if (lc) lc->n++;
   return cudaGetLastError();
