@@ -330,6 +330,7 @@ int build_tab(vtd_ctx* c, int in_size, int out_size, ResizeTab* t) {
   std::vector<int> lo(out_size), cnt(out_size), kk((size_t)out_size * ksize, 0);
   std::vector<double> w(ksize);
   const double ss = 1.0 / fs;
+  int maxcnt = 0;
   for (int xx = 0; xx < out_size; ++xx) {
     double center = (xx + 0.5) * scale;
     int xmin = (int)(center - support + 0.5); if (xmin < 0) xmin = 0;
@@ -348,6 +349,7 @@ int build_tab(vtd_ctx* c, int in_size, int out_size, ResizeTab* t) {
       kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (double)(1 << 22)) : (int)(0.5 + v * (double)(1 << 22));
     }
     lo[xx] = xmin; cnt[xx] = n;
+    if (n > maxcnt) maxcnt = n;
   }
   if (t->lo) { cudaFree(t->lo); cudaFree(t->cnt); cudaFree(t->kk); t->lo = t->cnt = t->kk = nullptr; }
   CK(cudaMalloc(&t->lo, out_size * 4)); CK(cudaMalloc(&t->cnt, out_size * 4)); CK(cudaMalloc(&t->kk, kk.size() * 4));
@@ -355,7 +357,7 @@ int build_tab(vtd_ctx* c, int in_size, int out_size, ResizeTab* t) {
   CK(cudaMemcpyAsync(t->cnt, cnt.data(), out_size * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(t->kk, kk.data(), kk.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));   // the host vectors die here
-  t->in_size = in_size; t->out_size = out_size; t->ksize = ksize;
+  t->in_size = in_size; t->out_size = out_size; t->ksize = ksize; t->maxcnt = maxcnt;
   return VTD_OK;
 }
 

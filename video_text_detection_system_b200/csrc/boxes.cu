@@ -115,10 +115,24 @@ __global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restri
 // sees NE as its N with a background NW and performs the union itself; only when E is background does
 // this pixel have to do it.
 
+// Four pixels per thread (16-byte load/store); pixels of one run carry the same label after ccl_rows/ccl_merge, so a
+// run costs one root chase per 4 pixels instead of four.
 __global__ void ccl_flatten_plane_kernel(int* __restrict__ labels, int plane_px) {
   int* L = labels + (size_t)blockIdx.y * plane_px;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane_px; i += gridDim.x * blockDim.x)
-    L[i] = uf_find(L, i);
+  if (plane_px & 3) {                                   // planes not 16-byte aligned: scalar
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane_px; i += gridDim.x * blockDim.x) L[i] = uf_find(L, i);
+    return;
+  }
+  const int quads = plane_px >> 2;
+  for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += gridDim.x * blockDim.x) {
+    int4 l = reinterpret_cast<const int4*>(L)[qd];
+    int4 r;
+    r.x = uf_find(L, l.x);
+    r.y = l.y == l.x ? r.x : uf_find(L, l.y);
+    r.z = l.z == l.y ? r.y : uf_find(L, l.z);
+    r.w = l.w == l.z ? r.z : uf_find(L, l.w);
+    reinterpret_cast<int4*>(L)[qd] = r;
+  }
 }
 
 // ---- 4. background roots connected to the frame
@@ -283,12 +297,36 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   const int* L = labels + (size_t)f * mh * mw;
 
   if (use_smem) {
-    for (int i = lane; i < rw * rh; i += 32) {
-      const int yy = i / rw, xx = i - yy * rw;
-      const int gx = bx0 + xx, gy = by0 + yy;
-      sm_mask[i] = ((unsigned)gx < (unsigned)mw && (unsigned)gy < (unsigned)mh) ? m[gy * mw + gx] : (uint8_t)0;
+    // membership of THIS component (label == raster index of its first pixel), bbox + 1 px border.  Foreground pixels
+    // 8-adjacent to a pixel of the component belong to the component, so the outer-border trace sees the same
+    // neighbourhood in this plane as in the mask.  Rows are fetched 4 at a time: 4 x ceil(rw/32) independent loads in
+    // flight per lane instead of one dependent L2 round trip per element.
+    for (int yy = 0; yy < rh; yy += 4) {
+      for (int xx = lane; xx < rw; xx += 32) {
+        const int gx = bx0 + xx;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int gy = by0 + yy + k;
+          v[k] = (yy + k < rh && (unsigned)gx < (unsigned)mw && (unsigned)gy < (unsigned)mh) ? L[(size_t)gy * mw + gx] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (yy + k < rh) sm_mask[(yy + k) * rw + xx] = v[k] == start ? (uint8_t)1 : (uint8_t)0;
+      }
     }
-  }
+    __syncwarp();
+    // per-row extremes: one lane per row, scanning shared memory
+    for (int r = lane; r < nrows; r += 32) {
+      const uint8_t* row = sm_mask + (r + 1) * rw + 1;        // x = xmin at offset 0
+      const int wd = xmax - xmin + 1;
+      int lo = 0, hi = wd - 1;
+      while (lo < wd && !row[lo]) ++lo;
+      while (hi >= 0 && !row[hi]) --hi;
+      rowmin[r] = lo < wd ? xmin + lo : (1 << 30);
+      rowmax[r] = hi >= 0 ? xmin + hi : -1;
+    }
+  } else {
   // per-row extremes of THIS component (label == raster index of its first pixel)
   for (int r = 0; r < nrows; ++r) {
     int lo = 1 << 30, hi = -1;
@@ -301,6 +339,7 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
       hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
     }
     if (lane == 0) { rowmin[r] = lo; rowmax[r] = hi; }
+  }
   }
   __syncwarp();
 
@@ -359,10 +398,17 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   } else {
     const float* p = prob + (size_t)f * mh * mw;
     double acc = 0.0;
-    for (int y = cy0; y < cy1; ++y) {
-      float rs = 0.f;
-      for (int x = cx0 + lane; x < cx1; x += 32) rs += p[(size_t)y * mw + x];
-      acc += (double)rs;
+    for (int y = cy0; y < cy1; y += 4) {                  // 4 rows of loads in flight; same summation order per row
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int x = cx0 + lane; x < cx1; x += 32) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = y + k < cy1 ? p[(size_t)(y + k) * mw + x] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rs[k] += v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (y + k < cy1) acc += (double)rs[k];
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
@@ -468,7 +514,7 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
   ccl_rows_kernel<<<dim3(mh, n), RT, 0, s>>>(mask, labels, mh, mw);
   if (mh > 1) ccl_merge_kernel<<<dim3(cdiv(mw, 128), mh - 1, n), 128, 0, s>>>(mask, labels, mh, mw);
   const int gx = min(cdiv((long long)px, 256), 148 * 8);
-  ccl_flatten_plane_kernel<<<dim3(gx, n), 256, 0, s>>>(labels, (int)px);
+  ccl_flatten_plane_kernel<<<dim3(min(cdiv((long long)px / 4 + 1, 256), 148 * 8), n), 256, 0, s>>>(labels, (int)px);
   mark_outside_kernel<<<dim3(cdiv(2 * (mh + mw), 256), n), 256, 0, s>>>(mask, labels, outside, mh, mw);
   collect_roots_kernel<<<dim3(gx, n), 256, 0, s>>>(mask, labels, outside, slot_plane, ca, mh, mw);
   run_extents_kernel<<<dim3(gx, n), 256, 0, s>>>(mask, labels, slot_plane, ca, mh, mw);

@@ -68,6 +68,7 @@ cudaError_t maxpool_nhwc(const T* in, T* out, int N, int H, int W, int C, int kh
 // ---- preprocess ----------------------------------------------------------------------------------
 struct ResizeTab {           // Pillow coefficient tables for one axis, device memory
   int in_size = 0, out_size = 0, ksize = 0;
+  int maxcnt = 0;            // largest cnt[]: <= 4 selects the word-wise fast path of the preprocess kernel
   int* lo = nullptr;         // [out]
   int* cnt = nullptr;        // [out]
   int* kk = nullptr;         // [out][ksize]

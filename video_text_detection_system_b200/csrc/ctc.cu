@@ -9,8 +9,10 @@
 //     number of characters emitted so far, not by the timestep; the result is their mean (0.0 if none).
 // `canonical != 0` switches to textbook CTC collapse (blank resets prev), for users who want it.
 //
-// One warp per sequence: the 32 lanes stride over the V classes of a timestep, online max / sum-of-exp,
-// shuffle argmax with lowest-index tie-break (torch.argmax), then lane 0 runs the <=64-step collapse.
+// One CTA per sequence, one WARP per timestep (the rows of a sequence are independent until the collapse): the 32
+// lanes stride over the V classes, max / sum-of-exp, shuffle argmax with lowest-index tie-break (torch.argmax); after
+// a CTA barrier thread 0 runs the <=64-step collapse.  (One warp walking the T rows of a sequence one after the other
+// was a chain of ~T x 3 dependent L2 round trips: 73 us for 800 x 31 rows; the bytes are 12 MB.)
 // HBM-bound: reads B*T*V*4 bytes once, writes ~T bytes.
 #include "common.cuh"
 #include "../../include/vtd.h"
@@ -75,47 +77,44 @@ __device__ __forceinline__ void collapse(const int* ids_t, const float* pm_t, in
   *conf_out = len > 0 ? (float)(csum / (double)len) : 0.f;
 }
 
-__global__ void __launch_bounds__(128) ctc_kernel(const float* __restrict__ x, int B, int T, int V, int ld, int is_prob,
-                                                  int canonical, uint8_t* __restrict__ ids, int ids_stride,
-                                                  int* __restrict__ lens, float* __restrict__ conf) {
-  __shared__ int s_idx[4][MAXT];
-  __shared__ float s_pm[4][MAXT];
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + wid;
-  if (b >= B) return;
-  for (int t = 0; t < T; ++t) {
+__global__ void __launch_bounds__(1024) ctc_kernel(const float* __restrict__ x, int B, int T, int V, int ld, int is_prob,
+                                                   int canonical, uint8_t* __restrict__ ids, int ids_stride,
+                                                   int* __restrict__ lens, float* __restrict__ conf) {
+  __shared__ int s_idx[MAXT];
+  __shared__ float s_pm[MAXT];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int b = blockIdx.x;
+  for (int t = wid; t < T; t += nw) {
     int bi; float pm;
     row_argmax(x + ((size_t)b * T + t) * ld, V, is_prob, lane, &bi, &pm);
-    if (lane == 0) { s_idx[wid][t] = bi; s_pm[wid][t] = pm; }
+    if (lane == 0) { s_idx[t] = bi; s_pm[t] = pm; }
   }
-  __syncwarp();
-  if (lane == 0) collapse(s_idx[wid], s_pm[wid], T, V, canonical, ids + (size_t)b * ids_stride, ids_stride, lens + b,
-                          conf + b);
+  __syncthreads();
+  if (threadIdx.x == 0) collapse(s_idx, s_pm, T, V, canonical, ids + (size_t)b * ids_stride, ids_stride, lens + b, conf + b);
 }
 
 // same, but the result lands in the vtd_record of the crop (crop ci of the chunk <-> record via offsets)
-__global__ void __launch_bounds__(128) ctc_records_kernel(const float* __restrict__ x, int n_crops, int first_crop,
-                                                          int T, int V, int ld, int canonical,
-                                                          const int* __restrict__ offsets, int n, int kmax,
-                                                          vtd_record* __restrict__ records) {
-  __shared__ int s_idx[4][MAXT];
-  __shared__ float s_pm[4][MAXT];
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 4 + wid;
-  if (b >= n_crops) return;
-  for (int t = 0; t < T; ++t) {
+__global__ void __launch_bounds__(1024) ctc_records_kernel(const float* __restrict__ x, int n_crops, int first_crop,
+                                                           int T, int V, int ld, int canonical,
+                                                           const int* __restrict__ offsets, int n, int kmax,
+                                                           vtd_record* __restrict__ records) {
+  __shared__ int s_idx[MAXT];
+  __shared__ float s_pm[MAXT];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int b = blockIdx.x;
+  for (int t = wid; t < T; t += nw) {
     int bi; float pm;
     row_argmax(x + ((size_t)b * T + t) * ld, V, 0, lane, &bi, &pm);
-    if (lane == 0) { s_idx[wid][t] = bi; s_pm[wid][t] = pm; }
+    if (lane == 0) { s_idx[t] = bi; s_pm[t] = pm; }
   }
-  __syncwarp();
-  if (lane == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
     const int ci = first_crop + b;
     int f = 0;
     while (f + 1 < n && offsets[f + 1] <= ci) ++f;
     vtd_record* r = records + (size_t)f * kmax + (ci - offsets[f]);
     int len; float cf;
-    collapse(s_idx[wid], s_pm[wid], T, V, canonical, r->ids, 36, &len, &cf);
+    collapse(s_idx, s_pm, T, V, canonical, r->ids, 36, &len, &cf);
     r->len = len; r->rec_conf = cf;
   }
 }
@@ -126,7 +125,7 @@ cudaError_t ctc_greedy(const float* x, int B, int T, int V, int ld, int is_prob,
                        int ids_stride, int* lens, float* conf, cudaStream_t s, LaunchCounter* lc) {
   if (B <= 0) return cudaSuccess;
   if (T > MAXT || T <= 0 || V <= 1) return cudaErrorInvalidValue;
-  ctc_kernel<<<(B + 3) / 4, 128, 0, s>>>(x, B, T, V, ld, is_prob, canonical, ids, ids_stride, lens, conf);
+  ctc_kernel<<<B, 32 * (T < 32 ? T : 32), 0, s>>>(x, B, T, V, ld, is_prob, canonical, ids, ids_stride, lens, conf);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
@@ -135,7 +134,7 @@ cudaError_t ctc_into_records(const float* logits, int n_crops, int first_crop, i
                              const int* offsets, int n, int kmax, void* records, cudaStream_t s, LaunchCounter* lc) {
   if (n_crops <= 0) return cudaSuccess;
   if (T > MAXT || T <= 0) return cudaErrorInvalidValue;
-  ctc_records_kernel<<<(n_crops + 3) / 4, 128, 0, s>>>(logits, n_crops, first_crop, T, V, ld, canonical, offsets, n, kmax,
+  ctc_records_kernel<<<n_crops, 32 * (T < 32 ? T : 32), 0, s>>>(logits, n_crops, first_crop, T, V, ld, canonical, offsets, n, kmax,
                                                       reinterpret_cast<vtd_record*>(records));
   if (lc) lc->n++;
   return cudaGetLastError();

@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
                                                         int srcb_cap, const float* __restrict__ lut_g,
                                                         T* __restrict__ out, OutLayout lay) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int ksx = tx.ksize, ksy = ty.ksize;
+  // coefficient rows are kept at a pitch of 4 ints (one 16-byte load) when no output sample has more than 4 taps
+  const bool fastx = tx.maxcnt <= 4, fasty = ty.maxcnt <= 4;
+  const int ksx = fastx ? 4 : tx.ksize, ksy = fasty ? 4 : ty.ksize;
   int* sx_lo = reinterpret_cast<int*>(smem);
   int* sx_cnt = sx_lo + TW;
   int* sx_k = sx_cnt + TW;
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
   int* sy_k = sy_cnt + TH;
   float* lut = reinterpret_cast<float*>(sy_k + TH * ksy);          // [3][256]: u8 -> (x/255 - mean)/std, IEEE fp32
   uint8_t* src = reinterpret_cast<uint8_t*>(lut + 768);
-  uint8_t* tmp = src + (size_t)rows_cap * srcb_cap;
+  uint32_t* tmp = reinterpret_cast<uint32_t*>(src + (size_t)rows_cap * srcb_cap);   // [rows + 4][TW] B | G<<8 | R<<16
 
   const uint8_t* __restrict__ f = frames[blockIdx.z];
   const int dw = tx.out_size, dh = ty.out_size;
@@ -66,9 +68,15 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
   const int tid = threadIdx.x;
 
   for (int i = tid; i < tw; i += NT) { sx_lo[i] = tx.lo[ox0 + i]; sx_cnt[i] = tx.cnt[ox0 + i]; }
-  for (int i = tid; i < tw * ksx; i += NT) sx_k[i] = tx.kk[(size_t)ox0 * ksx + i];
+  for (int i = tid; i < tw * ksx; i += NT) {
+    const int xo = i / ksx, j = i - xo * ksx;
+    sx_k[i] = j < tx.ksize ? tx.kk[(size_t)(ox0 + xo) * tx.ksize + j] : 0;
+  }
   for (int i = tid; i < th; i += NT) { sy_lo[i] = ty.lo[oy0 + i]; sy_cnt[i] = ty.cnt[oy0 + i]; }
-  for (int i = tid; i < th * ksy; i += NT) sy_k[i] = ty.kk[(size_t)oy0 * ksy + i];
+  for (int i = tid; i < th * ksy; i += NT) {
+    const int yo = i / ksy, j = i - yo * ksy;
+    sy_k[i] = j < ty.ksize ? ty.kk[(size_t)(oy0 + yo) * ty.ksize + j] : 0;
+  }
   for (int i = tid; i < 768; i += NT) lut[i] = __ldg(lut_g + i);
   const int r0 = ty.lo[oy0];
   const int r1 = ty.lo[oy0 + th - 1] + ty.cnt[oy0 + th - 1];       // exclusive (lo is non-decreasing)
@@ -113,22 +121,37 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
   }
   __syncthreads();
 
-  // ---- horizontal pass: one item = (source row, output column), all three channels; warps walk rows, lanes columns
+  // ---- horizontal pass: one item = (source row, output column), all three channels; warps walk rows, lanes columns.
+  // Fast path (<= 4 taps): the 12 source bytes of an item come in as four aligned 32-bit words realigned with funnel
+  // shifts and the four coefficients as one 16-byte load -- 5 shared-memory loads instead of 16 (the kernel was bound
+  // by the issue rate of byte loads, not by HBM); taps past cnt have zero coefficients.
   for (int r = tid >> 5; r < rows; r += NT / 32) {
     int skew = 0;
     if (PIX == 0) skew = (int)((reinterpret_cast<size_t>(f + (size_t)(r0 + r) * pitch) + c0 * 3) & 15);
-    const uint8_t* rowp = src + (size_t)r * srcb_cap + skew - c0 * 3;
+    const int rowoff = r * srcb_cap + skew - c0 * 3;                 // byte offset of source column 0 of this row in src
     for (int xo = tid & 31; xo < tw; xo += 32) {
-      const int lo = sx_lo[xo], cnt = sx_cnt[xo];
-      const int* kk = sx_k + xo * ksx;
-      const uint8_t* p = rowp + lo * 3;
+      const int lo = sx_lo[xo];
       int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
-      for (int j = 0; j < cnt; ++j) {
-        const int k = kk[j];
-        a0 += (int)p[j * 3] * k; a1 += (int)p[j * 3 + 1] * k; a2 += (int)p[j * 3 + 2] * k;
+      if (fastx) {
+        const int off = rowoff + lo * 3;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + (off & ~3));
+        const uint32_t sh = (uint32_t)(off & 3) * 8u;
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+        const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+        const int4 k = *reinterpret_cast<const int4*>(sx_k + xo * 4);
+        a0 += (int)(v0 & 255u) * k.x + (int)(v0 >> 24) * k.y + (int)((v1 >> 16) & 255u) * k.z + (int)((v2 >> 8) & 255u) * k.w;
+        a1 += (int)((v0 >> 8) & 255u) * k.x + (int)(v1 & 255u) * k.y + (int)(v1 >> 24) * k.z + (int)((v2 >> 16) & 255u) * k.w;
+        a2 += (int)((v0 >> 16) & 255u) * k.x + (int)((v1 >> 8) & 255u) * k.y + (int)(v2 & 255u) * k.z + (int)(v2 >> 24) * k.w;
+      } else {
+        const int cnt = sx_cnt[xo];
+        const int* kk = sx_k + xo * ksx;
+        const uint8_t* p = src + rowoff + lo * 3;
+        for (int j = 0; j < cnt; ++j) {
+          const int k = kk[j];
+          a0 += (int)p[j * 3] * k; a1 += (int)p[j * 3 + 1] * k; a2 += (int)p[j * 3 + 2] * k;
+        }
       }
-      uint8_t* t = tmp + (r * TW + xo) * 3;
-      t[0] = (uint8_t)clip8(a0 >> 22); t[1] = (uint8_t)clip8(a1 >> 22); t[2] = (uint8_t)clip8(a2 >> 22);
+      tmp[r * TW + xo] = (uint32_t)clip8(a0 >> 22) | ((uint32_t)clip8(a1 >> 22) << 8) | ((uint32_t)clip8(a2 >> 22) << 16);
     }
   }
   __syncthreads();
@@ -138,14 +161,25 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
     const int xo = it & (TW - 1), yo = it / TW;
     if (xo >= tw) continue;
     const int oy = oy0 + yo;
-    const int lo = sy_lo[yo] - r0, cnt = sy_cnt[yo];
-    const int* kk = sy_k + yo * ksy;
+    const int lo = sy_lo[yo] - r0;
     int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
-    const uint8_t* p = tmp + (lo * TW + xo) * 3;
-    for (int j = 0; j < cnt; ++j) {
-      const int k = kk[j];
-      a0 += (int)p[0] * k; a1 += (int)p[1] * k; a2 += (int)p[2] * k;
-      p += TW * 3;
+    const uint32_t* p = tmp + lo * TW + xo;
+    if (fasty) {
+      const int4 k = *reinterpret_cast<const int4*>(sy_k + yo * 4);
+      const uint32_t t0 = p[0], t1 = p[TW], t2 = p[2 * TW], t3 = p[3 * TW];      // rows past cnt: zero coefficients
+      a0 += (int)(t0 & 255u) * k.x + (int)(t1 & 255u) * k.y + (int)(t2 & 255u) * k.z + (int)(t3 & 255u) * k.w;
+      a1 += (int)((t0 >> 8) & 255u) * k.x + (int)((t1 >> 8) & 255u) * k.y + (int)((t2 >> 8) & 255u) * k.z +
+            (int)((t3 >> 8) & 255u) * k.w;
+      a2 += (int)((t0 >> 16) & 255u) * k.x + (int)((t1 >> 16) & 255u) * k.y + (int)((t2 >> 16) & 255u) * k.z +
+            (int)((t3 >> 16) & 255u) * k.w;
+    } else {
+      const int cnt = sy_cnt[yo];
+      const int* kk = sy_k + yo * ksy;
+      for (int j = 0; j < cnt; ++j) {
+        const int k = kk[j];
+        const uint32_t t = p[j * TW];
+        a0 += (int)(t & 255u) * k; a1 += (int)((t >> 8) & 255u) * k; a2 += (int)((t >> 16) & 255u) * k;
+      }
     }
     // source order is B,G,R; the network wants R,G,B (cvtColor at text_detector.py:120).  The table holds, per
     // channel, ToTensor (x/255) followed by Normalize ((x-mean)/std) evaluated with IEEE fp32 ops (see lut kernel).
@@ -183,9 +217,10 @@ cudaError_t preprocess_frames(const uint8_t* const* frames_dev, int n, int h, in
   const int rows_cap = (int)(TH * (sy > 1.0 ? sy : 1.0)) + ty.ksize + 2;
   const int cols_cap = (int)(TW * (sx > 1.0 ? sx : 1.0)) + tx.ksize + 2;
   const int srcb_cap = ((cols_cap * 3 + 15 + 15) / 16 + 1) * 16;          // + alignment skew, rounded to 16 bytes
-  size_t smem = sizeof(int) * (size_t)(2 * TW + TW * tx.ksize + 2 * TH + TH * ty.ksize);
+  const int ksx = tx.maxcnt <= 4 ? 4 : tx.ksize, ksy = ty.maxcnt <= 4 ? 4 : ty.ksize;
+  size_t smem = sizeof(int) * (size_t)(2 * TW + TW * ksx + 2 * TH + TH * ksy);
   smem = ((smem + 15) & ~(size_t)15) + 768 * sizeof(float);
-  smem += (size_t)rows_cap * srcb_cap + (size_t)rows_cap * TW * 3 + 16;
+  smem += (size_t)rows_cap * srcb_cap + (size_t)(rows_cap + 4) * TW * 4 + 16;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   dim3 grid((tx.out_size + TW - 1) / TW, (ty.out_size + TH - 1) / TH, n);
   cudaError_t e;
