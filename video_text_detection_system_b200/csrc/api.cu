@@ -207,7 +207,8 @@ int upload_f32(vtd_ctx* c, const std::vector<float>& h, float** dev) {
 
 // Append a conv op whose input/output live in the arena; N is the capacity the buffers were sized for.
 int add_conv(vtd_ctx* c, std::vector<Op>* prog, const HostConv& hc, int N, const Act& in, int stride, int pad,
-             bool relu, const Act* res, int res_mode, bool out_f32, Act* out, Op* standalone = nullptr) {
+             bool relu, const Act* res, int res_mode, bool out_f32, Act* out, Op* standalone = nullptr, int pool = 0,
+             bool* fused = nullptr) {
   if (in.C != hc.Cin_pad) FAIL(VTD_ERR_WEIGHT, "layer expects %d input channels, activation has %d", hc.Cin_pad, in.C);
   Op op;
   op.kind = Op::CONV;
@@ -231,14 +232,21 @@ int add_conv(vtd_ctx* c, std::vector<Op>* prog, const HostConv& hc, int N, const
   d.bias = bdev;
   size_t oes = out_f32 ? 4 : c->esz;
   void* o = nullptr;
+  // pool != 0 (tcgen05 tier only): the max-pool that follows is fused into the epilogue and `out` is the pooled map
+  // (the plan refuses when the staging would cost a ring slot: the caller then keeps the separate pooling kernel)
+  if (pool && !(c->bf16_mode && tc_supported(d))) pool = 0;
   r = dev_alloc(c, &o, (size_t)N * d.Ho * d.Wo * d.Cout * oes); if (r) return r;
   d.out = o;
   if (c->bf16_mode && tc_supported(d)) {
     std::string e;
+    d.pool = pool;
     op.plan = tc_plan_create(d, &e);
+    if (!op.plan && pool) { pool = 0; d.pool = 0; op.plan = tc_plan_create(d, &e); }
     if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 plan: %s", e.c_str());
   }
-  out->p = o; out->H = d.Ho; out->W = d.Wo; out->C = d.Cout;
+  const int pw = pool == 1 ? 2 : 1, ph = pool ? 2 : 1;
+  if (fused) *fused = pool != 0;
+  out->p = o; out->H = d.Ho / ph; out->W = d.Wo / pw; out->C = d.Cout;
   if (standalone) *standalone = op; else prog->push_back(op);
   return VTD_OK;
 }
@@ -505,6 +513,7 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
   std::vector<Op>& P = c->rec_prog;
   int r;
   Act a; a.p = c->crops; a.H = 32; a.W = cw; a.C = 4;
+  const bool fuse_pools = c->bf16_mode && !getenv("VTD_NO_POOL_FUSION");
   struct L { int conv, bn, k, pad; int pool; };   // pool: 0 none, 1 = 2x2 s2, 2 = (2,1) s(2,1)
   const L layers[7] = {{0, 1, 3, 1, 1}, {4, 5, 3, 1, 1}, {8, 9, 3, 1, 0}, {11, 12, 3, 1, 2},
                        {15, 16, 3, 1, 0}, {18, 19, 3, 1, 2}, {22, 23, 2, 0, 0}};
@@ -527,17 +536,25 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
       if ((r = upload_act_type(c, ww, &wdev)) || (r = upload_f32(c, hc.b, &bdev)) ||
           (r = dev_alloc(c, &o, (size_t)B * 32 * cw * 64 * c->esz)))
         return r;
+      const int fuse = (fuse_pools && layers[i].pool && cw % 2 == 0) ? layers[i].pool : 0;
       Op op;
       op.kind = Op::CONV;
       op.d.H = 32; op.d.W = cw; op.d.Cin = 4; op.d.Ho = 32; op.d.Wo = cw; op.d.Cout = 64; op.d.KH = op.d.KW = 3;
       op.d.stride = 1; op.d.pad = 1; op.d.N = B;
       std::string e;
-      op.plan = tc_plan_create_win(c->crops, B, 34, cw + 4, 8, 1, 3, 32, cw, wdev, bdev, o, 1, &e);
+      op.d.pool = fuse;
+      op.plan = tc_plan_create_win(c->crops, B, 34, cw + 4, 8, 1, 3, 32, cw, wdev, bdev, o, 1, &e, fuse);
       if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 CRNN stem plan: %s (set VTD_NO_WIN=1 to use the CUDA-core stem)", e.c_str());
       P.push_back(op);
-      a.p = o; a.H = 32; a.W = cw; a.C = 64;
+      a.p = o; a.H = fuse ? 16 : 32; a.W = fuse == 1 ? cw / 2 : cw; a.C = 64;
+      if (fuse) continue;
     } else {
-      if ((r = add_conv(c, &P, hc, B, a, 1, layers[i].pad, true, nullptr, RES_NONE, false, &a))) return r;
+      // nn.MaxPool2d after conv+BN+ReLU (text_recognizer.py:17-23): fused into the conv epilogue in the tcgen05 tier
+      const int fuse = (fuse_pools && layers[i].pool && a.H % 2 == 0 && (layers[i].pool == 2 || a.W % 2 == 0) &&
+                        hc.Cout % 64 == 0 && a.C % 64 == 0) ? layers[i].pool : 0;
+      bool fused = false;
+      if ((r = add_conv(c, &P, hc, B, a, 1, layers[i].pad, true, nullptr, RES_NONE, false, &a, nullptr, fuse, &fused))) return r;
+      if (fused) continue;
     }
     if (layers[i].pool == 1) { if ((r = add_pool(c, &P, B, a, 2, 2, 2, 2, 0, 0, &a))) return r; }
     else if (layers[i].pool == 2) { if ((r = add_pool(c, &P, B, a, 2, 1, 2, 1, 0, 0, &a))) return r; }

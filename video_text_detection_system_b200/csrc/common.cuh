@@ -32,6 +32,7 @@ struct ConvDesc {
   int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad;
   int relu, res_mode, out_mode;
   int out_f32;         // 1: `out` is fp32 regardless of the activation type (logits, gate pre-activations)
+  int pool = 0;        // tcgen05 path only: max-pool fused into the epilogue, `out` is the POOLED map: 1 = 2x2 s2, 2 = (2,1) s(2,1)
 };
 
 // generic CUDA-core path (any shape); T = float or bf16
@@ -41,7 +42,7 @@ template <typename T> cudaError_t conv_generic(const ConvDesc& d, cudaStream_t s
 struct TcPlan;   // opaque: tensor maps + launch geometry, built once per layer
 TcPlan* tc_plan_create(const ConvDesc& d, std::string* err);
 TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int stride, int nr, int Ho, int Wo,
-                           const void* w, const float* bias, void* out, int relu, std::string* err);
+                           const void* w, const float* bias, void* out, int relu, std::string* err, int pool = 0);
 TcPlan* tc_plan_create_dbhead(const void* feat, int N, int H4, int W4, const void* w1, const float* b1_host,
                               const float* w2_host, const float* b2_host, float* prob, float* thresh, uint8_t* mask,
                               std::string* err);

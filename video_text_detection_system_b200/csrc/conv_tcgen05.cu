@@ -74,6 +74,7 @@ struct TcParams {
   void* out;
   int stages, bres;           // operand ring depth; 1 = all weight K-slices stay resident in shared memory
   int epi_tma;                // 1 = epilogue stages 32 px x 128 B per warp in shared memory and leaves with a TMA store
+  int pool;                   // max-pool fused into the TMA-store epilogue (0 none, 1 = 2x2 s2, 2 = (2,1) s(2,1)); warp box is 16 x 2 px
   int res_tma;                // 1 = the residual of each warp's box arrives by TMA into shared memory, one item ahead
   int res_bytes;              // bytes of one residual box
   int kps;                    // K steps per ring slot: one full/empty handshake (and one tcgen05.commit) per kps steps
@@ -214,9 +215,9 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
 // 128B-swizzled staging block and one lane issues cp.async.bulk.tensor: full 128-byte rows, out-of-range pixels are
 // clipped by the tensor map, and the store drains while the warp converts the next group.
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUtensorMap* omap, uint32_t stg, uint32_t tmem_acc,
-                                                   int q, int lane, int g, bool use_res, const uint4 (&rv)[8], int nb, int cx,
-                                                   int cy, int cn) {
+__device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUtensorMap* omap, uint32_t stg, uint32_t pstg,
+                                                   uint32_t tmem_acc, int q, int lane, int g, bool use_res,
+                                                   const uint4 (&rv)[8], int nb, int cx, int cy, int cn) {
   const int gcols = p.out_f32 ? 32 : 64;                 // accumulator columns per 128-byte group
   const uint32_t row = stg + (uint32_t)lane * 128u;
   const uint32_t sw = (uint32_t)(lane & 7);
@@ -279,6 +280,50 @@ __device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUte
   for (int j = 0; j < 8; ++j)
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)j ^ sw) << 4)), "r"(o[j].x), "r"(o[j].y),
                  "r"(o[j].z), "r"(o[j].w) : "memory");
+  if (p.pool) {
+    // fused max-pool (nn.MaxPool2d after conv+BN+ReLU, text_recognizer.py:17-23): the warp's box is 16 x 2 pixels, so every
+    // pooling window lies inside it.  Each lane reduces a slice of one pooled pixel from the staged rows with packed
+    // bf16 max (max commutes with the bf16 rounding already applied) and only the pooled box goes to HBM.
+    __syncwarp();
+    const bool p22 = p.pool == 1;
+    const int pp = p22 ? lane >> 2 : lane >> 1;                 // pooled pixel of the box: 8 (2x2) or 16 ((2,1))
+    const int c_first = p22 ? (lane & 3) * 2 : (lane & 1) * 4;  // first 16-byte chunk of this lane's slice
+    const int nch = p22 ? 2 : 4;
+    const int r00 = p22 ? 2 * pp : pp;                          // top-left source row (pixel) of the window
+    const uint32_t prow = pstg + (uint32_t)pp * 128u;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) {
+      if (ci >= nch) break;
+      const uint32_t c = (uint32_t)(c_first + ci);
+      uint4 m4;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        if (!p22 && (w & 1)) continue;                          // (2,1): rows r and r + 16 only
+        const uint32_t r = (uint32_t)(r00 + (w & 1) + (w >> 1) * 16);
+        uint4 t;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+                     : "r"(stg + r * 128u + ((c ^ (r & 7u)) << 4)) : "memory");
+        if (w == 0) m4 = t;
+        else {
+          __nv_bfloat162 a, b;
+#define VTD_HMAX2(dst, src) a = *reinterpret_cast<__nv_bfloat162*>(&dst); b = *reinterpret_cast<__nv_bfloat162*>(&src); \
+          a = __hmax2(a, b); dst = *reinterpret_cast<uint32_t*>(&a);
+          VTD_HMAX2(m4.x, t.x) VTD_HMAX2(m4.y, t.y) VTD_HMAX2(m4.z, t.z) VTD_HMAX2(m4.w, t.w)
+#undef VTD_HMAX2
+        }
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c ^ ((uint32_t)pp & 7u)) << 4)), "r"(m4.x), "r"(m4.y),
+                   "r"(m4.z), "r"(m4.w) : "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(omap), "r"(pstg),
+                   "r"(co), "r"(p22 ? cx >> 1 : cx), "r"(cy >> 1), "r"(cn) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    return;
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
   if (lane == 0) {
@@ -308,15 +353,21 @@ __device__ __forceinline__ void epilogue_dbhead(const TcParams& p, const float* 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     const float* b1 = hs + g * 64 + ch * 32;
     const float4* w2 = reinterpret_cast<const float4*>(hs + 256) + ch * 32;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // packed fp32 (FADD2 / FFMA2, sm_100): the same IEEE operations in the same order, two lanes per instruction
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float h = fmaxf(__uint_as_float(v[j]) + b1[j], 0.f);
-      const float4 w = w2[j];
-      a0 = fmaf(h, w.x, a0); a1 = fmaf(h, w.y, a1); a2 = fmaf(h, w.z, a2); a3 = fmaf(h, w.w, a3);
+    for (int j = 0; j < 32; j += 2) {
+      float2 h = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                            *reinterpret_cast<const float2*>(b1 + j));
+      h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f);
+      const float4 w0 = w2[j], w1 = w2[j + 1];
+      a01 = __ffma2_rn(make_float2(h.x, h.x), make_float2(w0.x, w0.y), a01);
+      a23 = __ffma2_rn(make_float2(h.x, h.x), make_float2(w0.z, w0.w), a23);
+      a01 = __ffma2_rn(make_float2(h.y, h.y), make_float2(w1.x, w1.y), a01);
+      a23 = __ffma2_rn(make_float2(h.y, h.y), make_float2(w1.z, w1.w), a23);
     }
-    if (dx == 0) { o[0] += a0; o[1] += a1; o[2] += a2; o[3] += a3; }
-    else { o[4] += a0; o[5] += a1; o[6] += a2; o[7] += a3; }
+    if (dx == 0) { o[0] += a01.x; o[1] += a01.y; o[2] += a23.x; o[3] += a23.y; }
+    else { o[4] += a01.x; o[5] += a01.y; o[6] += a23.x; o[7] += a23.y; }
   }
   if (!valid) return;
   const int Wd = 4 * p.Wo, Hd = 4 * p.Ho;
@@ -426,7 +477,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const int ksteps_all = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
   const uint32_t bres0 = ring + stages * stage_bytes;                       // resident weight K-slices (if p.bres)
   const uint32_t bres_bytes = p.bres ? (uint32_t)ksteps_all * Cfg::B_STAGE_BYTES : 0u;
-  const uint32_t stg_bytes = (p.epi_tma ? (uint32_t)NUM_EPI_WARPS * 4096u : 0u) + (p.res_tma ? (uint32_t)NUM_EPI_WARPS * 4096u : 0u);
+  const uint32_t stg_bytes = (p.epi_tma ? (uint32_t)NUM_EPI_WARPS * 4096u : 0u) + (p.res_tma ? (uint32_t)NUM_EPI_WARPS * 4096u : 0u) +
+                             (p.pool ? (uint32_t)NUM_EPI_WARPS * 2048u : 0u);
   const uint32_t stg0 = bres0 + bres_bytes;                                  // 4 KB of store staging per epilogue warp
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + stages * stage_bytes + bres_bytes + stg_bytes);
   const uint32_t full0 = smem_u32(bars);                       // [MAX_STAGES]
@@ -597,6 +649,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       const int g0 = BLOCK_N == 64 ? 0 : half * (groups / 2), g1 = BLOCK_N == 64 ? groups : g0 + groups / 2;
       const bool use_res = p.res_mode != RES_NONE && !(p.dbg & 12);
       const uint32_t stg = stg0 + (uint32_t)(warp - 2) * 4096u;
+      const uint32_t pstg = stg0 + (uint32_t)NUM_EPI_WARPS * (4096u + (p.res_tma ? 4096u : 0u)) + (uint32_t)(warp - 2) * 2048u;
       const int m0 = q * 32;                              // first pixel of this warp inside the tile
       const int gcols = p.out_f32 ? 32 : 64;
       // residual: per-lane loads (16 B per lane at a pixel stride) cost one L1 tag lookup per lane and instruction; with
@@ -668,7 +721,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
           } else if (use_res && g > g0) {
             res_load(tile, g, rv);
           }
-          epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, tmem_acc, q, lane, g, use_res, rv, nb, tx * BW + (m0 & (BW - 1)),
+          epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, pstg, tmem_acc, q, lane, g, use_res, rv, nb, tx * BW + (m0 & (BW - 1)),
                                       ty * BH + ((m0 >> p.lw) & (BH - 1)), t * BNt + (m0 >> (p.lw + p.lh)));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -763,13 +816,15 @@ CUresult encode_act4d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int C
 
 // output map of the TMA-store epilogue: box = the 32 consecutive tile rows of one epilogue warp x 128 bytes of channels
 // up = 1: the map covers the half-resolution residual of an upsample-add; the box is the source pixels of the warp's box
+// pool: the map covers the POOLED output (W, H already pooled); 1 = 2x2, 2 = (2,1)
 CUresult encode_out(EncodeTiledFn enc, CUtensorMap* m, void* out, int out_f32, int C, int W, int H, int N, int lw, int lh, int up,
-                    int* box_bytes) {
+                    int* box_bytes, int pool = 0) {
   const int bw = 1 << lw, bh = 1 << lh;
   int sw = bw < 32 ? bw : 32;
   int sh = bh < 32 / sw ? bh : 32 / sw;
   const int sn = 32 / (sw * sh);
   if (up) { sw = sw > 1 ? sw / 2 : 1; sh = sh > 1 ? sh / 2 : 1; }
+  if (pool == 1) { sw /= 2; sh /= 2; } else if (pool == 2) { sh /= 2; }
   if (box_bytes) *box_bytes = sw * sh * sn * 128;
   const cuuint64_t es = out_f32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -829,13 +884,16 @@ bool tc_supported(const ConvDesc& d) {
   return true;
 }
 
-static void fill_common(TcPlan* pl, int N, int Ho, int Wo, int Cout, int Cin, int bn) {
+// pool != 0: the tile is 16 px wide and at least 2 rows high, so that an epilogue warp's 32 pixels are a 16 x 2 box
+// holding whole pooling windows
+static void fill_common(TcPlan* pl, int N, int Ho, int Wo, int Cout, int Cin, int bn, int pool = 0) {
   TcParams& p = pl->p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cin = Cin;
   p.KH = p.KW = 1; p.stride = 1; p.pad = 0;
   pick_tile(N, Ho, Wo, &p.lw, &p.lh);
-  if (const char* e = getenv("VTD_TILE")) {               // tuning aid: "lw,lh" for layers at least that large
+  if (pool) { p.lw = 4; p.lh = Ho >= 8 ? 3 : (Ho >= 4 ? 2 : 1); p.pool = pool; }
+  if (const char* e = pool ? nullptr : getenv("VTD_TILE")) {               // tuning aid: "lw,lh" for layers at least that large
     int a = 0, b = 0;
     if (sscanf(e, "%d,%d", &a, &b) == 2 && a + b <= 7 && (1 << a) <= Wo && (1 << b) <= Ho && (128 >> (a + b)) <= (N > 1 ? N : 1)) { p.lw = a; p.lh = b; }
   }
@@ -855,7 +913,10 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   memset(&pl->maps, 0, sizeof(pl->maps));
   pl->mode = MODE_CONV;
   const int bn = d.Cout % 256 == 0 ? 256 : (d.Cout % 128 == 0 ? 128 : 64);
-  fill_common(pl, d.N, d.Ho, d.Wo, d.Cout, d.Cin, bn);
+  if (d.pool && (d.out_f32 || d.res_mode != RES_NONE || (d.Ho & 1) || (d.pool == 1 && (d.Wo & 1)) || d.N * d.Ho * d.Wo < 128)) {
+    delete pl; return fail("fused pooling needs an even, bf16, residual-free output");
+  }
+  fill_common(pl, d.N, d.Ho, d.Wo, d.Cout, d.Cin, bn, d.pool);
   TcParams& p = pl->p;
   p.KH = d.KH; p.KW = d.KW; p.stride = d.stride; p.pad = d.pad;
   p.relu = d.relu; p.res_mode = d.res_mode; p.out_f32 = d.out_f32;
@@ -871,7 +932,8 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   }
   CUresult r = encode_weights(enc, &pl->maps.b, d.w, (long long)d.KH * d.KW * d.Cin, d.Cout, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
-  r = encode_out(enc, &pl->maps.o, d.out, d.out_f32, d.Cout, d.Wo, d.Ho, d.N, p.lw, p.lh, 0, nullptr);
+  r = encode_out(enc, &pl->maps.o, d.out, d.out_f32, d.Cout, d.pool == 1 ? d.Wo / 2 : d.Wo, d.pool ? d.Ho / 2 : d.Ho, d.N, p.lw, p.lh, 0,
+                 nullptr, d.pool);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r)); }
   if (d.res_mode != RES_NONE && !d.out_f32) {
     const int up = d.res_mode == RES_UP2 ? 1 : 0;
@@ -879,6 +941,7 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
     if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(residual) failed: " + std::to_string((int)r)); }
   }
   plan_finalize(pl);
+  if (d.pool && !pl->p.epi_tma) { delete pl; return fail("no shared memory left for the fused-pool staging"); }
   return pl;
 }
 
@@ -886,7 +949,7 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
 // top-left corner of the receptive field of output (0,0); consecutive outputs are `stride` pixels apart and
 // stride*cpp must be 8 elements (16 bytes).  Weights: [Cout=64][nr][32] bf16 (one 64-byte row per filter row).
 TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int stride, int nr, int Ho, int Wo,
-                           const void* w, const float* bias, void* out, int relu, std::string* err) {
+                           const void* w, const float* bias, void* out, int relu, std::string* err, int pool) {
   auto fail = [&](const std::string& m) -> TcPlan* { if (err) *err = m; return nullptr; };
   if (stride * cpp != 8 || (stride != 1 && stride != 2)) return fail("window stride must be 16 bytes");
   if ((Wo - 1) * stride * cpp + 32 > Wp * cpp) return fail("padded row too short for the last window");
@@ -895,7 +958,8 @@ TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int s
   TcPlan* pl = new TcPlan();
   memset(&pl->maps, 0, sizeof(pl->maps));
   pl->mode = MODE_WIN;
-  fill_common(pl, N, Ho, Wo, 64, 32, 64);
+  if (pool && ((Ho & 1) || (pool == 1 && (Wo & 1)))) { delete pl; return fail("fused pooling needs even output sizes"); }
+  fill_common(pl, N, Ho, Wo, 64, 32, 64, pool);
   TcParams& p = pl->p;
   p.nr = nr; p.sdiv = stride; p.relu = relu; p.bias = bias; p.out = out;
   const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
@@ -911,9 +975,10 @@ TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int s
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(window) failed: " + std::to_string((int)r)); }
   r = encode_weights(enc, &pl->maps.b, w, (long long)nr * 32, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
-  r = encode_out(enc, &pl->maps.o, out, 0, 64, Wo, Ho, N, p.lw, p.lh, 0, nullptr);
+  r = encode_out(enc, &pl->maps.o, out, 0, 64, pool == 1 ? Wo / 2 : Wo, pool ? Ho / 2 : Ho, N, p.lw, p.lh, 0, nullptr, pool);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r)); }
   plan_finalize(pl);
+  if (pool && !pl->p.epi_tma) { delete pl; return fail("no shared memory left for the fused-pool staging"); }
   return pl;
 }
 
@@ -1008,13 +1073,15 @@ static void plan_smem(TcPlan* pl) {
   };
   const int avail = SMEM_TOTAL - (p.bres ? bres_bytes : 0) - 1024 - Cfg::TAIL_BYTES;
   const int stg_bytes = NUM_EPI_WARPS * 4096;
+  const int pool_bytes = p.pool ? NUM_EPI_WARPS * 2048 : 0;
   int st_plain = 0, st_tma = 0;
   const int kps_plain = pick(avail, &st_plain);
-  const int kps_tma = pick(avail - stg_bytes, &st_tma);
+  const int kps_tma = pick(avail - stg_bytes - pool_bytes, &st_tma);
   // the TMA-store epilogue needs 32 KB of staging: take it unless that costs K-step batching or leaves < 3 ring slots
   // (the resident-weight 64-channel 3x3 layers, where the handshake per K step is the larger cost)
   bool tma = (MODE == MODE_CONV || MODE == MODE_WIN) && !getenv("VTD_NO_TMA_STORE") && kps_tma == kps_plain &&
              st_tma >= (st_plain < 3 ? st_plain : 3);
+  if (p.pool && !tma) { p.epi_tma = 0; p.kps = kps_plain; p.stages = st_plain; p.res_tma = 0; p.dbg = 0; pl->smem = 0; return; }   // caller falls back
   if (BN == 256 && tma && st_tma < 4 && st_plain >= 4) tma = false;
   if (p.out_f32 && p.res_mode != RES_NONE) tma = false;     // (no such layer) residual registers are sized for bf16 groups
   p.epi_tma = tma ? 1 : 0;
@@ -1025,14 +1092,14 @@ static void plan_smem(TcPlan* pl) {
   p.res_tma = 0;
   if (tma && p.res_mode != RES_NONE && !getenv("VTD_NO_TMA_RES") && (p.res_mode != RES_UP2 || p.lw >= 1)) {
     int st_r = 0;
-    if (pick(avail - 2 * stg_bytes, &st_r) == p.kps && st_r >= (p.stages < 4 ? p.stages : 4)) { p.res_tma = 1; p.stages = st_r; }
+    if (pick(avail - 2 * stg_bytes - pool_bytes, &st_r) == p.kps && st_r >= (p.stages < 4 ? p.stages : 4)) { p.res_tma = 1; p.stages = st_r; }
   }
   if (const char* e = getenv("VTD_TC_STAGES")) {          // tuning aid: cap the ring depth
     int cap = atoi(e);
     if (cap >= 2 && cap < p.stages) p.stages = cap;
   }
   p.dbg = getenv("VTD_DBG") ? atoi(getenv("VTD_DBG")) : 0;
-  pl->smem = p.stages * p.kps * step_bytes + (p.bres ? bres_bytes : 0) + (tma ? stg_bytes : 0) + (p.res_tma ? stg_bytes : 0) + 1024 +
+  pl->smem = p.stages * p.kps * step_bytes + (p.bres ? bres_bytes : 0) + (tma ? stg_bytes + pool_bytes : 0) + (p.res_tma ? stg_bytes : 0) + 1024 +
              Cfg::TAIL_BYTES;
 }
 
