@@ -602,14 +602,21 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
     int as = 0; uint32_t aphase = 0;
     TMR_DECL
     if (p.bres && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0);
+    bool ready = false;                                 // the slot about to be consumed is already known to be full
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TMR_WAIT(tmr_wait2, mbar_wait(tempty0 + 8 * as, aphase ^ 1))
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
       for (int ks0 = 0; ks0 < ksteps; ks0 += kps) {
         constexpr int nk = kps;
-        TMR_WAIT(tmr_wait, mbar_wait(full0 + 8 * stage, phase))
+        if (!ready) { TMR_WAIT(tmr_wait, mbar_wait(full0 + 8 * stage, phase)) }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // look one slot ahead before issuing (test_wait never suspends): the probe's round trip to the barrier overlaps
+        // the MMA issue below.  A/B on one box: -2..5 % on the N = 256 layers; the same trick in the producer, a second
+        // producer warp, and warp-uniform producer bookkeeping measured neutral or worse and were dropped.
+        const int nstage = stage + 1 == stages ? 0 : stage + 1;
+        const uint32_t nphase = stage + 1 == stages ? phase ^ 1 : phase;
+        const bool probe = mbar_test(full0 + 8 * nstage, nphase);
         if (elect_one()) {
           const uint32_t sa = ring + stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)kps * Cfg::A_BYTES;
@@ -626,8 +633,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
           umma_commit(empty0 + 8 * stage);            // frees the slot when these MMAs have read it
           if (ks0 + nk >= ksteps) umma_commit(tfull0 + 8 * as);   // accumulator complete
         }
-        __syncwarp();
-        if (++stage == stages) { stage = 0; phase ^= 1; }
+        ready = __any_sync(0xffffffffu, probe);       // a completed phase stays completed: any lane's "yes" holds for all
+        stage = nstage; phase = nphase;
       }
       if (++as == acc_n) { as = 0; aphase ^= 1; }
     }

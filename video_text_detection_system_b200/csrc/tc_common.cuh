@@ -41,6 +41,18 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// non-blocking probe (test_wait never suspends): used to look one ring slot ahead
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // Bounded wait, lean enough for the per-slot handshakes: a failed try_wait has already been suspended by the hardware
 // for its time limit, so a plain probe counter is the watchdog (2^26 failed probes is seconds): trap, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
