@@ -832,7 +832,7 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   c->frame_bytes_cap = (((size_t)cfg->max_src_h * cfg->max_src_w * 3) + 255) & ~(size_t)255;
   if ((r = dalloc(c, &c->frames_store, c->frame_bytes_cap * B)) || (r = dalloc(c, &c->store_ptrs_dev, sizeof(void*) * B)) ||
       (r = dalloc(c, &c->ext_ptrs_dev, sizeof(void*) * B)) ||
-      (r = dev_alloc(c, &c->pre, (size_t)B * (c->use_win ? (size_t)(dh + 6) * (dw + 8) : px) * 4 * c->esz)) || (r = dalloc(c, &c->prob, (size_t)B * px * 4)) ||
+      (r = dev_alloc(c, &c->pre, (size_t)B * (c->use_win ? (size_t)(dh + 6) * (dw + 8) : px) * 4 * c->esz + 4096 /* the stem's row copies overhang */)) || (r = dalloc(c, &c->prob, (size_t)B * px * 4)) ||
       (r = dalloc(c, &c->thresh, (size_t)B * px * 4)) || (r = dalloc(c, &c->mask, (size_t)B * px)) ||
       (r = dalloc(c, &c->records, sizeof(vtd_record) * (size_t)B * cfg->max_boxes)) ||
       (r = dalloc(c, &c->counts, sizeof(int) * B)) || (r = dalloc(c, &c->offsets, sizeof(int) * (B + 1))) ||

@@ -52,6 +52,8 @@ using namespace tc;
 constexpr int BLOCK_K = 64;          // bf16 elements = one 128-byte swizzle row
 constexpr int NUM_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 constexpr int NUM_EPI_WARPS = 8;
+constexpr int WIN2_SLAB = 2112;       // bytes of one input row a 128-pixel tile touches: (2 * 127 + 8) px * 8 B, rounded to 16
+constexpr int WIN2_SLOT = 15 * 1024;            // one ring slot = the 7 filter rows of a tile (14784 B), 1 KB granular
 
 struct alignas(64) TcMaps {
   CUtensorMap a[4];     // activation maps; [0] only for stride 1, [py*2+px] for stride 2
@@ -82,6 +84,10 @@ struct TcParams {
   int dbg;                    // VTD_DBG timing experiments (results are wrong): 1 no A loads, 2 no MMAs, 4 no stores
   // MODE_WIN
   int nr, sdiv;               // filter rows (= K steps), row phases (= conv stride)
+  int win2;                   // 1 = direct windows: one-row tiles, the nr input rows of a tile are copied ONCE (bulk copies) and
+                              //     the MMA reads the overlapping 64-byte windows in place (no-swizzle descriptor, 16-byte row pitch)
+  const uint8_t* win_in;      // win2: padded input, row / image pitches in bytes
+  long long win_rp, win_ip;
   // MODE_DBHEAD
   const float* logit_bias; float* prob; float* thresh; uint8_t* mask;
   // MODE_LSTM
@@ -131,6 +137,14 @@ struct TcCfg {
 
 };
 
+
+// No-swizzle K-major descriptor (core matrix = 8 rows x 16 bytes, rows 16 bytes apart): lbo = byte stride between core
+// matrices along K, sbo = along M.  With lbo = 16, sbo = 128 row m starts 16 bytes after row m-1 and rows OVERLAP: exactly
+// the im2col of a convolution whose consecutive outputs are 16 bytes apart in a padded NHWC row
+// (profiles/micro/umma_nosw.cu checks the hardware reads it that way).
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
 
 // ---- epilogues ---------------------------------------------------------------------------------------------
 
@@ -473,7 +487,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const int stages = p.stages;
   constexpr int kps = KPS;                       // K steps per ring slot (host: ksteps % KPS == 0)
   const uint32_t step_bytes = p.bres ? Cfg::A_BYTES : Cfg::STAGE_BYTES;      // bytes one K step brings in
-  const uint32_t stage_bytes = (uint32_t)kps * step_bytes;                   // slot = kps A slabs, then kps B slabs
+  const uint32_t stage_bytes = (MODE == MODE_WIN && p.win2) ? (uint32_t)WIN2_SLOT : (uint32_t)kps * step_bytes;   // slot = kps A slabs, then kps B slabs
   const int ksteps_all = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
   const uint32_t bres0 = ring + stages * stage_bytes;                       // resident weight K-slices (if p.bres)
   const uint32_t bres_bytes = p.bres ? (uint32_t)ksteps_all * Cfg::B_STAGE_BYTES : 0u;
@@ -562,6 +576,16 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
           const uint32_t sa = ring + stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)kps * Cfg::A_BYTES;
           const uint32_t fb = full0 + 8 * stage;
+          if (MODE == MODE_WIN && p.win2) {
+            // the nr input rows under this one-row tile, each copied once: 7 x 2112 B instead of 7 boxes of 128 overlapping
+            // 64-byte windows (57 KB; the windowed TMA ran at ~3.8 cycles per 64-byte row and bound the kernel)
+            mbar_expect_tx(fb, (uint32_t)nk * WIN2_SLAB);
+            const uint8_t* src = p.win_in + (size_t)n0 * p.win_ip + (size_t)(y0 * p.sdiv) * p.win_rp + (size_t)x0 * 16;
+#pragma unroll
+            for (int j = 0; j < nk; ++j)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(sa + j * WIN2_SLAB), "l"(src + (size_t)j * p.win_rp), "r"((uint32_t)WIN2_SLAB), "r"(fb) : "memory");
+          } else {
           if (p.dbg & 1) {
             if (p.bres) mbar_arrive(fb); else mbar_expect_tx(fb, (uint32_t)nk * Cfg::B_STAGE_BYTES);
           } else {
@@ -588,6 +612,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
                 tma_load_2d(sb + j * Cfg::B_STAGE_BYTES, &maps.b, fb, (r * p.KW + sx) * p.Cin + kc * BLOCK_K, nb * BLOCK_N);
               if (++kc == kchunks) { kc = 0; if (++sx == p.KW) { sx = 0; ++r; } }
             }
+          }
           }
         }
         __syncwarp();
@@ -623,7 +648,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
           if (!(p.dbg & 2)) {
 #pragma unroll
             for (int j = 0; j < nk; ++j) {
-              const uint64_t ad = umma_desc<ROWB>(sa + j * Cfg::A_BYTES);
+              const uint64_t ad = (MODE == MODE_WIN && p.win2) ? umma_desc_nosw(sa + j * WIN2_SLAB, 16, 128)
+                                                               : umma_desc<ROWB>(sa + j * Cfg::A_BYTES);
               const uint64_t bd = umma_desc<ROWB>(p.bres ? bres0 + (ks0 + j) * Cfg::B_STAGE_BYTES : sb + j * Cfg::B_STAGE_BYTES);
 #pragma unroll
               for (int k = 0; k < ROWB / 32; ++k)
@@ -969,6 +995,16 @@ TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int s
   fill_common(pl, N, Ho, Wo, 64, 32, 64, pool);
   TcParams& p = pl->p;
   p.nr = nr; p.sdiv = stride; p.relu = relu; p.bias = bias; p.out = out;
+  // DBNet stem: direct windows (see TcParams::win2).  One-row tiles of 128 outputs; the last tile of a row hangs over the
+  // right edge (its copies run into the next padded row: the buffer has slack after the last image, see api.cu).
+  p.win2 = (stride == 2 && cpp == 4 && nr == 7 && !pool && Wo >= 128 && !getenv("VTD_NO_WIN2")) ? 1 : 0;
+  if (p.win2) {
+    p.lw = 7; p.lh = 0;
+    p.tiles_x = (Wo + 127) / 128; p.tiles_y = Ho; p.tiles_n = N;
+    p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
+    p.win_in = reinterpret_cast<const uint8_t*>(in);
+    p.win_rp = (long long)Wp * cpp * 2; p.win_ip = (long long)Hp * Wp * cpp * 2;
+  }
   const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
   const long long row = (long long)Wp * cpp;            // elements per padded row
   // dims: window element, ox (16-byte stride: overlapping windows), row phase, oy, image
@@ -1070,9 +1106,9 @@ static void plan_smem(TcPlan* pl) {
     int kps = 1;
     for (int c = want; c >= 1; --c) {
       if (MODE == MODE_WIN ? (c != 7 && c != 3 && c != 1) : c > 3) continue;       // instantiated variants
-      if (ksteps % c == 0 && avail / (c * step_bytes) >= (c == 1 ? 2 : 3)) { kps = c; break; }
+      if (ksteps % c == 0 && avail / (p.win2 ? WIN2_SLOT : c * step_bytes) >= (c == 1 ? 2 : 3)) { kps = c; break; }
     }
-    int st = avail / (kps * step_bytes);
+    int st = avail / (p.win2 ? WIN2_SLOT : kps * step_bytes);
     if (st > Cfg::MAX_STAGES) st = Cfg::MAX_STAGES;
     if (!p.bres && kps == 1 && st > Cfg::STAGES) st = Cfg::STAGES;
     *stages_out = st;
@@ -1106,7 +1142,7 @@ static void plan_smem(TcPlan* pl) {
     if (cap >= 2 && cap < p.stages) p.stages = cap;
   }
   p.dbg = getenv("VTD_DBG") ? atoi(getenv("VTD_DBG")) : 0;
-  pl->smem = p.stages * p.kps * step_bytes + (p.bres ? bres_bytes : 0) + (tma ? stg_bytes + pool_bytes : 0) + (p.res_tma ? stg_bytes : 0) + 1024 +
+  pl->smem = p.stages * (p.win2 ? WIN2_SLOT : p.kps * step_bytes) + (p.bres ? bres_bytes : 0) + (tma ? stg_bytes + pool_bytes : 0) + (p.res_tma ? stg_bytes : 0) + 1024 +
              Cfg::TAIL_BYTES;
 }
 
