@@ -52,6 +52,9 @@ using namespace tc;
 constexpr int BLOCK_K = 64;          // bf16 elements = one 128-byte swizzle row
 constexpr int NUM_THREADS = 320;      // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 constexpr int NUM_EPI_WARPS = 8;
+constexpr int HALO_PW = 10, HALO_PH = 18;                 // patch of an 8 x 16 tile of a 3x3 pad-1 conv
+constexpr int HALO_BYTES = HALO_PW * HALO_PH * 128;      // 23040: one 64-channel chunk of the patch
+constexpr int HALO_SLOT = 23 * 1024;
 constexpr int WIN2_SLAB = 2112;       // bytes of one input row a 128-pixel tile touches: (2 * 127 + 8) px * 8 B, rounded to 16
 constexpr int WIN2_SLOT = 15 * 1024;            // one ring slot = the 7 filter rows of a tile (14784 B), 1 KB granular
 
@@ -79,6 +82,8 @@ struct TcParams {
   int pool;                   // max-pool fused into the TMA-store epilogue (0 none, 1 = 2x2 s2, 2 = (2,1) s(2,1)); warp box is 16 x 2 px
   int res_tma;                // 1 = the residual of each warp's box arrives by TMA into shared memory, one item ahead
   int res_bytes;              // bytes of one residual box
+  int halo;                   // 1 = 3x3 s1 p1 conv read from ONE halo patch per tile and 64-channel chunk: tile 8 x 16 px, patch 10 x 18 px
+                              //     (SWIZZLE_128B as TMA stores it); the 9 taps are 9 descriptor start addresses (row shifts)
   int kps;                    // K steps per ring slot: one full/empty handshake (and one tcgen05.commit) per kps steps
   long long* timers;          // VTD_TIMERS builds: [grid][3 roles][total, wait, wait2] cycles
   int dbg;                    // VTD_DBG timing experiments (results are wrong): 1 no A loads, 2 no MMAs, 4 no stores
@@ -144,6 +149,14 @@ struct TcCfg {
 // (profiles/micro/umma_nosw.cu checks the hardware reads it that way).
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+// SWIZZLE_128B K-major descriptor whose 8-row groups are `sbo` bytes apart and whose start may be any 128-byte row of a
+// swizzled region: the XOR pattern is a function of the absolute shared-memory address (profiles/micro/umma_shift.cu:
+// exact for start rows 1, 11, 21 with sbo = 1280 and the base-offset field left 0).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
 }
 
 // ---- epilogues ---------------------------------------------------------------------------------------------
@@ -487,7 +500,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const int stages = p.stages;
   constexpr int kps = KPS;                       // K steps per ring slot (host: ksteps % KPS == 0)
   const uint32_t step_bytes = p.bres ? Cfg::A_BYTES : Cfg::STAGE_BYTES;      // bytes one K step brings in
-  const uint32_t stage_bytes = (MODE == MODE_WIN && p.win2) ? (uint32_t)WIN2_SLOT : (uint32_t)kps * step_bytes;   // slot = kps A slabs, then kps B slabs
+  const uint32_t stage_bytes = (MODE == MODE_WIN && p.win2) ? (uint32_t)WIN2_SLOT
+                               : (MODE == MODE_CONV && p.halo) ? (uint32_t)HALO_SLOT : (uint32_t)kps * step_bytes;   // slot = kps A slabs, then kps B slabs
   const int ksteps_all = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
   const uint32_t bres0 = ring + stages * stage_bytes;                       // resident weight K-slices (if p.bres)
   const uint32_t bres_bytes = p.bres ? (uint32_t)ksteps_all * Cfg::B_STAGE_BYTES : 0u;
@@ -544,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const int BNt = BLOCK_M >> (p.lw + p.lh);
   constexpr int acc_n = Cfg::ACC;
   const int kchunks = p.Cin / BLOCK_K;
-  const int ksteps = MODE == MODE_WIN ? p.nr : p.KH * p.KW * kchunks;
+  const int ksteps = MODE == MODE_WIN ? p.nr : ((MODE == MODE_CONV && p.halo) ? kchunks : p.KH * p.KW * kchunks);   // ring slots x kps per tile
   const int total_tiles = p.total_tiles;
 
   if (warp == 0) {
@@ -576,7 +590,12 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
           const uint32_t sa = ring + stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)kps * Cfg::A_BYTES;
           const uint32_t fb = full0 + 8 * stage;
-          if (MODE == MODE_WIN && p.win2) {
+          if (MODE == MODE_CONV && p.halo) {
+            // one box per 64-channel chunk: the tile's pixels plus a 1-pixel ring (out-of-range rows / columns are zero
+            // filled = the padding); every tap reads it in place, so the activation crosses L2 -> SM once, not 9 times
+            mbar_expect_tx(fb, (uint32_t)HALO_BYTES);
+            tma_load_4d(sa, &maps.a[1], fb, ks0 * BLOCK_K, x0 - 1, y0 - 1, n0);
+          } else if (MODE == MODE_WIN && p.win2) {
             // the nr input rows under this one-row tile, each copied once: 7 x 2112 B instead of 7 boxes of 128 overlapping
             // 64-byte windows (57 KB; the windowed TMA ran at ~3.8 cycles per 64-byte row and bound the kernel)
             mbar_expect_tx(fb, (uint32_t)nk * WIN2_SLAB);
@@ -645,7 +664,15 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         if (elect_one()) {
           const uint32_t sa = ring + stage * stage_bytes;
           const uint32_t sb = sa + (uint32_t)kps * Cfg::A_BYTES;
-          if (!(p.dbg & 2)) {
+          if (MODE == MODE_CONV && p.halo) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint64_t ad = umma_desc_sw128(sa + (uint32_t)((t / 3) * HALO_PW + (t % 3)) * 128u, HALO_PW * 128u);
+              const uint64_t bd = umma_desc<ROWB>(bres0 + (uint32_t)(t * kchunks + ks0) * Cfg::B_STAGE_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ks0 | t | k) ? 1u : 0u);
+            }
+          } else if (!(p.dbg & 2)) {
 #pragma unroll
             for (int j = 0; j < nk; ++j) {
               const uint64_t ad = (MODE == MODE_WIN && p.win2) ? umma_desc_nosw(sa + j * WIN2_SLAB, 16, 128)
@@ -954,6 +981,18 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   p.KH = d.KH; p.KW = d.KW; p.stride = d.stride; p.pad = d.pad;
   p.relu = d.relu; p.res_mode = d.res_mode; p.out_f32 = d.out_f32;
   p.bias = d.bias; p.res = reinterpret_cast<const bf16*>(d.res); p.out = d.out;
+  // 64 -> 64 3x3 s1 p1 (ResNet layer1): halo mode, see TcParams::halo.  Needs the weights resident (72 KB) and one 64-channel
+  // chunk per pixel, tile 8 x 16 x 1 image.
+  p.halo = (d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && d.Cin == 64 && d.Cout == 64 && !d.pool && d.Ho >= 8 &&
+            d.Wo >= 8 && !getenv("VTD_NO_HALO") && !getenv("VTD_NO_BRES")) ? 1 : 0;
+  if (p.halo) {
+    p.lw = 3; p.lh = 4;
+    p.tiles_x = (d.Wo + 7) / 8; p.tiles_y = (d.Ho + 15) / 16; p.tiles_n = d.N;
+    p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
+    CUresult hr = encode_act4d(enc, &pl->maps.a[1], d.in, d.Cin, d.W, d.H, d.N, d.Cin, (long long)d.W * d.Cin,
+                               (long long)d.H * d.W * d.Cin, HALO_PW, HALO_PH, 1);
+    if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(halo patch) failed: " + std::to_string((int)hr)); }
+  }
   const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
   const int nmaps = d.stride == 1 ? 1 : 4;
   for (int mi = 0; mi < nmaps; ++mi) {
@@ -1099,16 +1138,16 @@ static void plan_smem(TcPlan* pl) {
   // K steps per ring slot.  A slot handshake costs ~300-500 cycles in the two role warps; the MMAs of one K step take
   // 4 x max(32, N/2) cycles.  N = 256 hides it with one step per slot; narrower tiles batch up to 3 steps (a divisor of
   // the step count, at least 3 slots in the ring); the 3-channel stems (2 MMAs per filter row) take the whole filter.
-  int want = MODE == MODE_WIN ? 7 : (BN >= 256 ? 1 : 3);
+  int want = MODE == MODE_WIN ? 7 : (BN >= 256 || p.halo ? 1 : 3);
   if (MODE == MODE_LSTM || MODE == MODE_DBHEAD) want = 1;
   if (const char* e = getenv("VTD_KPS")) { int v = atoi(e); if (v >= 1 && BN < 256) want = v; }
   auto pick = [&](int avail, int* stages_out) {
     int kps = 1;
     for (int c = want; c >= 1; --c) {
       if (MODE == MODE_WIN ? (c != 7 && c != 3 && c != 1) : c > 3) continue;       // instantiated variants
-      if (ksteps % c == 0 && avail / (p.win2 ? WIN2_SLOT : c * step_bytes) >= (c == 1 ? 2 : 3)) { kps = c; break; }
+      if (ksteps % c == 0 && avail / (p.win2 ? WIN2_SLOT : p.halo ? HALO_SLOT : c * step_bytes) >= (c == 1 ? 2 : 3)) { kps = c; break; }
     }
-    int st = avail / (p.win2 ? WIN2_SLOT : kps * step_bytes);
+    int st = avail / (p.win2 ? WIN2_SLOT : p.halo ? HALO_SLOT : kps * step_bytes);
     if (st > Cfg::MAX_STAGES) st = Cfg::MAX_STAGES;
     if (!p.bres && kps == 1 && st > Cfg::STAGES) st = Cfg::STAGES;
     *stages_out = st;
@@ -1135,14 +1174,14 @@ static void plan_smem(TcPlan* pl) {
   p.res_tma = 0;
   if (tma && p.res_mode != RES_NONE && !getenv("VTD_NO_TMA_RES") && (p.res_mode != RES_UP2 || p.lw >= 1)) {
     int st_r = 0;
-    if (pick(avail - 2 * stg_bytes - pool_bytes, &st_r) == p.kps && st_r >= (p.stages < 4 ? p.stages : 4)) { p.res_tma = 1; p.stages = st_r; }
+    if (pick(avail - 2 * stg_bytes - pool_bytes, &st_r) == p.kps && st_r >= (p.halo ? 3 : (p.stages < 4 ? p.stages : 4))) { p.res_tma = 1; p.stages = st_r; }
   }
   if (const char* e = getenv("VTD_TC_STAGES")) {          // tuning aid: cap the ring depth
     int cap = atoi(e);
     if (cap >= 2 && cap < p.stages) p.stages = cap;
   }
   p.dbg = getenv("VTD_DBG") ? atoi(getenv("VTD_DBG")) : 0;
-  pl->smem = p.stages * (p.win2 ? WIN2_SLOT : p.kps * step_bytes) + (p.bres ? bres_bytes : 0) + (tma ? stg_bytes + pool_bytes : 0) + (p.res_tma ? stg_bytes : 0) + 1024 +
+  pl->smem = p.stages * (p.win2 ? WIN2_SLOT : p.halo ? HALO_SLOT : p.kps * step_bytes) + (p.bres ? bres_bytes : 0) + (tma ? stg_bytes + pool_bytes : 0) + (p.res_tma ? stg_bytes : 0) + 1024 +
              Cfg::TAIL_BYTES;
 }
 
