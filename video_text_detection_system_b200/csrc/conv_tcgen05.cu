@@ -63,6 +63,7 @@ struct alignas(64) TcMaps {
   CUtensorMap b;        // weights
   CUtensorMap o;        // output (TMA-store epilogue): box = one epilogue warp's 32 pixels x 128 bytes of channels
   CUtensorMap r;        // residual (TMA-store epilogue with p.res_tma): the source pixels of that box
+  CUtensorMap b4;       // halo mode with streamed weights: {64, Cout, 64-channel chunk, tap}: one box = b_taps taps of one chunk
 };
 
 enum { MODE_CONV = 0, MODE_WIN = 1, MODE_DBHEAD = 2, MODE_LSTM = 3 };
@@ -84,6 +85,7 @@ struct TcParams {
   int res_bytes;              // bytes of one residual box
   int halo;                   // 1 = 3x3 s1 p1 conv read from ONE halo patch per tile and 64-channel chunk: tile 8 x 16 px, patch 10 x 18 px
                               //     (SWIZZLE_128B as TMA stores it); the 9 taps are 9 descriptor start addresses (row shifts)
+  int b_stages, b_taps;       // halo == 2 (weights streamed): second ring of b_stages slots, each b_taps taps of one 64-channel chunk
   int kps;                    // K steps per ring slot: one full/empty handshake (and one tcgen05.commit) per kps steps
   long long* timers;          // VTD_TIMERS builds: [grid][3 roles][total, wait, wait2] cycles
   int dbg;                    // VTD_DBG timing experiments (results are wrong): 1 no A loads, 2 no MMAs, 4 no stores
@@ -503,12 +505,14 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   const uint32_t stage_bytes = (MODE == MODE_WIN && p.win2) ? (uint32_t)WIN2_SLOT
                                : (MODE == MODE_CONV && p.halo) ? (uint32_t)HALO_SLOT : (uint32_t)kps * step_bytes;   // slot = kps A slabs, then kps B slabs
   const int ksteps_all = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
-  const uint32_t bres0 = ring + stages * stage_bytes;                       // resident weight K-slices (if p.bres)
+  const uint32_t bslot_bytes = (MODE == MODE_CONV && p.halo == 2) ? (uint32_t)p.b_taps * Cfg::B_STAGE_BYTES : 0u;
+  const uint32_t bring = ring + stages * stage_bytes;                       // halo == 2: the weight ring follows the patch ring
+  const uint32_t bres0 = bring + (uint32_t)(MODE == MODE_CONV && p.halo == 2 ? p.b_stages : 0) * bslot_bytes;   // resident weight K-slices (if p.bres)
   const uint32_t bres_bytes = p.bres ? (uint32_t)ksteps_all * Cfg::B_STAGE_BYTES : 0u;
   const uint32_t stg_bytes = (p.epi_tma ? (uint32_t)NUM_EPI_WARPS * 4096u : 0u) + (p.res_tma ? (uint32_t)NUM_EPI_WARPS * 4096u : 0u) +
                              (p.pool ? (uint32_t)NUM_EPI_WARPS * 2048u : 0u);
   const uint32_t stg0 = bres0 + bres_bytes;                                  // 4 KB of store staging per epilogue warp
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + stages * stage_bytes + bres_bytes + stg_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (bres0 - ring) + bres_bytes + stg_bytes);
   const uint32_t full0 = smem_u32(bars);                       // [MAX_STAGES]
   const uint32_t empty0 = full0 + 8 * Cfg::MAX_STAGES;         // [MAX_STAGES]
   const uint32_t tfull0 = empty0 + 8 * Cfg::MAX_STAGES;        // [4]
@@ -528,6 +532,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    if (MODE == MODE_CONV && p.halo == 2)
+      for (int i = 0; i < p.b_stages; ++i) { mbar_init(full0 + 8 * (8 + i), 1); mbar_init(empty0 + 8 * (8 + i), 1); }
     // BLOCK_N = 64 with the TMA-store epilogue: the two halves of the epilogue take alternate tiles (4 arrivals each)
     const uint32_t epi_arrivals = (BLOCK_N == 64 && p.epi_tma) ? NUM_EPI_WARPS / 2 : NUM_EPI_WARPS;
     for (int i = 0; i < Cfg::ACC; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, epi_arrivals); }
@@ -576,6 +582,38 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       }
       __syncwarp();
     }
+    if (MODE == MODE_CONV && p.halo == 2) {
+      // halo mode with streamed weights: two rings.  Per tile and 64-channel chunk ONE patch (patch ring) and 9 / b_taps weight
+      // boxes of b_taps taps each (weight ring): 4 + 12 TMAs per tile for 256 -> 128 instead of 72, and the activation
+      // crosses L2 -> SM once instead of nine times.
+      int bs = 0; uint32_t bph = 0;
+      const int tgroups = 9 / p.b_taps;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int nb = t % p.n_blocks; t /= p.n_blocks;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int x0 = tx * BW, y0 = ty * BH, n0 = t * BNt;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(full0 + 8 * stage, (uint32_t)HALO_BYTES);
+            tma_load_4d(ring + stage * stage_bytes, &maps.a[1], full0 + 8 * stage, kc * BLOCK_K, x0 - 1, y0 - 1, n0);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+          for (int tg = 0; tg < tgroups; ++tg) {
+            mbar_wait(empty0 + 8 * (8 + bs), bph ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(full0 + 8 * (8 + bs), bslot_bytes);
+              tma_load_4d(bring + bs * bslot_bytes, &maps.b4, full0 + 8 * (8 + bs), 0, nb * BLOCK_N, kc, tg * p.b_taps);
+            }
+            __syncwarp();
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int t = tile;
       const int nb = t % p.n_blocks; t /= p.n_blocks;
@@ -647,6 +685,53 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
     TMR_DECL
     if (p.bres && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0);
     bool ready = false;                                 // the slot about to be consumed is already known to be full
+    if (MODE == MODE_CONV && p.halo == 2) {
+      int bs = 0; uint32_t bph = 0;
+      const int tgroups = 9 / p.b_taps;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(full0 + 8 * stage, phase);
+          const uint32_t sa = ring + stage * stage_bytes;
+          int fr = 0, fs = 0;                               // filter row / column of the next tap
+          for (int tg = 0; tg < tgroups; ++tg) {
+            if (!ready) mbar_wait(full0 + 8 * (8 + bs), bph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int nbs = bs + 1 == p.b_stages ? 0 : bs + 1;
+            const uint32_t nbph = bs + 1 == p.b_stages ? bph ^ 1 : bph;
+            const bool probe = mbar_test(full0 + 8 * (8 + nbs), nbph);      // next weight slot, looked at before issuing
+            if (elect_one()) {
+              const uint32_t sbb = bring + bs * bslot_bytes;
+              const uint64_t ad0 = umma_desc_sw128(sa + (uint32_t)(fr * HALO_PW + fs) * 128u, HALO_PW * 128u);
+              const uint64_t bd0 = umma_desc<ROWB>(sbb);
+              if (p.b_taps == 3) {                            // one filter row per slot: taps are 128 B apart in the patch
+#pragma unroll
+                for (int tt = 0; tt < 3; ++tt)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(d_tmem, ad0 + (uint64_t)(tt * 8 + k * 2), bd0 + (uint64_t)(tt * (Cfg::B_STAGE_BYTES >> 4) + k * 2), idesc,
+                             (kc | tg | tt | k) ? 1u : 0u);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad0 + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 2), idesc, (kc | tg | k) ? 1u : 0u);
+              }
+              umma_commit(empty0 + 8 * (8 + bs));                       // weight slot free when these MMAs have read it
+              if (tg == tgroups - 1) {
+                umma_commit(empty0 + 8 * stage);                        // ... and so is the patch after its last tap
+                if (kc == kchunks - 1) umma_commit(tfull0 + 8 * as);    // accumulator complete
+              }
+            }
+            ready = __any_sync(0xffffffffu, probe);
+            if (p.b_taps == 3) ++fr; else if (++fs == 3) { fs = 0; ++fr; }
+            bs = nbs; bph = nbph;
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        if (++as == acc_n) { as = 0; aphase ^= 1; }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       TMR_WAIT(tmr_wait2, mbar_wait(tempty0 + 8 * as, aphase ^ 1))
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -985,6 +1070,13 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   // chunk per pixel, tile 8 x 16 x 1 image.
   p.halo = (d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && d.Cin == 64 && d.Cout == 64 && !d.pool && d.Ho >= 8 &&
             d.Wo >= 8 && !getenv("VTD_NO_HALO") && !getenv("VTD_NO_BRES")) ? 1 : 0;
+  // any other 3x3 s1 p1 layer whose maps tile into 8 x 16 pixels with little waste: halo mode with streamed weights (2)
+  if (!p.halo && d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && !d.pool && !getenv("VTD_NO_HALO")) {
+    const long long covered = (long long)((d.Wo + 7) / 8 * 8) * ((d.Ho + 15) / 16 * 16);
+    int mask = 3;                                         // bit 0: N = 128 layers, bit 1: N = 256 layers
+    if (const char* e = getenv("VTD_HALO2")) mask = atoi(e);
+    if (covered * 100 <= (long long)d.Wo * d.Ho * 108 && ((bn == 128 && (mask & 1)) || (bn == 256 && (mask & 2)))) p.halo = 2;
+  }
   if (p.halo) {
     p.lw = 3; p.lh = 4;
     p.tiles_x = (d.Wo + 7) / 8; p.tiles_y = (d.Ho + 15) / 16; p.tiles_n = d.N;
@@ -992,6 +1084,18 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
     CUresult hr = encode_act4d(enc, &pl->maps.a[1], d.in, d.Cin, d.W, d.H, d.N, d.Cin, (long long)d.W * d.Cin,
                                (long long)d.H * d.W * d.Cin, HALO_PW, HALO_PH, 1);
     if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(halo patch) failed: " + std::to_string((int)hr)); }
+    if (p.halo == 2) {
+      p.b_taps = bn <= 128 ? 3 : 1;
+      const long long K = 9LL * d.Cin;
+      cuuint64_t dims[4] = {64, (cuuint64_t)d.Cout, (cuuint64_t)(d.Cin / 64), 9};
+      cuuint64_t strides[3] = {(cuuint64_t)K * 2, 128, (cuuint64_t)d.Cin * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)bn, 1, (cuuint32_t)p.b_taps};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      hr = enc(&pl->maps.b4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.w), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights by tap) failed: " + std::to_string((int)hr)); }
+    }
   }
   const int bw = 1 << p.lw, bh = 1 << p.lh, bnn = 128 >> (p.lw + p.lh);
   const int nmaps = d.stride == 1 ? 1 : 4;
@@ -1134,6 +1238,33 @@ static void plan_smem(TcPlan* pl) {
   const bool can_res = (MODE == MODE_CONV || MODE == MODE_WIN) && p.n_blocks == 1 && bres_bytes <= 96 * 1024 &&
                        !getenv("VTD_NO_BRES");
   p.bres = can_res ? 1 : 0;
+  if (MODE == MODE_CONV && p.halo == 2) {
+    // patch ring (2 slots: a patch lasts 36 MMAs, one ahead is enough) + weight ring (what is left, 2..8 slots of b_taps
+    // taps) + store staging
+    p.bres = 0; p.kps = 1; p.res_tma = 0;
+    const int stg = NUM_EPI_WARPS * 4096;
+    const int bslot = p.b_taps * Cfg::B_STAGE_BYTES;
+    const int fixed = 1024 + Cfg::TAIL_BYTES;
+    p.stages = 2;
+    p.epi_tma = (p.out_f32 && p.res_mode != RES_NONE) || getenv("VTD_NO_TMA_STORE") ? 0 : 1;
+    int bst = (SMEM_TOTAL - fixed - p.stages * HALO_SLOT - (p.epi_tma ? stg : 0)) / bslot;
+    if (bst < 3 && p.epi_tma && BN == 256) { p.epi_tma = 0; bst = (SMEM_TOTAL - fixed - p.stages * HALO_SLOT) / bslot; }
+    if (bst > 8) bst = 8;
+    if (bst < 2) { p.halo = 0; }                          // (cannot happen for N <= 256)
+    else {
+      p.b_stages = bst;
+      // the residual by TMA as well when its staging still fits
+      if (p.epi_tma && p.res_mode != RES_NONE && !getenv("VTD_NO_TMA_RES") &&
+          (SMEM_TOTAL - fixed - p.stages * HALO_SLOT - 2 * stg) / bslot >= 2) {
+        p.res_tma = 1;
+        p.b_stages = (SMEM_TOTAL - fixed - p.stages * HALO_SLOT - 2 * stg) / bslot;
+        if (p.b_stages > 8) p.b_stages = 8;
+      }
+      p.dbg = 0;
+      pl->smem = p.stages * HALO_SLOT + p.b_stages * bslot + (p.epi_tma ? stg : 0) + (p.res_tma ? stg : 0) + fixed;
+      return;
+    }
+  }
   const int step_bytes = p.bres ? Cfg::A_BYTES : Cfg::STAGE_BYTES;
   // K steps per ring slot.  A slot handshake costs ~300-500 cycles in the two role warps; the MMAs of one K step take
   // 4 x max(32, N/2) cycles.  N = 256 hides it with one step per slot; narrower tiles batch up to 3 steps (a divisor of
