@@ -1075,7 +1075,8 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
     const long long covered = (long long)((d.Wo + 7) / 8 * 8) * ((d.Ho + 15) / 16 * 16);
     int mask = 3;                                         // bit 0: N = 128 layers, bit 1: N = 256 layers
     if (const char* e = getenv("VTD_HALO2")) mask = atoi(e);
-    if (covered * 100 <= (long long)d.Wo * d.Ho * 108 && ((bn == 128 && (mask & 1)) || (bn == 256 && (mask & 2)))) p.halo = 2;
+    const int waste = getenv("VTD_HALO_WASTE") ? atoi(getenv("VTD_HALO_WASTE")) : 13;   // percent of padded pixels tolerated
+    if (covered * 100 <= (long long)d.Wo * d.Ho * (100 + waste) && ((bn == 128 && (mask & 1)) || (bn == 256 && (mask & 2)))) p.halo = 2;
   }
   if (p.halo) {
     p.lw = 3; p.lh = 4;
