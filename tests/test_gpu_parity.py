@@ -142,6 +142,27 @@ def test_conv_tcgen05_matches_cuda_core_path(E, port):
     assert np.abs(t32 - t16).max() <= 1e-2
 
 
+def test_halo_and_direct_window_layers_vs_oracle(E, port):
+    """bf16 tier at a size where the one-patch-per-tile ("halo") convolutions and the direct-window stem are the ones
+    that run: 352x1024 -> stem output 176x512 (four full 128-pixel tiles per row), layer1 / FPN maps 88x256 (8x16 tiles
+    with a padded last tile row: 88 = 5.5 x 16), layer2 44x128.  Oracle: the reference's modules on the same input."""
+    net = port.build_dbnet("resnet18", seed=3)
+    h, w = 352, 1024
+    frames = port.synthetic_frames(2, 396, 1152, seed=6)
+    x = torch.cat([port.preprocess(f, h, w) for f in frames])
+    eng = E.Engine(backbone=18, det_h=h, det_w=w, max_batch=2, dtype="bf16")
+    eng.load_detector(net.state_dict())
+    p, t = eng.dbnet_forward(x.numpy())
+    with torch.no_grad():
+        ref = port.dbnet_forward(net, x, return_feats=True)
+    for name in ("c2", "c3", "p2"):
+        got, want = eng.debug_tensor(name, 2), ref[name].numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 0.03 * np.abs(want).max(), name
+    assert np.abs(p - ref["probability"].numpy()).max() <= 1e-2
+    assert np.abs(t - ref["threshold"].numpy()).max() <= 1e-2
+
+
 def test_logit_bias_plants_boxes(E, port):
     net = port.build_dbnet("resnet18", seed=0)
     h, w = 256, 1280
