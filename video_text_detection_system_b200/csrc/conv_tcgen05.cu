@@ -85,6 +85,7 @@ struct TcParams {
   int res_bytes;              // bytes of one residual box
   int halo;                   // 1 = 3x3 s1 p1 conv read from ONE halo patch per tile and 64-channel chunk: tile 8 x 16 px, patch 10 x 18 px
                               //     (SWIZZLE_128B as TMA stores it); the 9 taps are 9 descriptor start addresses (row shifts)
+  int cta2;                   // halo == 2 on CTA pairs (conv_tc2_kernel): tcgen05.mma.cta_group::2, each CTA streams half of the weights
   int b_stages, b_taps;       // halo == 2 (weights streamed): second ring of b_stages slots, each b_taps taps of one 64-channel chunk
   int kps;                    // K steps per ring slot: one full/empty handshake (and one tcgen05.commit) per kps steps
   long long* timers;          // VTD_TIMERS builds: [grid][3 roles][total, wait, wait2] cycles
@@ -924,6 +925,208 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   }
 }
 
+
+// ---- CTA-pair variant of the halo convolution (3x3 s1 p1, streamed weights, n_blocks == 1) -------------------------------
+// The single-CTA N = 128 / N = 256 tiles are bound by shared-memory bandwidth: per SS-form MMA the tensor core reads A (4 KB)
+// and B (N x 32 B) from shared memory while TMA writes the same slabs in (profiles/r01_ncu_notes.md, finding 9).  With
+// tcgen05.mma.cta_group::2 a cluster of two CTAs computes TWO spatial tiles (one per CTA: its own patch, its own 128 TMEM
+// lanes) against ONE copy of the weights split between them: CTA r streams and keeps rows r*N/2.. of every weight slab,
+// the tensor cores of both SMs read both halves.  Weight bytes written and read per SM halve.  (profiles/micro/umma_2cta.cu
+// checks the operand placement.)  Roles per CTA: warp 0 TMA producer (own patch + own weight half; every load completes
+// on the LEADER's full barrier), warp 1 MMA issuer (leader only; commits are multicast to both CTAs' empty / tfull
+// barriers), warps 2..9 epilogue (own TMEM; arrive on the leader's tempty).
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {          // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int HALF_N = BLOCK_N / 2;
+  constexpr int BSLAB = HALF_N * 128;                    // one tap of this CTA's weight half
+  constexpr int ACC = 512 / BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t ring = (raw + 1023u) & ~1023u;
+  uint8_t* ring_ptr = smem_raw + (ring - raw);
+  const int a_st = p.stages, b_st = p.b_stages, taps = p.b_taps;
+  const uint32_t bslot = (uint32_t)taps * BSLAB;
+  const uint32_t bring = ring + a_st * HALO_SLOT;
+  const uint32_t stg0 = bring + b_st * bslot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (stg0 - ring) + NUM_EPI_WARPS * 4096);
+  const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * 4, bfull0 = aempty0 + 8 * 4, bempty0 = bfull0 + 8 * 8;
+  const uint32_t tfull0 = bempty0 + 8 * 8, tempty0 = tfull0 + 8 * 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < a_st; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
+    for (int i = 0; i < b_st; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1); }
+    for (int i = 0; i < ACC; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * NUM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[1]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b4) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.o) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // both CTAs' barriers exist before anyone signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kchunks = p.Cin / BLOCK_K;
+  const int tgroups = 9 / taps;
+  const int total_tiles = p.total_tiles;
+  const int npairs = (total_tiles + 1) >> 1;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  auto my_tile = [&](int pair) { const int t = 2 * pair + (int)rank; return t < total_tiles ? t : total_tiles - 1; };   // odd tail: the peer repeats the last tile
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int as_ = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+    for (int pair = cluster_id; pair < npairs; pair += nclusters) {
+      int t = my_tile(pair);
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int x0 = tx * 8, y0 = ty * 16, n0 = t;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(aempty0 + 8 * as_, aph ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(afull0 + 8 * as_, 2u * HALO_BYTES);          // both CTAs' patches complete on the leader's barrier
+          tma_load_4d_2sm(ring + as_ * HALO_SLOT, &maps.a[1], afull0 + 8 * as_, kc * BLOCK_K, x0 - 1, y0 - 1, n0);
+        }
+        __syncwarp();
+        if (++as_ == a_st) { as_ = 0; aph ^= 1; }
+        for (int tg = 0; tg < tgroups; ++tg) {
+          mbar_wait(bempty0 + 8 * bs, bph ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(bfull0 + 8 * bs, 2u * bslot);
+            tma_load_4d_2sm(bring + bs * bslot, &maps.b4, bfull0 + 8 * bs, 0, (int)rank * HALF_N, kc, tg * taps);
+          }
+          __syncwarp();
+          if (++bs == b_st) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int as_ = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t accph = 0;
+      for (int pair = cluster_id; pair < npairs; pair += nclusters) {
+        mbar_wait(tempty0 + 8 * acc, accph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(afull0 + 8 * as_, aph);
+          const uint32_t sa = ring + as_ * HALO_SLOT;
+          int fr = 0, fs = 0;
+          for (int tg = 0; tg < tgroups; ++tg) {
+            mbar_wait(bfull0 + 8 * bs, bph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint64_t ad0 = umma_desc_sw128(sa + (uint32_t)(fr * HALO_PW + fs) * 128u, HALO_PW * 128u);
+              const uint64_t bd0 = umma_desc<128>(bring + bs * bslot);
+              for (int tt = 0; tt < taps; ++tt)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_2sm(d_tmem, ad0 + (uint64_t)(tt * 8 + k * 2), bd0 + (uint64_t)(tt * (BSLAB >> 4) + k * 2), idesc,
+                               (kc | tg | tt | k) ? 1u : 0u);
+              umma_commit_2sm(bempty0 + 8 * bs);
+              if (tg == tgroups - 1) {
+                umma_commit_2sm(aempty0 + 8 * as_);
+                if (kc == kchunks - 1) umma_commit_2sm(tfull0 + 8 * acc);
+              }
+            }
+            __syncwarp();
+            if (taps == 3) ++fr; else if (++fs == 3) { fs = 0; ++fr; }
+            if (++bs == b_st) { bs = 0; bph ^= 1; }
+          }
+          if (++as_ == a_st) { as_ = 0; aph ^= 1; }
+        }
+        if (++acc == ACC) { acc = 0; accph ^= 1; }
+      }
+    }
+  } else if (warp < 2 + NUM_EPI_WARPS) {
+    // ===================== epilogue =====================
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const int xx = m & 7, yy = (m >> 3) & 15;
+    const int groups = BLOCK_N * 2 / 128;
+    const int g0 = half * (groups / 2), g1 = g0 + groups / 2;
+    const bool use_res = p.res_mode != RES_NONE;
+    const uint32_t stg = stg0 + (uint32_t)(warp - 2) * 4096u;
+    const int m0 = q * 32;
+    uint32_t tempty_leader;                              // the leader's tempty barrier, cluster address (own when rank == 0)
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(tempty_leader) : "r"(tempty0), "r"(0u));
+    int acc = 0; uint32_t accph = 0;
+    for (int pair = cluster_id; pair < npairs; pair += nclusters) {
+      int t = my_tile(pair);
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int ox = tx * 8 + xx, oy = ty * 16 + yy, n = t;
+      const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BLOCK_N);
+      mbar_wait(tfull0 + 8 * acc, accph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int g = g0; g < g1; ++g) {
+        uint4 rv[8];
+        if (use_res) {
+          if (valid) {
+            const size_t rpix = p.res_mode == RES_SAME ? ((size_t)n * p.Ho + oy) * p.Wo + ox
+                                                       : ((size_t)n * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + g * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = __ldg(rp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, 0u, tmem_acc, q, lane, g, use_res, rv, 0, tx * 8 + (m0 & 7),
+                                    ty * 16 + ((m0 >> 3) & 15), t);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader + 8 * acc) : "memory");
+      if (++acc == ACC) { acc = 0; accph ^= 1; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // nobody exits while the peer may still address its memory
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 
 // tile shape: BN x BH x BW = 128, all powers of two, least padding; ties prefer wider rows
@@ -1086,11 +1289,14 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
                                (long long)d.H * d.W * d.Cin, HALO_PW, HALO_PH, 1);
     if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(halo patch) failed: " + std::to_string((int)hr)); }
     if (p.halo == 2) {
-      p.b_taps = bn <= 128 ? 3 : 1;
+      int cmask = 3;                                      // CTA pairs: bit 0 N = 128 layers, bit 1 N = 256 layers
+      if (const char* e = getenv("VTD_CTA2")) cmask = atoi(e);
+      p.cta2 = (p.n_blocks == 1 && !d.out_f32 && p.total_tiles >= 2 && ((bn == 128 && (cmask & 1)) || (bn == 256 && (cmask & 2)))) ? 1 : 0;
+      p.b_taps = (bn <= 128 || p.cta2) ? 3 : 1;
       const long long K = 9LL * d.Cin;
       cuuint64_t dims[4] = {64, (cuuint64_t)d.Cout, (cuuint64_t)(d.Cin / 64), 9};
       cuuint64_t strides[3] = {(cuuint64_t)K * 2, 128, (cuuint64_t)d.Cin * 2};
-      cuuint32_t box[4] = {64, (cuuint32_t)bn, 1, (cuuint32_t)p.b_taps};
+      cuuint32_t box[4] = {64, (cuuint32_t)(p.cta2 ? bn / 2 : bn), 1, (cuuint32_t)p.b_taps};
       cuuint32_t es[4] = {1, 1, 1, 1};
       hr = enc(&pl->maps.b4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.w), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1243,6 +1449,16 @@ static void plan_smem(TcPlan* pl) {
     // patch ring (2 slots: a patch lasts 36 MMAs, one ahead is enough) + weight ring (what is left, 2..8 slots of b_taps
     // taps) + store staging
     p.bres = 0; p.kps = 1; p.res_tma = 0;
+    if (p.cta2) {                                         // conv_tc2_kernel: patch ring (2) + this CTA's weight halves + staging
+      const int bslot2 = p.b_taps * (BN / 2) * 128;
+      const int fixed2 = 1024 + 512;
+      p.stages = 2; p.epi_tma = 1;
+      int bst = (SMEM_TOTAL - fixed2 - p.stages * HALO_SLOT - NUM_EPI_WARPS * 4096) / bslot2;
+      p.b_stages = bst > 8 ? 8 : bst;
+      p.dbg = 0;
+      pl->smem = p.stages * HALO_SLOT + p.b_stages * bslot2 + NUM_EPI_WARPS * 4096 + fixed2;
+      return;
+    }
     const int stg = NUM_EPI_WARPS * 4096;
     const int bslot = p.b_taps * Cfg::B_STAGE_BYTES;
     const int fixed = 1024 + Cfg::TAIL_BYTES;
@@ -1383,6 +1599,22 @@ cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchC
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
   NoExtra none{0};
   cudaError_t e;
+  if (pl->mode == MODE_CONV && p.cta2) {
+    static bool attr2_done[2] = {false, false};
+    const int which = pl->block_n == 256 ? 1 : 0;
+    if (!attr2_done[which]) {
+      cudaError_t ae = which ? cudaFuncSetAttribute(conv_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                             : cudaFuncSetAttribute(conv_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (ae != cudaSuccess) return ae;
+      attr2_done[which] = true;
+    }
+    const int pairs = (p.total_tiles + 1) / 2;
+    const int clusters = pairs < sm_count() / 2 ? pairs : sm_count() / 2;
+    if (which) conv_tc2_kernel<256><<<2 * clusters, NUM_THREADS, pl->smem, s>>>(pl->maps, p);
+    else conv_tc2_kernel<128><<<2 * clusters, NUM_THREADS, pl->smem, s>>>(pl->maps, p);
+    if (lc) lc->n++;
+    return cudaGetLastError();
+  }
   const int key = pl->mode == MODE_WIN ? 1000 + p.kps : pl->block_n * 10 + p.kps;
   switch (key) {                                  // the (tile width, K steps per slot) pairs plan_smem() can pick
     case 1007: e = launch_tc<64, MODE_WIN, 7>(pl, p, none, s); break;
