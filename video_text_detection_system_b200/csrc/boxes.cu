@@ -249,6 +249,9 @@ struct GeoParams {
 // trips; per-row extremes come from the label plane in parallel (lanes stride over x); lane 0 then runs the hull /
 // rotating-calipers arithmetic (O(#rows), scratch in shared memory), and the whole warp reduces the mean
 // probability of the resulting box.  Components too large for the per-warp budget fall back to global scratch.
+#ifdef VTD_TIMERS
+__device__ int getenv_timers = 1;
+#endif
 constexpr int GW = 4;                    // candidates (warps) per CTA
 constexpr int GSMEM = 16 * 1024;         // shared-memory bytes per candidate
 
@@ -262,8 +265,12 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.y;
   const int nc = min(cd.count[f], cd.kc);
-  const int c = blockIdx.x * GW + warp;
-  if (c >= nc) return;
+  // a fixed, small grid walks the candidate list (the capacity is 1024 per plane, a frame has ~50: one CTA per
+  // capacity slot spent most of the kernel scheduling 4096 CTAs of 64 KB that exit at once)
+  for (int c = blockIdx.x * GW + warp; c < nc; c += gridDim.x * GW) {
+#ifdef VTD_TIMERS
+  const long long gt0 = clock64(); long long gt1 = 0, gt2 = 0, gt3 = 0, gt4 = 0, gt5 = 0;
+#endif
   TmpBox& tb = tmp[(size_t)f * cd.kc + c];
   if (lane == 0) tb.valid = 0;
   const int s = cd.slot[(size_t)f * cd.kc + c];
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
     int off = 0;
     if (lane == 0) off = atomicAdd(pool_used + f, scratch_words);
     off = __shfl_sync(0xffffffffu, off, 0);
-    if (off + scratch_words > gp.pool_words) { if (lane == 0) atomicExch(overflow, 1); return; }
+    if (off + scratch_words > gp.pool_words) { if (lane == 0) atomicExch(overflow, 1); continue; }
     scr = pool + (size_t)f * gp.pool_words + off;
   }
   int* rowmin = scr;
@@ -343,6 +350,9 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   }
   __syncwarp();
 
+#ifdef VTD_TIMERS
+  gt1 = clock64();
+#endif
   int ok = 0;
   if (lane == 0) {
     do {
@@ -353,11 +363,20 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
       const long long max_steps = 8LL * mw * mh;
       long long area2 = use_smem ? trace_outer_area2(fg_s, x0, y0, max_steps, nullptr)
                                  : trace_outer_area2(fg_g, x0, y0, max_steps, nullptr);
+#ifdef VTD_TIMERS
+      gt2 = clock64();
+#endif
       if (area2 < 0) area2 = -area2;
       if (area2 < 200) break;                  // cv2.contourArea(contour) < 100 -> skip (text_detector.py:150)
       int nh = hull_from_rows(rowmin, rowmax, y0, nrows, hull);
+#ifdef VTD_TIMERS
+      gt3 = clock64();
+#endif
       if (nh < 3) break;
       RotRect rr = min_area_rect(hull, nh, fl, fl + nh, fl + 2 * nh);
+#ifdef VTD_TIMERS
+      gt4 = clock64();
+#endif
       unclip_rect(rr, gp.unclip);
       PtF bp[4];
       box_points(rr, bp);
@@ -387,7 +406,7 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
     } while (false);
   }
   ok = __shfl_sync(0xffffffffu, ok, 0);
-  if (!ok) return;
+  if (!ok) continue;
   // mean probability inside the box (np.mean of the slice; empty slice -> nan)
   const int cy0 = __shfl_sync(0xffffffffu, tb.cy0, 0), cy1 = __shfl_sync(0xffffffffu, tb.cy1, 0);
   const int cx0 = __shfl_sync(0xffffffffu, tb.cx0, 0), cx1 = __shfl_sync(0xffffffffu, tb.cx1, 0);
@@ -414,7 +433,15 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     res = (float)(acc / ((double)h * (double)w));
   }
+#ifdef VTD_TIMERS
+  gt5 = clock64();
+  if (lane == 0 && f == 0 && c < 2 && getenv_timers)
+    printf("GEOM c=%d rw=%d rh=%d nrows=%d | stage+extremes %lld trace %lld hull %lld calipers %lld rest+conf %lld total %lld\n", c, rw, rh,
+           nrows, gt1 - gt0, gt2 - gt1, gt3 - gt2, gt4 - gt3, gt5 - gt4, gt5 - gt0);
+#endif
   if (lane == 0) { tb.conf = res; __threadfence_block(); tb.valid = 1; }
+  __syncwarp();
+  }
 }
 
 // ---- 10. order by raster start, keep kmax, write records.  One CTA per plane.
@@ -526,7 +553,7 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
     if (ge != cudaSuccess) return ge;
     geo_attr = true;
   }
-  geometry_kernel<<<dim3(cdiv(lay.kc, GW), n), GW * 32, GW * GSMEM, s>>>(mask, labels, prob, ca, cd, gp, pool, pool_used,
+  geometry_kernel<<<dim3(min(cdiv(lay.kc, GW), 32), n), GW * 32, GW * GSMEM, s>>>(mask, labels, prob, ca, cd, gp, pool, pool_used,
                                                                         tmp, overflow);
   pack_kernel<<<n, 256, 0, s>>>(cd, tmp, reinterpret_cast<vtd_record*>(records), counts, p.kmax, overflow);
   if (lc) lc->n += (mh > 1 ? 9 : 8);
