@@ -1127,6 +1127,186 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
 }
 
+
+// ---- CTA-pair variant of the GENERAL implicit-GEMM convolution (N = 256 tiles, streamed weights) -----------------------------
+// Same idea as conv_tc2_kernel for the layers that cannot run in halo mode (CRNN 8x32 / 4x32 maps, stride-2 and 1x1 layers,
+// the LSTM input projections): per K step every CTA loads the tap-shifted box of ITS tile (16 KB) and ITS half of the
+// weight slab (128 rows, 16 KB); one tcgen05.mma.cta_group::2 stream of the leader multiplies both tiles.  Tiles of a pair
+// share the N block.
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_tc2g_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+  constexpr int BLOCK_N = 256, HALF_N = 128;
+  constexpr int A_BYTES = BLOCK_M * 128, BH_BYTES = HALF_N * 128, SLOT = A_BYTES + BH_BYTES;
+  constexpr int ACC = 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t ring = (raw + 1023u) & ~1023u;
+  uint8_t* ring_ptr = smem_raw + (ring - raw);
+  const int stages = p.stages;
+  const uint32_t stg0 = ring + stages * SLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (stg0 - ring) + NUM_EPI_WARPS * 4096);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * 8, tfull0 = empty0 + 8 * 8, tempty0 = tfull0 + 8 * 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < ACC; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * NUM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b4) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.o) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int BW = 1 << p.lw, BH = 1 << p.lh;
+  const int BNt = BLOCK_M >> (p.lw + p.lh);
+  const int kchunks = p.Cin / BLOCK_K;
+  const int ksteps = p.KH * p.KW * kchunks;
+  const int spatial = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int spairs = (spatial + 1) >> 1;
+  const int npairs = spairs * p.n_blocks;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  // pair -> (N block, this CTA's spatial tile); the peer of an odd tail repeats the last tile
+  auto decode = [&](int pair, int& nb, int& tx, int& ty, int& tn) {
+    nb = pair % p.n_blocks;
+    int t = 2 * (pair / p.n_blocks) + (int)rank;
+    if (t >= spatial) t = spatial - 1;
+    tx = t % p.tiles_x; t /= p.tiles_x;
+    ty = t % p.tiles_y; tn = t / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int pair = cluster_id; pair < npairs; pair += nclusters) {
+      int nb, tx, ty, tn;
+      decode(pair, nb, tx, ty, tn);
+      const int x0 = tx * BW, y0 = ty * BH, n0 = tn * BNt;
+      for (int r = 0; r < p.KH; ++r)
+        for (int sx = 0; sx < p.KW; ++sx) {
+          int mi = 0, xo, yo;
+          if (p.stride == 1) { xo = sx - p.pad; yo = r - p.pad; }
+          else {
+            const int tyy = r - p.pad, txx = sx - p.pad;
+            const int py = tyy & 1, px = txx & 1;
+            mi = py * 2 + px; yo = (tyy - py) / 2; xo = (txx - px) / 2;
+          }
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            if (elect_one()) {
+              const uint32_t sa = ring + stage * SLOT, fb = full0 + 8 * stage;
+              if (rank == 0) mbar_expect_tx(fb, 2u * SLOT);
+              tma_load_4d_2sm(sa, &maps.a[mi], fb, kc * BLOCK_K, x0 + xo, y0 + yo, n0);
+              tma_load_2d_2sm(sa + A_BYTES, &maps.b4, fb, (r * p.KW + sx) * p.Cin + kc * BLOCK_K, nb * BLOCK_N + (int)rank * HALF_N);
+            }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accph = 0;
+      bool ready = false;
+      for (int pair = cluster_id; pair < npairs; pair += nclusters) {
+        mbar_wait(tempty0 + 8 * acc, accph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          if (!ready) mbar_wait(full0 + 8 * stage, phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int nstage = stage + 1 == stages ? 0 : stage + 1;
+          const uint32_t nphase = stage + 1 == stages ? phase ^ 1 : phase;
+          const bool probe = mbar_test(full0 + 8 * nstage, nphase);
+          if (elect_one()) {
+            const uint32_t sa = ring + stage * SLOT;
+            const uint64_t ad = umma_desc<128>(sa), bd = umma_desc<128>(sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_2sm(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ks | k) ? 1u : 0u);
+            umma_commit_2sm(empty0 + 8 * stage);
+            if (ks == ksteps - 1) umma_commit_2sm(tfull0 + 8 * acc);
+          }
+          ready = __any_sync(0xffffffffu, probe);
+          stage = nstage; phase = nphase;
+        }
+        if (++acc == ACC) { acc = 0; accph ^= 1; }
+      }
+    }
+  } else if (warp < 2 + NUM_EPI_WARPS) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const int xx = m & (BW - 1), yy = (m >> p.lw) & (BH - 1), nn = m >> (p.lw + p.lh);
+    const int groups = (p.out_f32 ? BLOCK_N * 4 : BLOCK_N * 2) / 128;
+    const int gcols = p.out_f32 ? 32 : 64;
+    const int g0 = half * (groups / 2), g1 = g0 + groups / 2;
+    const bool use_res = p.res_mode != RES_NONE && !p.out_f32;
+    const uint32_t stg = stg0 + (uint32_t)(warp - 2) * 4096u;
+    const int m0 = q * 32;
+    uint32_t tempty_leader;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(tempty_leader) : "r"(tempty0), "r"(0u));
+    int acc = 0; uint32_t accph = 0;
+    for (int pair = cluster_id; pair < npairs; pair += nclusters) {
+      int nb, tx, ty, tn;
+      decode(pair, nb, tx, ty, tn);
+      const int ox = tx * BW + xx, oy = ty * BH + yy, n = tn * BNt + nn;
+      const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BLOCK_N);
+      mbar_wait(tfull0 + 8 * acc, accph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int g = g0; g < g1; ++g) {
+        uint4 rv[8];
+        if (use_res) {
+          if (valid) {
+            const size_t rpix = p.res_mode == RES_SAME ? ((size_t)n * p.Ho + oy) * p.Wo + ox
+                                                       : ((size_t)n * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + nb * BLOCK_N + g * gcols);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = __ldg(rp + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, 0u, tmem_acc, q, lane, g, use_res, rv, nb, tx * BW + (m0 & (BW - 1)),
+                                    ty * BH + ((m0 >> p.lw) & (BH - 1)), tn * BNt + (m0 >> (p.lw + p.lh)));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader + 8 * acc) : "memory");
+      if (++acc == ACC) { acc = 0; accph ^= 1; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 
 // tile shape: BN x BH x BW = 128, all powers of two, least padding; ties prefer wider rows
@@ -1315,6 +1495,14 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   }
   CUresult r = encode_weights(enc, &pl->maps.b, d.w, (long long)d.KH * d.KW * d.Cin, d.Cout, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
+  // CTA pairs for the remaining N = 256 layers with streamed weights (conv_tc2g_kernel): decided here, confirmed in plan_smem
+  if (!p.halo && bn == 256 && !d.pool && !(d.out_f32 && d.res_mode != RES_NONE) &&
+      (long long)d.KH * d.KW * (d.Cin / 64) * 256 * 128 > 96 * 1024 && p.tiles_x * p.tiles_y * p.tiles_n >= 2 &&
+      !(getenv("VTD_CTA2") && !(atoi(getenv("VTD_CTA2")) & 4))) {
+    p.cta2 = 2;
+    r = encode_weights(enc, &pl->maps.b4, d.w, (long long)d.KH * d.KW * d.Cin, d.Cout, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weight halves) failed: " + std::to_string((int)r)); }
+  }
   r = encode_out(enc, &pl->maps.o, d.out, d.out_f32, d.Cout, d.pool == 1 ? d.Wo / 2 : d.Wo, d.pool ? d.Ho / 2 : d.Ho, d.N, p.lw, p.lh, 0,
                  nullptr, d.pool);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(output) failed: " + std::to_string((int)r)); }
@@ -1445,6 +1633,14 @@ static void plan_smem(TcPlan* pl) {
   const bool can_res = (MODE == MODE_CONV || MODE == MODE_WIN) && p.n_blocks == 1 && bres_bytes <= 96 * 1024 &&
                        !getenv("VTD_NO_BRES");
   p.bres = can_res ? 1 : 0;
+  if (MODE == MODE_CONV && p.cta2 == 2) {                 // conv_tc2g_kernel: slots of A box + weight half, store staging
+    p.bres = 0; p.kps = 1; p.res_tma = 0; p.epi_tma = 1; p.dbg = 0;
+    const int slot = BLOCK_M * 128 + 128 * 128, fixed2 = 1024 + 256;
+    int st = (SMEM_TOTAL - fixed2 - NUM_EPI_WARPS * 4096) / slot;
+    p.stages = st > 8 ? 8 : st;
+    pl->smem = p.stages * slot + NUM_EPI_WARPS * 4096 + fixed2;
+    return;
+  }
   if (MODE == MODE_CONV && p.halo == 2) {
     // patch ring (2 slots: a patch lasts 36 MMAs, one ahead is enough) + weight ring (what is left, 2..8 slots of b_taps
     // taps) + store staging
@@ -1599,6 +1795,20 @@ cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchC
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
   NoExtra none{0};
   cudaError_t e;
+  if (pl->mode == MODE_CONV && p.cta2 == 2) {
+    static bool attrg_done = false;
+    if (!attrg_done) {
+      cudaError_t ae = cudaFuncSetAttribute(conv_tc2g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (ae != cudaSuccess) return ae;
+      attrg_done = true;
+    }
+    const int spatial = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int pairs = ((spatial + 1) / 2) * p.n_blocks;
+    const int clusters = pairs < sm_count() / 2 ? pairs : sm_count() / 2;
+    conv_tc2g_kernel<<<2 * clusters, NUM_THREADS, pl->smem, s>>>(pl->maps, p);
+    if (lc) lc->n++;
+    return cudaGetLastError();
+  }
   if (pl->mode == MODE_CONV && p.cta2) {
     static bool attr2_done[2] = {false, false};
     const int which = pl->block_n == 256 ? 1 : 0;
