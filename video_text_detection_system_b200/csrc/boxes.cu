@@ -86,29 +86,54 @@ __global__ void __launch_bounds__(RT) ccl_rows_kernel(const uint8_t* __restrict_
 }
 
 // ---- 2. merge runs of adjacent rows
-__global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ labels, int mh, int mw) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y + 1;
-  if (x >= mw || y >= mh) return;
-  const size_t plane = (size_t)blockIdx.z * mh * mw;
-  const uint8_t* m = mask + plane;
-  int* L = labels + plane;
-  const int i = y * mw + x;
-  const bool f = m[i] != 0;
-  const bool n = (m[i - mw] != 0);
-  const bool w = x > 0 ? (m[i - 1] != 0) : !f;              // out of frame == "other class"
-  const bool nw = x > 0 ? (m[i - mw - 1] != 0) : !f;
+// Four pixels per thread: the two mask rows come in as 32-bit words (plus the byte left and right of them), so a pixel
+// costs ~1.5 loads instead of 5; the union rules are the per-pixel ones, unchanged.
+__device__ __forceinline__ void ccl_merge_px(const uint8_t* __restrict__ m, int* L, int mw, int x, int i, bool f, bool n, bool w,
+                                             bool nw, bool ne, bool e) {
   if (f) {
     if (n) {
       if (!w || !nw) uf_union(L, i, i - mw);
     } else {
       if (x > 0 && nw && !w) uf_union(L, i, i - mw - 1);
-      if (x + 1 < mw && m[i - mw + 1] != 0 && m[i + 1] == 0) uf_union(L, i, i - mw + 1);
+      if (x + 1 < mw && ne && !e) uf_union(L, i, i - mw + 1);
     }
   } else {
     if (!n) {
       if (w || nw || x == 0) uf_union(L, i, i - mw);
     }
+  }
+}
+
+__global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ labels, int mh, int mw) {
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y + 1;
+  if (x0 >= mw || y >= mh) return;
+  const size_t plane = (size_t)blockIdx.z * mh * mw;
+  const uint8_t* m = mask + plane;
+  int* L = labels + plane;
+  const int i0 = y * mw + x0;
+  uint8_t cur[6], up[6];                                  // pixels x0-1 .. x0+4 of rows y and y-1 (out of frame: see below)
+  if ((mw & 3) == 0 && x0 + 4 <= mw) {
+    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(m + i0), u4 = *reinterpret_cast<const uint32_t*>(m + i0 - mw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { cur[k + 1] = (uint8_t)(c4 >> (8 * k)); up[k + 1] = (uint8_t)(u4 >> (8 * k)); }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool in = x0 + k < mw;
+      cur[k + 1] = in ? m[i0 + k] : 0; up[k + 1] = in ? m[i0 + k - mw] : 0;
+    }
+  }
+  cur[0] = x0 > 0 ? m[i0 - 1] : 0; up[0] = x0 > 0 ? m[i0 - mw - 1] : 0;
+  cur[5] = x0 + 4 < mw ? m[i0 + 4] : 0; up[5] = x0 + 4 < mw ? m[i0 + 4 - mw] : 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x0 + k;
+    if (x >= mw) break;
+    const bool f = cur[k + 1] != 0;
+    const bool w = x > 0 ? (cur[k] != 0) : !f;              // out of frame == "other class"
+    const bool nw = x > 0 ? (up[k] != 0) : !f;
+    ccl_merge_px(m, L, mw, x, i0 + k, f, up[k + 1] != 0, w, nw, up[k + 2] != 0, cur[k + 2] != 0);
   }
 }
 // NOTE on the foreground NE rule: when N is background and NE is foreground, pixel E (if foreground)
@@ -539,7 +564,7 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
   if ((e = cudaMemsetAsync(outside, 0, px * n, s)) != cudaSuccess) return e;
 
   ccl_rows_kernel<<<dim3(mh, n), RT, 0, s>>>(mask, labels, mh, mw);
-  if (mh > 1) ccl_merge_kernel<<<dim3(cdiv(mw, 128), mh - 1, n), 128, 0, s>>>(mask, labels, mh, mw);
+  if (mh > 1) ccl_merge_kernel<<<dim3(cdiv(cdiv(mw, 4), 128), mh - 1, n), 128, 0, s>>>(mask, labels, mh, mw);
   const int gx = min(cdiv((long long)px, 256), 148 * 8);
   ccl_flatten_plane_kernel<<<dim3(min(cdiv((long long)px / 4 + 1, 256), 148 * 8), n), 256, 0, s>>>(labels, (int)px);
   mark_outside_kernel<<<dim3(cdiv(2 * (mh + mw), 256), n), 256, 0, s>>>(mask, labels, outside, mh, mw);

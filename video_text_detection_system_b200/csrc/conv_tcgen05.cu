@@ -374,7 +374,7 @@ __device__ __forceinline__ void epilogue_dbhead(const TcParams& p, const float* 
   float o[8];                                       // [dx][(dy2,dx2)]
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = b2;
-#pragma unroll 1
+#pragma unroll 2
   for (int it = 0; it < 4; ++it) {                  // (dx, 32-channel half)
     const int dx = it >> 1, ch = it & 1;
     const int g = half * 2 + dx;
