@@ -13,14 +13,27 @@
 // (py,px), W and H strides doubled), so every tap is still a dense box.  Weights are [Cout][taps*Cin]
 // (K-major), one 2-D box {64, BLOCK_N} per stage.
 //
-// CTA = 6 warps, persistent over output tiles (static stride schedule):
-//   warp 0 lane 0 : TMA producer            (full/empty mbarrier ring of STAGES slots)
-//   warp 1        : TMEM allocator + MMA issuer: one elected lane issues tcgen05.mma 128 x BLOCK_N x 16,
-//                   accumulators in TMEM, double buffered (2 x BLOCK_N columns) so the epilogue of tile i
-//                   overlaps the MMAs of tile i+1; tcgen05.commit releases smem slots / publishes the tile
-//   warps 2..5    : epilogue: tcgen05.ld 32 lanes x 32 columns -> +bias (folded BN) -> +residual (same size,
-//                   or nearest-2x upsampled = the FPN top-down add) -> ReLU -> bf16 (or fp32) NHWC store.
-// Every mbarrier wait is bounded (clock64) and traps instead of hanging the GPU.
+// CTA = 10 warps, persistent over output tiles (static stride schedule):
+//   warp 0        : TMA producer (whole warp converged, one elected lane issues): full/empty mbarrier ring; one ring slot
+//                   holds KPS K steps (the slot hand-over costs ~500 cycles, more than the MMAs of one narrow K step)
+//   warp 1        : TMEM allocator + MMA issuer: tcgen05.mma 128 x BLOCK_N x 16, 2-4 accumulators in TMEM so the epilogue
+//                   of tile i overlaps the MMAs of tile i+1; probes the next slot (mbarrier.test_wait) before issuing;
+//                   tcgen05.commit releases smem slots / publishes the tile
+//   warps 2..9    : epilogue (two per TMEM lane quarter): tcgen05.ld -> +bias (folded BN) -> +residual (same size, or
+//                   nearest-2x upsampled = the FPN top-down add; its box arrives by TMA) -> ReLU -> bf16 / fp32 -> 4 KB
+//                   128B-swizzled staging block per warp -> cp.async.bulk.tensor store (optionally 2x2 max-pooled first).
+// Every mbarrier wait is bounded and traps instead of hanging the GPU.
+//
+// Operand delivery, by layer shape (all decided in the plan, see tc_plan_create / plan_smem):
+//   * generic           : one tap-shifted 4-D box per K step, weights streamed or resident (small K, one N block);
+//   * halo (3x3 s1 p1)  : ONE (8+2) x (16+2) pixel patch per tile and 64-channel chunk; the nine taps are nine start
+//                         addresses of a SWIZZLE_128B descriptor whose 8-row groups are 1280 B apart; weights resident
+//                         (64->64) or streamed by tap through a second ring;
+//   * direct windows    : the 7x7 s2 stem reads overlapping 64-byte windows of bulk-copied input rows through a
+//                         no-swizzle descriptor (row pitch 16 B);
+//   * CTA pairs         : conv_tc2_kernel (halo) / conv_tc2g_kernel (generic) run the N = 256 / 128 layers with streamed
+//                         weights as tcgen05.mma.cta_group::2 on clusters of two CTAs, each CTA holding half of every
+//                         weight slab (the single-CTA wide tiles are bound by shared-memory bandwidth).
 //
 // The same warp-specialised skeleton runs four modes (template parameter MODE):
 //   MODE_CONV   : the implicit-GEMM convolution described above.
