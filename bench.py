@@ -362,11 +362,12 @@ def main():
         per_launch_flops = top["gflop"] * 1e9 / top["launches"]
         per_launch_ms = top["ms"] / top["launches"]
         ach = per_launch_flops / (per_launch_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM) %dx%d %d->%d k%d" %
+        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv (CTA pairs, cta_group::2) %dx%d %d->%d k%d" %
                 (top["H"], top["W"], top["Cin"], top["Cout"], top["KH"]),
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                 "traffic": top_kernel_traffic(top),
                 "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "frac_of_burst_peak": ach / pk["tflops_burst"],
                 "ms_per_launch": per_launch_ms, "gflop_per_launch": per_launch_flops / 1e9,
                 "all_tc_convs": {"tflops": tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None,
                                  "share_of_step": tc_ms / ms_1 if ms_1 > 0 else None,
