@@ -110,8 +110,9 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
   uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + L_W_BYTES + L_A_BYTES);
   const uint32_t wfull = smem_u32(bars), tfull = wfull + 8;
   const uint32_t afree = wfull + 16;      // 4 arrivals: the MMAs of a step have completed in every CTA of the cluster
-  const uint32_t hready = wfull + 24;     // 1 arrival (own MMA thread, expect_tx 64 KB) + the st.async bytes of h_t from all 4 CTAs
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t hready = wfull + 24;     // [4], one per K-chunk = per source CTA: the chunk of h_t written by CTA kc has landed
+                                          // (own chunk: the local epilogue's arrive; a peer's: expect_tx of this MMA thread + its bulk copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x;                            // == rank in cluster: hidden units 64*jt ..
@@ -122,7 +123,7 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
     mbar_init(wfull, 1);
     mbar_init(tfull, 1);
     mbar_init(afree, 4);
-    mbar_init(hready, 2);                               // MMA thread (expect_tx of the 3 remote slices) + own epilogue (local slice)
+    for (int kc = 0; kc < 4; ++kc) mbar_init(hready + 8 * kc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_whh) : "memory");
   }
@@ -156,19 +157,27 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
     mbar_wait(wfull, 0);
     LT_DECL
     for (int s = 0; s < p.T; ++s) {
-      if (s > 0) {                                      // h_{s-1} of all 256 units (64 KB, written by st.async) has landed here
-        if (elect_one()) mbar_expect_tx(hready, 3u * (uint32_t)p.rows * 128u);
-        __syncwarp();
-        LT(lt_a, mbar_wait(hready, (uint32_t)((s - 1) & 1)))
-      }
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (elect_one()) {
+      // K-chunk kc of the A operand is the h slice of CTA kc.  The MMAs of a chunk are issued as soon as THAT chunk has
+      // landed (own chunk first), so the tensor core works while the peers' copies are still in flight.
+      if (s > 0 && elect_one()) {
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
+        for (int kc = 0; kc < 4; ++kc)
+          if (kc != jt) mbar_expect_tx(hready + 8 * kc, (uint32_t)p.rows * 128u);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kc = (jt + i) & 3;
+        if (s > 0) { LT(lt_a, mbar_wait(hready + 8 * kc, (uint32_t)((s - 1) & 1))) }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
           const uint64_t ad = umma_desc<128>(abuf + kc * (128 * 128)), bd = umma_desc<128>(wbuf + kc * (256 * 128));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_acc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (i | k) ? 1u : 0u);
         }
+        __syncwarp();
+      }
+      if (elect_one()) {
         umma_commit(tfull);                       // accumulators of this step ready (own epilogue)
         umma_commit_multicast(afree, 0xF);        // ... and this CTA no longer reads h_{s-1} (tell all four CTAs)
       }
@@ -198,7 +207,7 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
     for (int r = 0; r < 4; ++r) dst_chunk[r] = map_to_cta(own_chunk, (uint32_t)r);
     uint32_t hrdy[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) hrdy[r] = map_to_cta(hready, (uint32_t)r);
+    for (int r = 0; r < 4; ++r) hrdy[r] = map_to_cta(hready + 8 * jt, (uint32_t)r);   // "chunk jt has landed" in CTA r
     LT_DECL
     for (int s = 0; active && s < p.T; ++s) {
       const int t = dir == 0 ? s : p.T - 1 - s;
@@ -291,7 +300,7 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
             if (r != jt)
               asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                            ::"r"(dst_chunk[r]), "r"(own_chunk), "r"((uint32_t)p.rows * 128u), "r"(hrdy[r]) : "memory");
-          mbar_arrive(hready);                              // own slice is in place (release; the MMA thread's wait acquires)
+          mbar_arrive(hready + 8 * jt);                     // own slice is in place (release; the MMA thread's wait acquires)
         }
 #ifdef VTD_TIMERS
         lt_e += clock64() - lt_s0;
