@@ -157,3 +157,24 @@ def test_records_to_detections_and_vocab():
     v = port.build_vocab()
     assert _lib.ids_to_text([v["0"], v["z"], v[" "], v["~"]]) == "0z ~"
     assert _lib.ids_to_text([0, 96, 200]) == ""
+
+
+def test_frame_pointer_tables_bgr_and_nv12():
+    """Host-side argument checking of the batch entry points (no GPU): BGR frames are HxWx3, NV12 frames (H*3/2)xW planes
+    with even H and W; mixed sizes in one batch are refused."""
+    import numpy as np
+    import pytest
+    from video_text_detection_system_b200 import _lib
+    bgr = [np.zeros((36, 64, 3), np.uint8), np.zeros((36, 64, 3), np.uint8)]
+    ptrs, h, w, pitch, keep = _lib.Engine._frame_ptrs(bgr)
+    assert (h, w, pitch) == (36, 64, 192) and len(keep) == 2 and ptrs[0] == bgr[0].ctypes.data
+    nv12 = [np.zeros((54, 64), np.uint8), np.zeros((54, 64), np.uint8)]
+    ptrs, h, w, pitch, keep = _lib.Engine._frame_ptrs(nv12, _lib.VTD_PIX_NV12)
+    assert (h, w, pitch) == (36, 64, 64)
+    with pytest.raises(ValueError):
+        _lib.Engine._frame_ptrs([np.zeros((54, 64, 3), np.uint8)], _lib.VTD_PIX_NV12)      # not a plane
+    with pytest.raises(ValueError):
+        _lib.Engine._frame_ptrs([np.zeros((53, 64), np.uint8)], _lib.VTD_PIX_NV12)         # rows not a multiple of 3
+    with pytest.raises(ValueError):
+        _lib.Engine._frame_ptrs([bgr[0], np.zeros((40, 64, 3), np.uint8)])                  # mixed sizes
+    assert _lib.STAGE_NAMES[4] == "lstm0" and len(_lib.STAGE_NAMES) == 7
