@@ -1164,7 +1164,7 @@ conv_tc2g_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   uint8_t* ring_ptr = smem_raw + (ring - raw);
   const int stages = p.stages;
   const uint32_t stg0 = ring + stages * SLOT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (stg0 - ring) + NUM_EPI_WARPS * 4096);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (stg0 - ring) + NUM_EPI_WARPS * 4096 + (p.pool ? NUM_EPI_WARPS * 2048 : 0));
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * 8, tfull0 = empty0 + 8 * 8, tempty0 = tfull0 + 8 * 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1298,8 +1298,9 @@ conv_tc2g_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int j = 0; j < 8; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
           }
         }
-        epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, 0u, tmem_acc, q, lane, g, use_res, rv, nb, tx * BW + (m0 & (BW - 1)),
-                                    ty * BH + ((m0 >> p.lw) & (BH - 1)), tn * BNt + (m0 >> (p.lw + p.lh)));
+        epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, stg0 + (uint32_t)NUM_EPI_WARPS * 4096u + (uint32_t)(warp - 2) * 2048u, tmem_acc, q,
+                                    lane, g, use_res, rv, nb, tx * BW + (m0 & (BW - 1)), ty * BH + ((m0 >> p.lw) & (BH - 1)),
+                                    tn * BNt + (m0 >> (p.lw + p.lh)));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -1509,7 +1510,7 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   CUresult r = encode_weights(enc, &pl->maps.b, d.w, (long long)d.KH * d.KW * d.Cin, d.Cout, 64, bn, CU_TENSOR_MAP_SWIZZLE_128B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); }
   // CTA pairs for the remaining N = 256 layers with streamed weights (conv_tc2g_kernel): decided here, confirmed in plan_smem
-  if (!p.halo && bn == 256 && !d.pool && !(d.out_f32 && d.res_mode != RES_NONE) &&
+  if (!p.halo && bn == 256 && !(d.out_f32 && d.res_mode != RES_NONE) &&
       (long long)d.KH * d.KW * (d.Cin / 64) * 256 * 128 > 96 * 1024 && p.tiles_x * p.tiles_y * p.tiles_n >= 2 &&
       !(getenv("VTD_CTA2") && !(atoi(getenv("VTD_CTA2")) & 4))) {
     p.cta2 = 2;
@@ -1649,9 +1650,10 @@ static void plan_smem(TcPlan* pl) {
   if (MODE == MODE_CONV && p.cta2 == 2) {                 // conv_tc2g_kernel: slots of A box + weight half, store staging
     p.bres = 0; p.kps = 1; p.res_tma = 0; p.epi_tma = 1; p.dbg = 0;
     const int slot = BLOCK_M * 128 + 128 * 128, fixed2 = 1024 + 256;
-    int st = (SMEM_TOTAL - fixed2 - NUM_EPI_WARPS * 4096) / slot;
+    const int stg2 = NUM_EPI_WARPS * 4096 + (p.pool ? NUM_EPI_WARPS * 2048 : 0);      // + pooled-box staging
+    int st = (SMEM_TOTAL - fixed2 - stg2) / slot;
     p.stages = st > 8 ? 8 : st;
-    pl->smem = p.stages * slot + NUM_EPI_WARPS * 4096 + fixed2;
+    pl->smem = p.stages * slot + stg2 + fixed2;
     return;
   }
   if (MODE == MODE_CONV && p.halo == 2) {
