@@ -43,29 +43,33 @@ struct PtF { float x, y; };
 // order cv::findContours visits it, and returns twice the signed shoelace area of the polygon
 // through the visited pixel centres (cv::contourArea = |area2|/2).  Fg(x,y) must return false
 // outside the image.  steps_out (optional) receives the number of border steps.
+// The 8 directions (E, NE, N, NW, W, SW, S, SE) as packed 2-bit fields (value + 1): no table in local memory on the
+// device, where this loop is one lane's dependent chain.
+VTD_HD int trace_dx(int s) { return (int)((0x901Au >> (2 * (s & 7))) & 3u) - 1; }   // {1,1,0,-1,-1,-1,0,1}
+VTD_HD int trace_dy(int s) { return (int)((0xA901u >> (2 * (s & 7))) & 3u) - 1; }   // {0,-1,-1,-1,0,1,1,1}
+
 template <class Fg>
 VTD_HD long long trace_outer_area2(const Fg& fg, int x0, int y0, long long max_steps, long long* steps_out) {
-  const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-  const int dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
   int s = 4, s_end = 4;
   int x1 = x0, y1 = y0;
   do {
     s = (s - 1) & 7;
-    x1 = x0 + dx[s]; y1 = y0 + dy[s];
+    x1 = x0 + trace_dx(s); y1 = y0 + trace_dy(s);
   } while (!fg(x1, y1) && s != s_end);
   if (steps_out) *steps_out = 0;
   if (s == s_end) return 0;                 // isolated pixel
   long long area2 = 0, steps = 0;
   int x3 = x0, y3 = y0;
   for (;;) {
-    int x4, y4;
+    int ddx, ddy;
     for (;;) {
       ++s;
-      x4 = x3 + dx[s & 7]; y4 = y3 + dy[s & 7];
-      if (fg(x4, y4)) break;
+      ddx = trace_dx(s); ddy = trace_dy(s);
+      if (fg(x3 + ddx, y3 + ddy)) break;
     }
     s &= 7;
-    area2 += (long long)x3 * y4 - (long long)x4 * y3;
+    const int x4 = x3 + ddx, y4 = y3 + ddy;
+    area2 += (long long)(x3 * ddy - ddx * y3);          // == x3*y4 - x4*y3 (consecutive border pixels are 8-neighbours)
     ++steps;
     if ((x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) || steps >= max_steps) break;
     x3 = x4; y3 = y4;
