@@ -55,11 +55,12 @@ def top_kernel_traffic(op):
     try:
         d = json.load(open(p))
         if (op["H"], op["W"], op["Cin"], op["Cout"], op["KH"]) == (184, 328, 256, 256, 3):
-            return {"bytes_per_launch": d["dram_bytes_per_launch"], "algorithmic_bytes_per_launch":
-                    d["algorithmic_bytes_per_launch"], "source": "profiles/r01_top_kernel_ncu.json"}
+            return float(d["dram_bytes_per_launch"]), {"algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"],
+                                                       "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                                                       "source": "profiles/r01_top_kernel_ncu.json"}
     except Exception:
         pass
-    return None
+    return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -365,7 +366,7 @@ def main():
         roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM conv (CTA pairs, cta_group::2) %dx%d %d->%d k%d" %
                 (top["H"], top["W"], top["Cin"], top["Cout"], top["KH"]),
                 "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                "traffic": top_kernel_traffic(top),
+                "traffic": top_kernel_traffic(top)[0], "traffic_detail": top_kernel_traffic(top)[1],
                 "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": ach / pk["tflops_burst"],
                 "ms_per_launch": per_launch_ms, "gflop_per_launch": per_launch_flops / 1e9,
