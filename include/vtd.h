@@ -101,7 +101,9 @@ int  vtd_load_recognizer(vtd_ctx* ctx, const vtd_tensor* tensors, int n);
  * (text_detector.py:99-104,117-124): BGR->RGB, Pillow antialiased bilinear resize (bit-exact,
  * 22-bit fixed point, u8 intermediate), /255, ImageNet mean/std, NHWC.  frames[i] points to frame i
  * (host or device memory); all n frames share h,w,pitch.  The source frames are kept (or copied to)
- * device memory for the later crop stage. */
+ * device memory for the later crop stage.  pixfmt = VTD_PIX_NV12: frames are decoder surfaces (h rows of Y, h/2 rows of
+ * interleaved UV, even h and w, pitch in bytes); both this stage and the crop gather convert per tap with the BT.601
+ * fixed point of cv2.cvtColor(COLOR_YUV2BGR_NV12), so the results equal those of the converted BGR frames bit for bit. */
 int  vtd_preprocess(vtd_ctx* ctx, const uint8_t* const* frames, int n, int h, int w, int pitch,
                     int pixfmt, int frames_on_device);
 
