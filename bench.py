@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight (contexts/streams/host threads)")
-    ap.add_argument("--cpu-frames", type=int, default=3, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU-baseline sample (~10 s of host time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-op device-time table (JSON) here")
     args = ap.parse_args()
