@@ -35,7 +35,8 @@ DET_H, DET_W = 736, 1312
 CROP_W = 128
 BOXES = 50
 GF_DET_PER_FRAME = 184.51          # SURVEY.md 8d, DBNet-R18 @736x1312, live layers
-GF_CRNN_PER_CROP = 1.787           # @32x128
+GF_CRNN = {128: 1.787, 100: 1.394}  # SURVEY.md 8d, GFLOP per crop @32x128 (reference default) / @32x100 (BASELINE wording)
+GF_CRNN_PER_CROP = GF_CRNN[CROP_W]
 METRIC = "1080p detect+recognize frames/sec"
 
 
@@ -149,7 +150,7 @@ def run_reference_arm(args, rank, world):
 
 def workload_config(batch, world, inflight=1):
     return {"workload": "configs[2]: full pipeline DBNet-ResNet18 detect (1080p -> 736x1312, fused DB head, box "
-                        "extraction) + CRNN recognise (32x128 crops, CTC greedy), ~50 planted boxes/frame",
+                        "extraction) + CRNN recognise (32x%d crops, CTC greedy), ~50 planted boxes/frame" % CROP_W,
             "frame": [SRC_H, SRC_W], "det": [DET_H, DET_W], "crop": [32, CROP_W], "boxes_per_frame": BOXES,
             "frames_per_step_per_gpu": batch, "batches_in_flight": inflight, "parallelism": "frame-sharded dp%d" % world,
             "l2": "frame pool of 32 distinct 1080p frames (199 MB) + per-step activations exceed the 126 MB L2"}
@@ -157,6 +158,7 @@ def workload_config(batch, world, inflight=1):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
+    global CROP_W, GF_CRNN_PER_CROP
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -166,9 +168,13 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight (contexts/streams/host threads)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU-baseline sample (~10 s of host time)")
+    ap.add_argument("--crop-w", type=int, default=CROP_W, choices=sorted(GF_CRNN),
+                    help="recogniser crop width: 128 = the reference's text_recognizer.py:118 (default, the larger "
+                         "workload), 100 = BASELINE.json configs[2] as worded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-op device-time table (JSON) here")
     args = ap.parse_args()
+    CROP_W, GF_CRNN_PER_CROP = args.crop_w, GF_CRNN[args.crop_w]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))

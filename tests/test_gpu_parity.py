@@ -312,16 +312,18 @@ def test_crnn_logits(E, port, dtype, tol):
             assert conf[i] == pytest.approx(r["confidence"], abs=2e-3)
 
 
-def test_crnn_w100_shapes(E, port):
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", 5e-3)])
+def test_crnn_w100_shapes(E, port, dtype, tol):
+    """BASELINE configs[2] words the crops as 32x100 (T=24); measured round 1: 6e-8 (fp32) / 2.6e-4 (bf16)."""
     net = port.build_crnn(seed=3)
-    eng = E.Engine(det_h=32, det_w=32, crop_w=100, max_batch=1, max_boxes=64, max_src_h=32, max_src_w=32)
+    eng = E.Engine(det_h=32, det_w=32, crop_w=100, max_batch=1, max_boxes=64, max_src_h=32, max_src_w=32, dtype=dtype)
     eng.load_recognizer(net.state_dict())
     x = np.random.default_rng(1).random((5, 3, 32, 100)).astype(np.float32)
     out = eng.crnn_forward(x)
     with torch.no_grad():
         ref = net(torch.from_numpy(x)).numpy()
     assert out.shape == ref.shape == (5, 24, 97)
-    assert np.abs(out - ref).max() <= 2e-3
+    assert np.abs(out - ref).max() <= tol
 
 
 def test_ctc_golden_bit_exact(E, port):
