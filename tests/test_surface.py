@@ -178,3 +178,92 @@ def test_frame_pointer_tables_bgr_and_nv12():
     with pytest.raises(ValueError):
         _lib.Engine._frame_ptrs([bgr[0], np.zeros((40, 64, 3), np.uint8)])                  # mixed sizes
     assert _lib.STAGE_NAMES[4] == "lstm0" and len(_lib.STAGE_NAMES) == 7
+
+
+def test_records_to_regions_matches_per_record_definition():
+    """The vectorised record -> dict conversion (one bytes.translate for a frame's texts) against the plain
+    per-record definition, on random bytes: ids outside 1..95, lengths beyond the ids field, empty texts."""
+    rng = np.random.default_rng(5)
+    rec = np.zeros((4, 64), _lib.RECORD_DTYPE)
+    rec["bbox"] = rng.integers(0, 1920, (4, 64, 4))
+    rec["polygon"] = rng.integers(-5, 1312, (4, 64, 8))
+    rec["det_conf"], rec["rec_conf"] = rng.random((4, 64)), rng.random((4, 64))
+    rec["len"] = rng.integers(0, 45, (4, 64))
+    rec["ids"] = rng.integers(0, 256, (4, 64, 36))
+    rec["ids"][1] = rng.integers(1, 96, (64, 36))                 # a frame without any NUL after translation
+    for i in range(4):
+        count = (0, 64, 50, 1)[i]
+        regions = _lib.records_to_regions(rec[i], count)
+        dets = _lib.records_to_detections(rec[i], count, with_text=True)
+        assert len(regions) == len(dets) == count
+        for k, (r, d) in enumerate(zip(regions, dets)):
+            n = min(int(rec[i, k]["len"]), 36)
+            want = _lib.ids_to_text(rec[i, k]["ids"][:n].tolist())
+            assert r["text"] == d["text"] == want
+            assert r["bbox"] == d["bbox"] == rec[i, k]["bbox"].tolist()
+            assert r["polygon"] == d["polygon"] == rec[i, k]["polygon"].reshape(4, 2).tolist()
+            assert r["detection_confidence"] == d["confidence"] == float(rec[i, k]["det_conf"])
+            assert r["recognition_confidence"] == d["recognition_confidence"] == float(rec[i, k]["rec_conf"])
+            assert list(r) == ["bbox", "text", "detection_confidence", "recognition_confidence", "polygon"]
+        json.dumps(regions)
+
+
+def test_gc_paused_is_reentrant_and_restores_state():
+    import gc
+    import threading
+    assert gc.isenabled()
+    with _lib.gc_paused():
+        assert not gc.isenabled()
+        with _lib.gc_paused():
+            assert not gc.isenabled()
+        assert not gc.isenabled()
+    assert gc.isenabled()
+    ths = [threading.Thread(target=lambda: [_lib.gc_paused().__enter__() or _lib.gc_paused().__exit__() for _ in range(200)])
+           for _ in range(4)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with _lib.gc_paused():
+            pass
+        assert not gc.isenabled()                                  # a caller's own gc.disable() is respected
+    finally:
+        gc.enable()
+
+
+def test_process_video_fused_path_keeps_frame_order_with_batches_in_flight(tmp_path):
+    """The fused path of process_video (one detect_and_recognize call per batch, `inflight` batches on executor
+    threads) with the device call replaced: results stay in frame order whatever order the batches finish in, the
+    tail batch is processed, progress is reported per retired batch, and the collector is left as it was found."""
+    import gc
+    import time as _time
+    video = str(tmp_path / "w.mp4")
+    _make_video(video, n=66)                                       # 22 sampled frames: 5 batches of 4 + a tail of 2
+    if not os.path.exists(video) or os.path.getsize(video) == 0:
+        pytest.skip("no mp4 encoder in this OpenCV build")
+    p = VideoTextPipeline(use_transformer_ocr=False, batch_size=4, backbone="resnet18", pretrained=False, inflight=3)
+    seen = []
+
+    def fake(frames, slot=0):
+        k = len(seen)
+        seen.append((len(frames), slot))
+        _time.sleep(0.03 * ((7 - k) % 3))                          # later batches finish first
+        return [[{"bbox": [1, 2, 30 + k, 40], "text": "b%d" % k, "detection_confidence": 0.5,
+                  "recognition_confidence": 0.25, "polygon": [[1, 2], [30, 2], [30, 40], [1, 40]]}] for _ in frames]
+
+    calls = []
+
+    async def progress(pr, done, total):
+        calls.append(done)
+
+    with patch.object(p, "detect_and_recognize", side_effect=fake):
+        res = asyncio.run(p.process_video(video, str(tmp_path), progress))
+    assert res["status"] == "success"
+    assert [r["frame_number"] for r in res["results"]] == list(range(22))
+    assert [r["detections"][0]["text"] for r in res["results"]] == ["b%d" % (i // 4) for i in range(22)]
+    assert [n for n, _ in seen] == [4, 4, 4, 4, 4, 2] and {s for _, s in seen[:5]} == {0, 1, 2}
+    assert calls == [4, 8, 12, 16, 20]                              # the reference reports per full batch (:63-65)
+    assert res["summary"]["total_frames"] == 22 and res["summary"]["total_detections"] == 22
+    assert gc.isenabled() and gc.get_freeze_count() == 0
+    json.dumps(res)
