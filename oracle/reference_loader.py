@@ -92,3 +92,60 @@ def reference_recognizer(state_dict=None):
         r.model.load_state_dict(state_dict, strict=True)
     r.model.eval()
     return r
+
+
+def reference_sinks():
+    """The reference's result sinks, unmodified, as plain callables:
+    (export_results_csv, export_results_xml, _draw_detections, save_results_to_database).
+    Their modules import celery / sqlalchemy / settings, which are absent here, so only the four function bodies
+    are compiled (by AST, from the files where they lie) into a namespace holding what they use.  The database sink's
+    Pydantic/CRUD collaborators are replaced by recorders that return what they were called with."""
+    import ast
+    import asyncio
+    import csv
+    import io
+    import logging
+    import xml.etree.ElementTree as ET
+    from typing import Any, Dict, List, Optional
+
+    import cv2
+
+    def functions(rel, names):
+        path = os.path.join(REF_ROOT, rel)
+        with open(path) as f:
+            tree = ast.parse(f.read(), path)
+        found = [n for n in ast.walk(tree)
+                 if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef)) and n.name in names]
+        mod = ast.Module(body=found, type_ignores=[])
+        return compile(mod, path, "exec")
+
+    class Row(dict):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.__dict__.update(kw)
+
+    class FrameCRUD:
+        @staticmethod
+        def create_bulk(db, frames):
+            db["frames"] = frames
+            return [Row(id=1000 + i, **f) for i, f in enumerate(frames)]
+
+    class TextDetectionCRUD:
+        @staticmethod
+        def create_bulk(db, detections):
+            db["detections"] = detections
+            return detections
+
+    ns = {"io": io, "csv": csv, "ET": ET, "cv2": cv2, "np": np, "Dict": Dict, "Any": Any, "List": List,
+          "Optional": Optional, "logger": logging.getLogger("reference_sinks"), "Session": dict,
+          "FrameCreate": Row, "TextDetectionCreate": Row, "FrameCRUD": FrameCRUD,
+          "TextDetectionCRUD": TextDetectionCRUD}
+    exec(functions("app/services/processing_service.py",
+                   {"export_results_csv", "export_results_xml", "_draw_detections"}), ns)
+    exec(functions("app/tasks/video_processing.py", {"save_results_to_database"}), ns)
+
+    def run(coro_fn):
+        return lambda data: asyncio.run(coro_fn(None, data))
+
+    return (run(ns["export_results_csv"]), run(ns["export_results_xml"]),
+            lambda frame, dets: ns["_draw_detections"](None, frame, dets), ns["save_results_to_database"])
