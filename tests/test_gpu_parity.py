@@ -6,6 +6,7 @@ bf16; identical masks away from threshold ties; box sets identical as integer se
 bit-exact CTC token ids for the same logits; preprocess bit-exact; crop resize within 1 LSB.
 """
 import json
+import os
 
 import numpy as np
 import pytest
@@ -14,6 +15,9 @@ import torch
 from conftest import golden_json, load_golden
 
 pytestmark = pytest.mark.gpu
+# VTD_STORAGE=f16 runs the same tests against libvtd_b200_f16.so (IEEE half as the 16-bit storage type of the speed tier)
+HALF_STORAGE = os.environ.get("VTD_STORAGE", "") == "f16"
+STORAGE_16 = torch.float16 if HALF_STORAGE else torch.bfloat16
 
 
 @pytest.fixture(scope="module")
@@ -80,7 +84,7 @@ def test_preprocess_vs_oracle(E, port, src, det):
     engb = E.Engine(det_h=det[0], det_w=det[1], max_batch=2, max_src_h=src[0], max_src_w=src[1], dtype="bf16")
     engb.preprocess(list(frames))
     xb = engb.debug_tensor("input", 2)
-    assert np.array_equal(xb, torch.from_numpy(x).bfloat16().float().numpy())
+    assert np.array_equal(xb, torch.from_numpy(x).to(STORAGE_16).float().numpy())
 
 
 # ---------------------------------------------------------------- stages 2+3: DBNet + fused head
@@ -183,6 +187,11 @@ def test_config1_640x640_maps_and_boxes_vs_oracle(E, port, dtype, tol):
     for got, want in ((p, ref["probability"].numpy()[:, 0]), (t, ref["threshold"].numpy()[:, 0])):
         err = np.abs(got - want)
         if dtype == "fp32":
+            assert err.max() <= tol, err.max()
+        elif HALF_STORAGE:
+            # libvtd_b200_f16.so (VTD_STORAGE=f16): IEEE half as the 16-bit storage type meets the bar outright
+            # (CPU emulation of the rounding points: 1.9e-3 / 2.0e-3, profiles/r01_bf16_error_budget.md)
+            print("f16 640x640: max %.4f" % err.max())
             assert err.max() <= tol, err.max()
         else:
             # 819 200 pixels per map.  Measured for this net (randomised BN statistics, seed 0): probability map 0.11 % of

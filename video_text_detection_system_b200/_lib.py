@@ -74,10 +74,12 @@ def load_library():
     with _lib_lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            from .build import build_library
-            build_library()
-        lib = C.CDLL(LIB_PATH)
+        from .build import build_library, variant_paths
+        variant = os.environ.get("VTD_STORAGE", "")            # "" = shipped bf16 library; "f16" = half-storage build
+        path = variant_paths(variant)[1]
+        if not os.path.exists(path):
+            build_library(variant=variant)
+        lib = C.CDLL(path)
         vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
         lib.vtd_create.argtypes = [C.POINTER(vp), C.POINTER(VtdConfig)]
         lib.vtd_destroy.argtypes = [vp]; lib.vtd_destroy.restype = None

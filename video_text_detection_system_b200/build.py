@@ -37,8 +37,20 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def variant_paths(variant: str = ""):
+    """(object directory, library path, extra nvcc flags) of a build variant.  "" = the shipped library (bf16 speed
+    tier); "f16" = the same sources with IEEE half as the 16-bit storage type (-DVTD_HALF_STORAGE, csrc/common.cuh):
+    libvtd_b200_f16.so, selected at load time with VTD_STORAGE=f16."""
+    if variant in ("", "bf16"):
+        return OBJ, LIB, []
+    if variant == "f16":
+        return OBJ + "_f16", os.path.join(HERE, "libvtd_b200_f16.so"), ["-DVTD_HALF_STORAGE"]
+    raise ValueError("unknown build variant %r" % variant)
+
+
+def build_library(force: bool = False, verbose: bool = False, variant: str = "") -> str:
     nvcc = _nvcc()
+    OBJ, LIB, extra = variant_paths(variant)
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
@@ -50,7 +62,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def run(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("VTD_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + extra + os.environ.get("VTD_NVCC_EXTRA", "").split() + ["-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (s, r.stdout, r.stderr))
@@ -71,4 +83,4 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv, verbose=True, variant="f16" if "--f16" in sys.argv else ""))

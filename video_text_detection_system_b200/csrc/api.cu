@@ -190,7 +190,7 @@ int fold_conv(vtd_ctx* c, const SD& sd, const std::string& conv, const std::stri
 int upload_act_type(vtd_ctx* c, const std::vector<float>& h, void** dev) {
   if (c->bf16_mode) {
     std::vector<bf16> t(h.size());
-    for (size_t i = 0; i < h.size(); ++i) t[i] = __float2bfloat16_rn(h[i]);
+    for (size_t i = 0; i < h.size(); ++i) t[i] = f32_to_16(h[i]);
     int r = dev_alloc(c, dev, t.size() * 2); if (r) return r;
     CK(cudaMemcpy(*dev, t.data(), t.size() * 2, cudaMemcpyHostToDevice));
   } else {

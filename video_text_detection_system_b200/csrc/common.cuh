@@ -2,20 +2,43 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 #include <string.h>
 
 namespace vtd {
 
+// The 16-bit storage type of the speed tier (activations, weights, tcgen05 A/B operands).  bfloat16 in the shipped
+// build.  -DVTD_HALF_STORAGE builds the same kernels over IEEE half instead (tcgen05 kind::f16 takes either at the same
+// rate): three more mantissa bits, i.e. ~8x smaller rounding error per stored value, at the price of half's range
+// (profiles/r01_bf16_error_budget.md).  The type keeps the name `bf16` throughout the sources in both variants.
+#ifdef VTD_HALF_STORAGE
+typedef __half bf16;
+typedef __half2 bf16x2;
+#define VTD_TMAP_16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define VTD_UMMA_AB_FMT 0u                              // instruction-descriptor A/B format: F16
+__host__ __device__ __forceinline__ bf16 f32_to_16(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float f16_to_32(bf16 v) { return __half2float(v); }
+__device__ __forceinline__ bf16x2 pack2(float a, float b) { return __floats2half2_rn(a, b); }
+__device__ __forceinline__ float2 unpack2(bf16x2 h) { return __half22float2(h); }
+#else
 typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf16x2;
+#define VTD_TMAP_16 CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define VTD_UMMA_AB_FMT 1u                              // instruction-descriptor A/B format: BF16
+__host__ __device__ __forceinline__ bf16 f32_to_16(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float f16_to_32(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ bf16x2 pack2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ float2 unpack2(bf16x2 h) { return __bfloat1622float2(h); }
+#endif
 
 // ---- element load/store helpers (activations are fp32 or bf16, math is fp32) -------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
-__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(bf16 v) { return f16_to_32(v); }
 template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return f32_to_16(v); }
 
 struct LaunchCounter { long long n = 0; };
 

@@ -28,9 +28,9 @@ template <> struct Vec8<bf16> {
   float v[8];
   __device__ __forceinline__ void load(const bf16* p) {
     uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const bf16x2* h = reinterpret_cast<const bf16x2*>(&a);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    for (int i = 0; i < 4; ++i) { float2 f = unpack2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
   }
 };
 
@@ -40,8 +40,8 @@ template <> __device__ __forceinline__ void load4<float>(const float* p, float* 
 }
 template <> __device__ __forceinline__ void load4<bf16>(const bf16* p, float* v) {
   uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
-  float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+  const bf16x2* h = reinterpret_cast<const bf16x2*>(&a);
+  float2 f0 = unpack2(h[0]), f1 = unpack2(h[1]);
   v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
 }
 
@@ -50,7 +50,7 @@ template <> __device__ __forceinline__ void store4<float>(float* p, const float*
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
 template <> __device__ __forceinline__ void store4<bf16>(bf16* p, const float* v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  bf16x2 a = pack2(v[0], v[1]), b = pack2(v[2], v[3]);
   uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
   *reinterpret_cast<uint2*>(p) = u;
 }

@@ -218,10 +218,10 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
       if (has_res) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[i][j]);
+          const bf16x2* h = reinterpret_cast<const bf16x2*>(&rv[i][j]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            float2 r2 = __bfloat1622float2(h[e]);
+            float2 r2 = unpack2(h[e]);
             f[j * 8 + e * 2] += r2.x; f[j * 8 + e * 2 + 1] += r2.y;
           }
         }
@@ -239,10 +239,10 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint4 u;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+          bf16x2 h0 = pack2(f[8 * j], f[8 * j + 1]);
+          bf16x2 h1 = pack2(f[8 * j + 2], f[8 * j + 3]);
+          bf16x2 h2 = pack2(f[8 * j + 4], f[8 * j + 5]);
+          bf16x2 h3 = pack2(f[8 * j + 6], f[8 * j + 7]);
           u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
           u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
           op[j] = u;
@@ -286,10 +286,10 @@ __device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUte
     if (use_res) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rv[hh * 4 + j]);
+        const bf16x2* h = reinterpret_cast<const bf16x2*>(&rv[hh * 4 + j]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float2 r2 = __bfloat1622float2(h[e]);
+          float2 r2 = unpack2(h[e]);
           f[j * 8 + e * 2] += r2.x; f[j * 8 + e * 2 + 1] += r2.y;
         }
       }
@@ -306,10 +306,10 @@ __device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUte
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-        __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+        bf16x2 h0 = pack2(f[8 * j], f[8 * j + 1]);
+        bf16x2 h1 = pack2(f[8 * j + 2], f[8 * j + 3]);
+        bf16x2 h2 = pack2(f[8 * j + 4], f[8 * j + 5]);
+        bf16x2 h3 = pack2(f[8 * j + 6], f[8 * j + 7]);
         o[hh * 4 + j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                                    *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
       }
@@ -348,8 +348,8 @@ __device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUte
                      : "r"(stg + r * 128u + ((c ^ (r & 7u)) << 4)) : "memory");
         if (w == 0) m4 = t;
         else {
-          __nv_bfloat162 a, b;
-#define VTD_HMAX2(dst, src) a = *reinterpret_cast<__nv_bfloat162*>(&dst); b = *reinterpret_cast<__nv_bfloat162*>(&src); \
+          bf16x2 a, b;
+#define VTD_HMAX2(dst, src) a = *reinterpret_cast<bf16x2*>(&dst); b = *reinterpret_cast<bf16x2*>(&src); \
           a = __hmax2(a, b); dst = *reinterpret_cast<uint32_t*>(&a);
           VTD_HMAX2(m4.x, t.x) VTD_HMAX2(m4.y, t.y) VTD_HMAX2(m4.z, t.z) VTD_HMAX2(m4.w, t.w)
 #undef VTD_HMAX2
@@ -487,9 +487,9 @@ __device__ __forceinline__ void epilogue_lstm(const TcParams& p, uint32_t tmem_a
         *reinterpret_cast<float4*>(cs + u) = make_float4(cv[0], cv[1], cv[2], cv[3]);
       }
       uint4 w0, w1;
-      __nv_bfloat162 h2[8];
+      bf16x2 h2[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) h2[e] = __floats2bfloat162_rn(hv[2 * e], hv[2 * e + 1]);
+      for (int e = 0; e < 8; ++e) h2[e] = pack2(hv[2 * e], hv[2 * e + 1]);
       w0.x = *reinterpret_cast<uint32_t*>(&h2[0]); w0.y = *reinterpret_cast<uint32_t*>(&h2[1]);
       w0.z = *reinterpret_cast<uint32_t*>(&h2[2]); w0.w = *reinterpret_cast<uint32_t*>(&h2[3]);
       w1.x = *reinterpret_cast<uint32_t*>(&h2[4]); w1.y = *reinterpret_cast<uint32_t*>(&h2[5]);
@@ -1046,7 +1046,7 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (VTD_UMMA_AB_FMT << 7) | (VTD_UMMA_AB_FMT << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int as_ = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t accph = 0;
       for (int pair = cluster_id; pair < npairs; pair += nclusters) {
         mbar_wait(tempty0 + 8 * acc, accph ^ 1);
@@ -1236,7 +1236,7 @@ conv_tc2g_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (VTD_UMMA_AB_FMT << 7) | (VTD_UMMA_AB_FMT << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accph = 0;
       bool ready = false;
       for (int pair = cluster_id; pair < npairs; pair += nclusters) {
@@ -1341,7 +1341,7 @@ CUresult encode_weights(EncodeTiledFn enc, CUtensorMap* m, const void* w, long l
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_n};
   cuuint32_t es[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+  return enc(m, VTD_TMAP_16, 2, const_cast<void*>(w), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
@@ -1351,7 +1351,7 @@ CUresult encode_act4d(EncodeTiledFn enc, CUtensorMap* m, const void* base, int C
   cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bnn};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+  return enc(m, VTD_TMAP_16, 4, const_cast<void*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
@@ -1373,7 +1373,7 @@ CUresult encode_out(EncodeTiledFn enc, CUtensorMap* m, void* out, int out_f32, i
   cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
   cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sn};
   cuuint32_t est[4] = {1, 1, 1, 1};
-  return enc(m, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, est,
+  return enc(m, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : VTD_TMAP_16, 4, out, dims, strides, box, est,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
@@ -1492,7 +1492,7 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
       cuuint64_t strides[3] = {(cuuint64_t)K * 2, 128, (cuuint64_t)d.Cin * 2};
       cuuint32_t box[4] = {64, (cuuint32_t)(p.cta2 ? bn / 2 : bn), 1, (cuuint32_t)p.b_taps};
       cuuint32_t es[4] = {1, 1, 1, 1};
-      hr = enc(&pl->maps.b4, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.w), dims, strides, box, es,
+      hr = enc(&pl->maps.b4, VTD_TMAP_16, 4, const_cast<void*>(d.w), dims, strides, box, es,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights by tap) failed: " + std::to_string((int)hr)); }
@@ -1564,7 +1564,7 @@ TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int s
   cuuint64_t strides[4] = {16, (cuuint64_t)row * 2, (cuuint64_t)row * stride * 2, (cuuint64_t)row * Hp * 2};
   cuuint32_t box[5] = {32, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bnn};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(&pl->maps.a[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(in), dims, strides, box, es,
+  CUresult r = enc(&pl->maps.a[0], VTD_TMAP_16, 5, const_cast<void*>(in), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(window) failed: " + std::to_string((int)r)); }

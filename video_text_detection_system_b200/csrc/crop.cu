@@ -44,7 +44,7 @@ template <> __device__ __forceinline__ void store_px<float>(float* o, float b, f
   if (cpp == 8) *reinterpret_cast<float4*>(o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 template <> __device__ __forceinline__ void store_px<bf16>(bf16* o, float b, float g, float r, int cpp) {
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(b, g), p1 = __floats2bfloat162_rn(r, 0.f);
+  bf16x2 p0 = pack2(b, g), p1 = pack2(r, 0.f);
   if (cpp == 8) {
     uint4 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1); u.z = 0u; u.w = 0u;
     *reinterpret_cast<uint4*>(o) = u;

@@ -248,15 +248,15 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
         const uint32_t tb = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * L_UPT + j * 8);
         tmem_ld8(tb, vi); tmem_ld8(tb + 64, vf); tmem_ld8(tb + 128, vg); tmem_ld8(tb + 192, vo);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const __nv_bfloat162* xi2 = reinterpret_cast<const __nv_bfloat162*>(&xr[0][j]);
-        const __nv_bfloat162* xf2 = reinterpret_cast<const __nv_bfloat162*>(&xr[1][j]);
-        const __nv_bfloat162* xg2 = reinterpret_cast<const __nv_bfloat162*>(&xr[2][j]);
-        const __nv_bfloat162* xo2 = reinterpret_cast<const __nv_bfloat162*>(&xr[3][j]);
+        const bf16x2* xi2 = reinterpret_cast<const bf16x2*>(&xr[0][j]);
+        const bf16x2* xf2 = reinterpret_cast<const bf16x2*>(&xr[1][j]);
+        const bf16x2* xg2 = reinterpret_cast<const bf16x2*>(&xr[2][j]);
+        const bf16x2* xo2 = reinterpret_cast<const bf16x2*>(&xr[3][j]);
         float hv[8];
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
-          const float2 xi = __bfloat1622float2(xi2[e2]), xf = __bfloat1622float2(xf2[e2]);
-          const float2 xg = __bfloat1622float2(xg2[e2]), xo = __bfloat1622float2(xo2[e2]);
+          const float2 xi = unpack2(xi2[e2]), xf = unpack2(xf2[e2]);
+          const float2 xg = unpack2(xg2[e2]), xo = unpack2(xo2[e2]);
           const float xiv[2] = {xi.x, xi.y}, xfv[2] = {xf.x, xf.y}, xgv[2] = {xg.x, xg.y}, xov[2] = {xo.x, xo.y};
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -268,8 +268,8 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
             hv[u] = valid ? sigmoid_approx(go) * tanh_approx(cn) : 0.f;
           }
         }
-        __nv_bfloat162 a0 = __floats2bfloat162_rn(hv[0], hv[1]), a1 = __floats2bfloat162_rn(hv[2], hv[3]);
-        __nv_bfloat162 a2 = __floats2bfloat162_rn(hv[4], hv[5]), a3 = __floats2bfloat162_rn(hv[6], hv[7]);
+        bf16x2 a0 = pack2(hv[0], hv[1]), a1 = pack2(hv[2], hv[3]);
+        bf16x2 a2 = pack2(hv[4], hv[5]), a3 = pack2(hv[6], hv[7]);
         uint4 u4;
         u4.x = *reinterpret_cast<uint32_t*>(&a0); u4.y = *reinterpret_cast<uint32_t*>(&a1);
         u4.z = *reinterpret_cast<uint32_t*>(&a2); u4.w = *reinterpret_cast<uint32_t*>(&a3);
@@ -349,7 +349,7 @@ LstmPlan* lstm_plan_create(const void* whh /*[2*1024][256] bf16, rows (dir, unit
   cuuint64_t strides[1] = {256 * 2};
   cuuint32_t box[2] = {64, 256};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(&pl->map_whh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(whh), dims, strides, box, es,
+  CUresult r = enc(&pl->map_whh, VTD_TMAP_16, 2, const_cast<void*>(whh), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -30,7 +30,7 @@ template <> struct PoolVec<bf16> {
     uint32_t u = 0xff80ff80u; return make_uint4(u, u, u, u);
   }
   static __device__ __forceinline__ uint32_t m2(uint32_t a, uint32_t b) {
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    bf16x2 r = __hmax2(*reinterpret_cast<bf16x2*>(&a), *reinterpret_cast<bf16x2*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
   }
   static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) {

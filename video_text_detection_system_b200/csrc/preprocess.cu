@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(NT) preprocess_kernel(const uint8_t* const* __
     if (sizeof(T) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = make_float4(vr, vg, vb, 0.f);
     } else {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(vr, vg), p1 = __floats2bfloat162_rn(vb, 0.f);
+      bf16x2 p0 = pack2(vr, vg), p1 = pack2(vb, 0.f);
       uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + o) = u;
     }

@@ -96,7 +96,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=BLOCK_N
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+  return (1u << 4) | (VTD_UMMA_AB_FMT << 7) | (VTD_UMMA_AB_FMT << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
