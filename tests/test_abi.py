@@ -68,3 +68,21 @@ def test_bad_config_rejected(lib_built):
     for kw in ({"backbone": 34}, {"det_h": 100}, {"crop_w": 130}, {"max_boxes": 5000}, {"max_batch": 0}):
         with pytest.raises(_lib.VtdError):
             _lib.Engine(**kw)
+
+
+def test_half_storage_variant_builds_and_holds_no_bf16_code():
+    """libvtd_b200_f16.so (-DVTD_HALF_STORAGE, selected with VTD_STORAGE=f16): same exports, tcgen05/TMA present, and
+    not one BF16 conversion or BF16-typed MMA left in its SASS (the shipped library holds hundreds)."""
+    import shutil
+    import subprocess
+    from video_text_detection_system_b200.build import build_library
+    path = build_library(variant="f16")
+    lib = ctypes.CDLL(path)
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out and "UTMALDG" in out
+    assert "BF16" not in out and "F16" in out
