@@ -201,7 +201,12 @@ def pillow_coeffs(in_size: int, out_size: int):
 def pillow_resize_restated(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     """NumPy restatement of PIL.Image.resize((out_w,out_h), BILINEAR) on HxWxC uint8:
     horizontal pass first, uint8 intermediate, then vertical.
-    This is the arithmetic the CUDA preprocess kernel implements."""
+    This is the arithmetic the CUDA preprocess kernel implements.
+
+    Domain: bit-exact to Pillow 12.2 for every source no taller than 100x its width
+    (tests/test_oracle_golden.py sweeps sizes, up- and down-scaling on either axis).  For a source with
+    h > 100*w whose height shrinks, Pillow runs the vertical pass first and the u8 intermediate rounds
+    differently (+-1 LSB); video frames are nowhere near that aspect ratio."""
     h, w, c = img.shape
     src = img.astype(np.int64)
     if out_w != w:

@@ -41,6 +41,48 @@ def test_preprocess_and_restated_pillow_resize():
         assert np.array_equal(port.preprocess_restated(frame, 640, 640), t)
 
 
+def test_restated_pillow_resize_size_sweep():
+    """The integer restatement the CUDA preprocess kernel is held to, against the installed Pillow over a seeded sweep
+    of shapes: up- and down-scaling on either axis, 1-pixel sources, odd sizes, the BASELINE frame sizes (scaled down
+    4x to keep the pure-NumPy restatement quick).  Plus its stated limit: sources taller than 100x their width."""
+    from PIL import Image
+    rng = np.random.default_rng(123)
+    sizes = [(270, 480, 184, 328), (180, 320, 184, 328), (540, 960, 544, 960), (160, 160, 160, 160), (64, 64, 640, 640),
+             (641, 639, 640, 640), (1, 1, 32, 32), (2, 3, 32, 64), (333, 777, 96, 160), (37, 53, 64, 32), (300, 3, 32, 256),
+             (3, 400, 32, 64), (100, 10, 50, 40), (64, 16, 32, 32)]
+    for _ in range(16):
+        sizes.append((int(rng.integers(1, 500)), int(rng.integers(5, 500)), int(rng.integers(1, 12)) * 32,
+                      int(rng.integers(1, 12)) * 32))
+    for h, w, oh, ow in sizes:
+        assert h <= 100 * w
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        want = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+        assert np.array_equal(port.pillow_resize_restated(img, oh, ow), want), (h, w, oh, ow)
+    # beyond the limit Pillow swaps its passes: within 1 LSB, and equal to the restatement run vertical-first
+    img = rng.integers(0, 256, (342, 3, 3), dtype=np.uint8)
+    want = np.asarray(Image.fromarray(img).resize((256, 288), Image.BILINEAR)).astype(int)
+    got = port.pillow_resize_restated(img, 288, 256).astype(int)
+    assert 0 < np.abs(got - want).max() <= 1
+    swapped = port.pillow_resize_restated(port.pillow_resize_restated(img, 288, 3), 288, 256)
+    assert np.array_equal(swapped, want)
+
+
+def test_restated_cv_resize_size_sweep():
+    """cv2.resize INTER_LINEAR to 32 x {128,100} (text_recognizer.py:118) against the portable fixed-point restatement the
+    crop kernel implements: within 1 LSB of the installed wheel for crops of any shape (the wheel's SIMD path differs
+    from OpenCV's own portable path by at most that)."""
+    import cv2
+    rng = np.random.default_rng(9)
+    shapes = [(1, 1), (1, 500), (500, 1), (11, 11), (12, 300), (31, 127), (33, 129), (32, 128), (32, 100), (2, 2), (300, 900)]
+    shapes += [(int(rng.integers(1, 400)), int(rng.integers(1, 900))) for _ in range(30)]
+    for h, w in shapes:
+        c = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for cw in (128, 100):
+            a = port.cv_resize_linear_restated(c, 32, cw).astype(int)
+            b = cv2.resize(c, (cw, 32)).astype(int)
+            assert np.abs(a - b).max() <= 1, (h, w, cw)
+
+
 def _cases():
     g = load_golden("postprocess")
     return sorted({k[:-4] for k in g.files if k.endswith("_map")})
