@@ -72,3 +72,68 @@ def test_components_match_cv2(host_harness, name, mask):
         mine = np.array(list(c.box), np.float32).reshape(4, 2)
         # bit-exact: same hull order, same calipers decisions, same float32 arithmetic as cv2
         assert np.array_equal(mine, box), (name, start, mine, box)
+
+
+def shape_masks():
+    """Shapes the blur/noise masks above do not produce: rotated rectangles (the production shape) at regular and
+    degenerate angles, squares and diamonds (calipers ties), ellipses, dilated text, thin and 1-pixel diagonal lines,
+    blobs touching the image border, the 10x11 / 11x11 area-threshold pair."""
+    rng = np.random.default_rng(42)
+    for ang in list(range(-90, 91, 5)) + [45.0, -45.0, 26.565, 63.435, 1e-3, 89.999]:
+        for bw, bh in ((80, 24), (40, 40), (101, 13)):
+            m = np.zeros((160, 200), np.uint8)
+            cv2.fillPoly(m, [np.round(cv2.boxPoints(((100, 80), (bw, bh), float(ang)))).astype(np.int32)], 1)
+            yield "rect a=%s %dx%d" % (ang, bw, bh), m > 0
+    for k in range(20):
+        m = np.zeros((300, 400), np.uint8)
+        for _ in range(12):
+            box = cv2.boxPoints(((rng.uniform(30, 370), rng.uniform(30, 270)),
+                                 (rng.uniform(15, 100), rng.uniform(11, 40)), rng.uniform(-90, 90)))
+            cv2.fillPoly(m, [np.round(box).astype(np.int32)], 1)
+        yield "multi%d" % k, m > 0
+    for k in range(12):
+        m = np.zeros((200, 300), np.uint8)
+        cv2.ellipse(m, (150, 100), (int(rng.integers(8, 120)), int(rng.integers(8, 80))), float(rng.uniform(0, 180)),
+                    0, 360, 1, -1)
+        yield "ellipse%d" % k, m > 0
+    for k in range(12):
+        m = np.zeros((120, 500), np.uint8)
+        cv2.putText(m, "Text %d gq!" % k, (10, 80), cv2.FONT_HERSHEY_SIMPLEX, rng.uniform(1, 3), 1, int(rng.integers(2, 8)))
+        yield "text%d" % k, (cv2.dilate(m, np.ones((5, 9), np.uint8)) if k % 2 else m) > 0
+    for k in range(8):
+        m = np.zeros((200, 300), np.uint8)
+        cv2.line(m, (int(rng.integers(0, 300)), int(rng.integers(0, 200))),
+                 (int(rng.integers(0, 300)), int(rng.integers(0, 200))), 1, int(rng.integers(1, 4)))
+        yield "line%d" % k, m > 0
+    for k in range(8):
+        m = np.zeros((100, 150), np.uint8)
+        m[:int(rng.integers(5, 40)), :int(rng.integers(20, 150))] = 1
+        m[-int(rng.integers(5, 40)):, -int(rng.integers(20, 150)):] = 1
+        yield "border%d" % k, m > 0
+    for hh_, name in ((10, "10x11"), (11, "11x11")):
+        m = np.zeros((64, 64), bool)
+        m[10:21, 10:10 + hh_] = True
+        yield name, m
+    m = np.zeros((64, 64), bool)
+    m[np.arange(10, 50), np.arange(10, 50)] = True
+    yield "diagonal-1px", m
+    yy, xx = np.mgrid[0:101, 0:101]
+    yield "diamond", (np.abs(xx - 50) + np.abs(yy - 50)) <= 30
+
+
+def test_shape_sweep_matches_cv2(host_harness):
+    boxes = 0
+    for name, mask in shape_masks():
+        comps = run_harness(host_harness, mask)
+        ext = {c.start: c for c in comps if c.external}
+        ref = cv_externals(mask)
+        assert set(ext) == set(ref), name
+        for start, contour in ref.items():
+            c = ext[start]
+            assert abs(c.area2) / 2.0 == cv2.contourArea(contour), (name, start)
+            if cv2.contourArea(contour) < 100:
+                continue
+            box = cv2.boxPoints(cv2.minAreaRect(contour))
+            assert np.array_equal(np.array(list(c.box), np.float32).reshape(4, 2), box), (name, start)
+            boxes += 1
+    assert boxes >= 400
