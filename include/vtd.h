@@ -37,7 +37,9 @@ enum {
 };
 
 enum { VTD_FP32 = 0,     /* fp32 activations, CUDA-core FFMA implicit GEMM: the <=1e-3 parity tier */
-       VTD_BF16 = 1 };   /* bf16 activations, tcgen05/TMEM implicit GEMM fed by TMA: the speed tier */
+       VTD_BF16 = 1 };   /* 16-bit activations, tcgen05/TMEM implicit GEMM fed by TMA: the speed tier.  bfloat16 in
+                            libvtd_b200.so; libvtd_b200_f16.so (-DVTD_HALF_STORAGE, same sources and ABI) stores IEEE
+                            half instead: ~8x smaller rounding error, half's range (profiles/r01_f16_variant.md) */
 
 enum { VTD_IDS_STRIDE = 64 }; /* row pitch of the ids_out arrays of the decode / recognise drop-ins */
 
