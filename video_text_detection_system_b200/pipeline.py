@@ -142,26 +142,26 @@ class VideoTextPipeline:
         tasks = [loop.run_in_executor(self.executor, self.detector.detect, f, self.confidence_threshold)
                  for f in frames]
         batch_detections = await asyncio.gather(*tasks)
-        results = []
-        for i, detections in enumerate(batch_detections):
-            frame_number, timestamp = frame_info[i]
-            frame = frames[i]
-            if not detections:
-                results.append({"frame_number": frame_number, "timestamp": timestamp, "detections": []})
+        return [{"frame_number": number, "timestamp": stamp,
+                 "detections": self._recognize_regions(frame, detections or [], with_polygon=True)}
+                for (number, stamp), frame, detections in zip(frame_info, frames, batch_detections)]
+
+    def _recognize_regions(self, frame: np.ndarray, detections: List[Dict], with_polygon: bool) -> List[Dict]:
+        """Per-detection crop + recognize() of the reference's control flow (pipeliine.py:112-133 for a batch, with
+        'polygon'; :153-166 for a single frame, without).  Only used when a caller patched detect/recognize/forward."""
+        regions = []
+        for det in detections:
+            x1, y1, x2, y2 = det["bbox"]
+            crop = frame[y1:y2, x1:x2]
+            if crop.size == 0:                       # :122-123
                 continue
-            text_regions = []
-            for detection in detections:
-                x1, y1, x2, y2 = detection["bbox"]
-                crop = frame[y1:y2, x1:x2]
-                if crop.size == 0:
-                    continue
-                t = self.recognizer.recognize(crop)
-                text_regions.append({"bbox": detection["bbox"], "text": t["text"],
-                                     "detection_confidence": detection["confidence"],
-                                     "recognition_confidence": t["confidence"],
-                                     "polygon": detection.get("polygon", [])})
-            results.append({"frame_number": frame_number, "timestamp": timestamp, "detections": text_regions})
-        return results
+            rec = self.recognizer.recognize(crop)
+            region = {"bbox": det["bbox"], "text": rec["text"], "detection_confidence": det["confidence"],
+                      "recognition_confidence": rec["confidence"]}
+            if with_polygon:
+                region["polygon"] = det.get("polygon", [])
+            regions.append(region)
+        return regions
 
     def process_single_frame(self, frame: np.ndarray) -> Dict[str, Any]:
         try:
@@ -170,19 +170,7 @@ class VideoTextPipeline:
                 # pipeliine.py:161-166: the single-frame path returns no 'polygon'
                 return {"detections": [{k: v for k, v in r.items() if k != "polygon"} for r in regions]}
             detections = self.detector.detect(frame, self.confidence_threshold)
-            if not detections:
-                return {"detections": []}
-            text_regions = []
-            for detection in detections:
-                x1, y1, x2, y2 = detection["bbox"]
-                crop = frame[y1:y2, x1:x2]
-                if crop.size == 0:
-                    continue
-                t = self.recognizer.recognize(crop)
-                text_regions.append({"bbox": detection["bbox"], "text": t["text"],
-                                     "detection_confidence": detection["confidence"],
-                                     "recognition_confidence": t["confidence"]})
-            return {"detections": text_regions}
+            return {"detections": self._recognize_regions(frame, detections or [], with_polygon=False)}
         except Exception as e:
             logger.error(f"Single frame processing failed: {e}")
             return {"detections": [], "error": str(e)}
