@@ -68,6 +68,15 @@ def test_shard_and_gather_world2(tmp_path, n_frames):
     assert open(out).read() == "ok"
 
 
+@pytest.mark.parametrize("n_frames", [3, 9])
+def test_shard_and_gather_world4_with_idle_and_ragged_ranks(tmp_path, n_frames):
+    """World size 4: 3 frames leave rank 3 without work (it still takes part in the gather with a zero count),
+    9 frames give rank 0 one frame more than the others."""
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_worker, args=(4, _free_port(), n_frames, 5, out), nprocs=4, join=True)
+    assert open(out).read() == "ok"
+
+
 def test_shard_indices_cover_everything():
     for n in (0, 1, 5, 16, 3000):
         for w in (1, 2, 4, 8):
