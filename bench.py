@@ -64,6 +64,36 @@ def top_kernel_traffic(op):
     return None, None
 
 
+def hbm_stage_rooflines(stages, steps, batch, crops_per_step, crop_src_bytes_per_step, hbm_gbs, bias_plane=True):
+    """Achieved HBM GB/s of the stages that are HBM-bound by their bytes (north_star: "achieved HBM GB/s for the
+    elementwise, post-processing and gather stages").  `stages` = Engine.op_profile(2) of a profiled pass of `steps`
+    steps with ONE batch in flight (CUDA-event time per stage, summed over the steps).  ALGORITHMIC bytes per step,
+    SURVEY.md 8d (bf16 tier, s = 2): what the stage must read and write once, not what the kernels happen to move."""
+    px = DET_H * DET_W
+    per_step = {
+        # K1: BGR frame in, 3 normalised channels out
+        "preprocess": batch * (SRC_H * SRC_W * 3 + 3 * px * 2),
+        # K3: feat [Hd/4, Wd/4, 128] bf16 in; prob + thresh fp32 and the u8 mask out; + the planted fp32 logit plane
+        "head_tail": batch * ((px // 16) * 128 * 2 + 2 * px * 4 + px + (px * 4 if bias_plane else 0)),
+        # K4-K6: mask in, the int32 label plane written and read once, the records out
+        "boxes": batch * (px + 2 * px * 4 + 64 * 128),
+        # K7: the source pixels under the boxes in, 32 x crop_w x 3 bf16 per crop out
+        "crop": crop_src_bytes_per_step + crops_per_step * 3 * 32 * CROP_W * 2,
+        # K10: [T, 97] fp32 logits per crop in, ids + length + confidence out
+        "ctc": crops_per_step * ((CROP_W // 4 - 1) * 97 * 4 + 36 + 8),
+    }
+    out = []
+    for st in stages:
+        name = st.get("name")
+        if name not in per_step or not st.get("ms") or steps <= 0:
+            continue
+        ms = st["ms"] / steps
+        gbs = per_step[name] / (ms * 1e-3) / 1e9
+        out.append({"stage": name, "ms_per_step": ms, "algorithmic_bytes_per_step": int(per_step[name]),
+                    "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_gbs})
+    return out
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (pynvml; same counters as nvidia-smi)."""
 
@@ -383,6 +413,14 @@ def main():
         fl = 2.0 * 0
         roof = {"bound": "tensor", "achieved": None, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": None, "traffic": None}
     alg_gf = GF_DET_PER_FRAME + GF_CRNN_PER_CROP * float(counts.mean())
+    hbm_stages = None
+    try:    # reporting only: never let it cost the bench line
+        recs = rec_t[0].cpu().numpy().reshape(B, 64, 128).view(_lib.RECORD_DTYPE).reshape(B, 64)
+        bb = np.concatenate([recs[i]["bbox"][:int(counts[i])] for i in range(B)]).astype(np.int64)
+        crop_src = int(((bb[:, 2] - bb[:, 0]) * (bb[:, 3] - bb[:, 1])).sum()) * 3
+        hbm_stages = hbm_stage_rooflines(prof["stages"], max(3, args.steps // 2), B, int(counts.sum()), crop_src, pk["hbm"])
+    except Exception as ex:
+        print("hbm stage table unavailable: %r" % (ex,), file=sys.stderr)
     if args.profile_out and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
         json.dump({"ms_total": ms_1, "steps": max(3, args.steps // 2), "batch": B, "ops": prof}, open(args.profile_out, "w"), indent=1)
@@ -408,6 +446,7 @@ def main():
                         "d2h_bytes_per_step": B * 64 * 128 + B * 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roof,
                 "cpu_baseline": cpu,
+                "hbm_stages": hbm_stages,
                 "boxes_per_frame": float(counts.mean()),
                 "alg_gflop_per_frame": alg_gf,
                 "e2e_tensor_frac": (alg_gf * 1e9 * value / world) / (pk["tflops"] * 1e12)}

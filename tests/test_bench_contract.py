@@ -48,3 +48,17 @@ def test_reference_arm_other_ranks_print_nothing():
 def test_b200_arm_refuses_without_device():
     r = run_bench("--steps", "1", "--no-cpu-baseline")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_hbm_stage_rooflines_from_a_committed_profile():
+    """bench.py's `hbm_stages` table, computed offline from a committed --profile-out file of the B200 run."""
+    sys.path.insert(0, ROOT)
+    import bench
+    d = json.load(open(os.path.join(ROOT, "profiles", "r01_ops_final_events.json")))
+    rows = bench.hbm_stage_rooflines(d["ops"]["stages"], d["steps"], d["batch"], 800, 800 * 4800 * 3, 6531.9)
+    assert [r["stage"] for r in rows] == ["preprocess", "head_tail", "boxes", "crop", "ctc"]
+    pre = rows[0]
+    assert pre["algorithmic_bytes_per_step"] == 16 * (1080 * 1920 * 3 + 3 * 736 * 1312 * 2)       # SURVEY.md 8d, K1
+    assert pre["achieved_gbs"] == pytest.approx(pre["algorithmic_bytes_per_step"] / (pre["ms_per_step"] * 1e-3) / 1e9)
+    assert all(0 < r["frac_of_hbm_peak"] < 1 for r in rows)
+    assert bench.hbm_stage_rooflines([], 3, 16, 0, 0, 6531.9) == []
