@@ -78,6 +78,8 @@ class VideoTextPipeline:
     # ---- reference surface ----------------------------------------------------------------------------
     async def process_video(self, video_path: str, output_dir: str, progress_callback=None) -> Dict[str, Any]:
         frozen = False
+        # an application that froze its own heap (the prefork gc.freeze() idiom) keeps it: we neither add to nor undo it
+        may_freeze = self.freeze_results and gc.get_freeze_count() == 0
         try:
             start_time = time.time()
             video_info = self.video_processor.get_video_info(video_path)
@@ -94,7 +96,7 @@ class VideoTextPipeline:
                 nonlocal frame_count, frozen
                 task, n = pending.pop(0)
                 all_results.extend(await task)
-                if self.freeze_results and gc.isenabled():
+                if may_freeze and gc.isenabled():
                     gc.freeze()
                     frozen = True
                 frame_count += n
