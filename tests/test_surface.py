@@ -257,6 +257,7 @@ def test_process_video_fused_path_keeps_frame_order_with_batches_in_flight(tmp_p
     async def progress(pr, done, total):
         calls.append(done)
 
+    frozen_before = gc.get_freeze_count()
     with patch.object(p, "detect_and_recognize", side_effect=fake):
         res = asyncio.run(p.process_video(video, str(tmp_path), progress))
     assert res["status"] == "success"
@@ -265,5 +266,5 @@ def test_process_video_fused_path_keeps_frame_order_with_batches_in_flight(tmp_p
     assert [n for n, _ in seen] == [4, 4, 4, 4, 4, 2] and {s for _, s in seen[:5]} == {0, 1, 2}
     assert calls == [4, 8, 12, 16, 20]                              # the reference reports per full batch (:63-65)
     assert res["summary"]["total_frames"] == 22 and res["summary"]["total_detections"] == 22
-    assert gc.isenabled() and gc.get_freeze_count() == 0
+    assert gc.isenabled() and gc.get_freeze_count() <= frozen_before   # nothing of ours left in the permanent generation
     json.dumps(res)

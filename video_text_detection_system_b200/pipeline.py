@@ -78,8 +78,9 @@ class VideoTextPipeline:
     # ---- reference surface ----------------------------------------------------------------------------
     async def process_video(self, video_path: str, output_dir: str, progress_callback=None) -> Dict[str, Any]:
         frozen = False
-        # an application that froze its own heap (the prefork gc.freeze() idiom) keeps it: we neither add to nor undo it
-        may_freeze = self.freeze_results and gc.get_freeze_count() == 0
+        # an application that froze its own heap (the prefork gc.freeze() idiom: 10^5..10^6 objects) keeps it: we neither
+        # add to nor undo it.  A fresh interpreter already holds a few hundred objects in the permanent generation.
+        may_freeze = self.freeze_results and gc.get_freeze_count() < 10000
         try:
             start_time = time.time()
             video_info = self.video_processor.get_video_info(video_path)
