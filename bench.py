@@ -195,7 +195,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"],
+                    help="bf16 = the shipped speed tier; fp16 = the same kernels over IEEE half (libvtd_b200_f16.so); "
+                         "fp32 = the CUDA-core parity tier")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight (contexts/streams/host threads)")
     ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the bounded CPU-baseline sample (~10 s of host time)")
     ap.add_argument("--crop-w", type=int, default=CROP_W, choices=sorted(GF_CRNN),

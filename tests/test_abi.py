@@ -86,3 +86,29 @@ def test_half_storage_variant_builds_and_holds_no_bf16_code():
     out = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True).stdout
     assert "UTCHMMA" in out and "UTMALDG" in out
     assert "BF16" not in out and "F16" in out
+
+
+def test_dtype_fp16_selects_the_half_storage_library(monkeypatch):
+    """Engine(dtype="fp16") = the speed tier (VTD_BF16 enum value) of libvtd_b200_f16.so; "bf16"/"fp32" use the shipped
+    library; both stay loaded side by side."""
+    from video_text_detection_system_b200 import _lib
+    asked = []
+    real = _lib.load_library
+
+    def spy(variant=None):
+        asked.append(variant)
+        return real(variant)
+
+    monkeypatch.setattr(_lib, "load_library", spy)
+    monkeypatch.delenv("VTD_STORAGE", raising=False)
+    for dt in ("fp32", "bf16", "fp16", "half"):
+        if torch.cuda.is_available():
+            _lib.Engine(dtype=dt, det_h=64, det_w=64, max_src_h=64, max_src_w=64)
+        else:
+            with pytest.raises(_lib.VtdError):
+                _lib.Engine(dtype=dt)
+    assert asked == [None, None, "f16", "f16"]
+    a, b = real(""), real("f16")
+    assert a is not b and a is real(None) and a._name.endswith("libvtd_b200.so") and b._name.endswith("libvtd_b200_f16.so")
+    monkeypatch.setenv("VTD_STORAGE", "f16")
+    assert real(None) is b

@@ -68,14 +68,21 @@ def exported_symbols() -> List[str]:
             "vtd_get_records", "vtd_debug_tensor", "vtd_set_profiling", "vtd_op_count", "vtd_op_info"]
 
 
-def load_library():
-    """dlopen libvtd_b200.so (building it first if it is missing and nvcc exists)."""
+_libs: Dict[str, object] = {}
+
+
+def load_library(variant: Optional[str] = None):
+    """dlopen libvtd_b200.so (building it first if it is missing and nvcc exists).  variant: "" = the shipped library
+    (bfloat16 speed tier), "f16" = libvtd_b200_f16.so (IEEE half as the 16-bit storage type, same ABI); None = what the
+    environment variable VTD_STORAGE names, default "".  Both may be loaded in one process (Engine(dtype="fp16"))."""
     global _lib
+    if variant is None:
+        variant = os.environ.get("VTD_STORAGE", "")
+    variant = "" if variant == "bf16" else variant
     with _lib_lock:
-        if _lib is not None:
-            return _lib
+        if variant in _libs:
+            return _libs[variant]
         from .build import build_library, variant_paths
-        variant = os.environ.get("VTD_STORAGE", "")            # "" = shipped bf16 library; "f16" = half-storage build
         path = variant_paths(variant)[1]
         if not os.path.exists(path):
             build_library(variant=variant)
@@ -111,7 +118,9 @@ def load_library():
         lib.vtd_set_profiling.argtypes = [vp, i32]
         lib.vtd_op_count.argtypes = [vp, i32]
         lib.vtd_op_info.argtypes = [vp, i32, i32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
-        _lib = lib
+        _libs[variant] = lib
+        if _lib is None:
+            _lib = lib
         return lib
 
 
@@ -146,10 +155,12 @@ class Engine:
     def __init__(self, device: int = 0, backbone: int = 18, dtype: str = "fp32", det_h: int = 640, det_w: int = 640,
                  crop_w: int = 128, max_batch: int = 1, max_boxes: int = 256, max_src_h: int = 2160,
                  max_src_w: int = 3840, canonical_ctc: bool = False, unclip_ratio: float = 1.0):
-        self.lib = load_library()
+        d = str(dtype).lower()
+        half = d in ("fp16", "f16", "half", "float16")        # the speed tier over IEEE half: the half-storage library
+        self.lib = load_library("f16" if half else None)
         cfg = VtdConfig()
         cfg.device, cfg.backbone = int(device), int(backbone)
-        cfg.dtype = VTD_BF16 if str(dtype).lower() in ("bf16", "bfloat16", "1") else VTD_FP32
+        cfg.dtype = VTD_BF16 if half or d in ("bf16", "bfloat16", "1") else VTD_FP32
         cfg.det_h, cfg.det_w, cfg.crop_w = int(det_h), int(det_w), int(crop_w)
         cfg.max_batch, cfg.max_boxes = int(max_batch), int(max_boxes)
         cfg.max_src_h, cfg.max_src_w = int(max_src_h), int(max_src_w)
