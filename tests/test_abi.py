@@ -112,3 +112,28 @@ def test_dtype_fp16_selects_the_half_storage_library(monkeypatch):
     assert a is not b and a is real(None) and a._name.endswith("libvtd_b200.so") and b._name.endswith("libvtd_b200_f16.so")
     monkeypatch.setenv("VTD_STORAGE", "f16")
     assert real(None) is b
+
+
+def test_header_is_plain_c99_and_layouts_match_the_binding(tmp_path):
+    """include/vtd.h must be consumable from C (cgo / JNI / ctypes users): compiled as C99 with -pedantic, and the
+    struct sizes/offsets a C compiler sees equal the ctypes and NumPy mirrors in _lib.py."""
+    import shutil
+    import subprocess
+    from video_text_detection_system_b200 import _lib
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "vtd.h"\n#include <stddef.h>\n#include <stdio.h>\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vtd_record), sizeof(vtd_config),'
+                   ' sizeof(vtd_tensor), offsetof(vtd_record, det_conf), offsetof(vtd_record, len),'
+                   ' offsetof(vtd_record, ids), offsetof(vtd_record, start_index)); return 0;}\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    R = _lib.VtdRecord
+    assert got == [ctypes.sizeof(R), ctypes.sizeof(_lib.VtdConfig), ctypes.sizeof(_lib.VtdTensor), R.det_conf.offset,
+                   R.len.offset, R.ids.offset, R.start_index.offset]
+    f = _lib.RECORD_DTYPE.fields
+    assert got[3:] == [f["det_conf"][1], f["len"][1], f["ids"][1], f["start_index"][1]]
