@@ -44,3 +44,28 @@ def test_reference_recognizer_agrees_with_port():
     assert R.vocab == port.build_vocab()
     # a 2-D crop makes the reference return the empty result
     assert R.recognize(np.zeros((20, 40), np.uint8)) == {"text": "", "confidence": 0.0}
+
+
+def test_decode_exhaustive_over_a_small_alphabet():
+    """Every argmax sequence of length <= 5 over {blank, '0', '1', <unk>} through the reference's _decode_prediction
+    and the oracle's restatement: same text, same confidence.  Exhaustive over the collapse logic and its quirks
+    (blank does not reset the previous character, <unk> is dropped but becomes the previous character, the confidence
+    is indexed by emitted count)."""
+    import itertools
+    R = RL.reference_recognizer()
+    V = len(R.vocab)
+    symbols = [0, 1, 2, V - 1]
+    rng = np.random.default_rng(0)
+    n = 0
+    for T in range(1, 6):
+        for seq in itertools.product(symbols, repeat=T):
+            p = rng.random((T, V)).astype(np.float32) * 0.5
+            p[np.arange(T), list(seq)] = 0.5 + rng.random(T).astype(np.float32) * 0.5      # argmax = seq
+            p /= p.sum(1, keepdims=True)
+            t = torch.from_numpy(p)
+            text_ref, conf_ref = R._decode_prediction(t)
+            text, conf, ids = port.decode_prediction(t)
+            assert text == text_ref and conf == pytest.approx(conf_ref, abs=1e-7), seq
+            assert "".join(port.CHARS[i - 1] for i in ids) == text
+            n += 1
+    assert n == sum(4 ** T for T in range(1, 6))
