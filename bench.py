@@ -12,6 +12,11 @@ A step is one batch of --batch frames through the whole path.
   roofline     : dominant kernel (tcgen05 implicit-GEMM conv, all launches of the timed region), algorithmic
                  FLOPs / CUDA-event time, against MEASURED_PEAKS.json bf16_tflops_sustained
   cpu_baseline : oracle/port.py (the reference's PyTorch/PIL/OpenCV arithmetic) on the host cores, bounded sample
+  hbm_stages   : the non-GEMM stages (preprocess, DB head tail, box extraction, crop gather, CTC): algorithmic bytes
+                  / CUDA-event time against MEASURED_PEAKS.json hbm_gbs
+
+`--crop-w 100` runs BASELINE's wording of configs[2] (32x100 crops; default 128 = the reference's own width, the larger
+workload).  `--dtype fp16` runs the speed tier of the half-storage library (libvtd_b200_f16.so).
 
 `--impl reference` times that CPU path alone (one frame per step).  N>1: one process per GPU (torchrun), frames
 sharded by rank, records gathered to rank 0 every step with NCCL; time = max over ranks.
