@@ -156,6 +156,27 @@ def cpu_frame(port, det, rec, frame, bias):
                               per_crop=True)
 
 
+CPU_WORKERS = 4     # the reference detects frames on ThreadPoolExecutor(max_workers=4) (pipeliine.py:32,96-101)
+
+
+def cpu_frames(port, det, rec, frames, bias):
+    """`frames` through the reference's path with every host thread in use: CPU_WORKERS frames in parallel (the
+    reference's executor width), each with cores/CPU_WORKERS intra-op torch threads -- measured faster than one frame at
+    a time on all cores (0.94 vs 0.74 frames/s on 8 cores).  Returns the number of text regions found."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // CPU_WORKERS))
+    with ThreadPoolExecutor(CPU_WORKERS) as ex:
+        return sum(ex.map(lambda f: len(cpu_frame(port, det, rec, f, bias)), frames))
+
+
+def cpu_sample_text(n_frames, boxes):
+    cores = os.cpu_count() or 1
+    return ("%d frames of the same workload, %d frames in parallel (the reference's ThreadPoolExecutor(4)) x %d torch "
+            "threads each = %d cores, per-frame detect + per-crop recognise as pipeliine.py:117-125, %.1f boxes/frame"
+            % (n_frames, CPU_WORKERS, max(1, cores // CPU_WORKERS), cores, boxes / max(n_frames, 1)))
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -163,12 +184,10 @@ def run_reference_arm(args, rank, world):
     n = args.warmup + args.steps
     frames = port.synthetic_frames(min(n, 4), SRC_H, SRC_W, seed=0)
     bias = port.planted_logit_bias(1, DET_H, DET_W, seed=0, boxes=BOXES)[0]
-    for i in range(args.warmup):
-        cpu_frame(port, det, rec, frames[i % len(frames)], bias)
+    if args.warmup:
+        cpu_frames(port, det, rec, [frames[i % len(frames)] for i in range(args.warmup)], bias)
     t0 = time.perf_counter()
-    nb = 0
-    for i in range(args.steps):
-        nb += len(cpu_frame(port, det, rec, frames[(args.warmup + i) % len(frames)], bias))
+    nb = cpu_frames(port, det, rec, [frames[(args.warmup + i) % len(frames)] for i in range(args.steps)], bias)
     dt = time.perf_counter() - t0
     fps = args.steps / dt
     cores = os.cpu_count() or 1
@@ -177,8 +196,7 @@ def run_reference_arm(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.batch, 1),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": "%d frames, 1 frame per step, per-crop recognise as pipeliine.py:117-125, "
-                                       "%.1f boxes/frame" % (args.steps, nb / max(args.steps, 1))},
+                             "sample": "1 frame per step; " + cpu_sample_text(args.steps, nb)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -437,13 +455,12 @@ def main():
         p2, det, rec = cpu_models()
         fr = host_pool[:max(1, args.cpu_frames)].numpy()
         b0 = bias[0].cpu().numpy()
-        cpu_frame(p2, det, rec, fr[0], b0)                          # warm-up
+        cpu_frames(p2, det, rec, list(fr[:CPU_WORKERS]), b0)       # warm-up
         t0 = time.perf_counter()
-        nb = sum(len(cpu_frame(p2, det, rec, f, b0)) for f in fr)
+        nb = cpu_frames(p2, det, rec, list(fr), b0)
         dt = time.perf_counter() - t0
         cpu = {"value": len(fr) / dt, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "%d frames of the same workload, reference-style per-frame detect + per-crop recognise, "
-                         "%.1f boxes/frame, torch threads=%d" % (len(fr), nb / len(fr), os.cpu_count() or 1)}
+               "sample": cpu_sample_text(len(fr), nb)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
