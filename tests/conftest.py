@@ -46,8 +46,8 @@ def host_harness():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libhostharness.so")
     src = os.path.join(ROOT, "tests", "host_harness.cpp")
-    hdr = os.path.join(ROOT, "video_text_detection_system_b200", "csrc", "box_geom.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "video_text_detection_system_b200", "csrc", h) for h in ("box_geom.cuh", "resize_tab.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-x", "c++", src,
                                "-o", so])
     return ctypes.CDLL(so)

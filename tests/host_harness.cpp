@@ -9,6 +9,7 @@
 #include <vector>
 #include <algorithm>
 #include "../video_text_detection_system_b200/csrc/box_geom.cuh"
+#include "../video_text_detection_system_b200/csrc/resize_tab.h"
 
 using namespace vtd::geom;
 
@@ -102,4 +103,19 @@ extern "C" int hh_hull_rows(const int* rowmin, const int* rowmax, int y0, int nr
   int nh = hull_from_rows(rowmin, rowmax, y0, nrows, hull.data());
   for (int i = 0; i < nh; ++i) { out_xy[2 * i] = hull[i].x; out_xy[2 * i + 1] = hull[i].y; }
   return nh;
+}
+
+
+// The product's Pillow coefficient tables (csrc/resize_tab.h, what vtd_preprocess uploads for the resize kernel).
+// lo/cnt: [out_size]; kk: [out_size * ksize_cap] (rows padded with zeros); returns ksize, or -1 if ksize > ksize_cap.
+extern "C" int hh_resize_tab(int in_size, int out_size, int* lo, int* cnt, int* kk, int ksize_cap, int* maxcnt) {
+  std::vector<int> l, c, k;
+  int ksize = 0;
+  vtd::compute_resize_tab(in_size, out_size, &l, &c, &k, &ksize, maxcnt);
+  if (ksize > ksize_cap) return -1;
+  for (int i = 0; i < out_size; ++i) {
+    lo[i] = l[i]; cnt[i] = c[i];
+    for (int x = 0; x < ksize_cap; ++x) kk[(size_t)i * ksize_cap + x] = x < ksize ? k[(size_t)i * ksize + x] : 0;
+  }
+  return ksize;
 }

@@ -137,3 +137,29 @@ def test_shape_sweep_matches_cv2(host_harness):
             assert np.array_equal(np.array(list(c.box), np.float32).reshape(4, 2), box), (name, start)
             boxes += 1
     assert boxes >= 300
+
+
+def test_resize_coefficient_tables_match_the_oracle(host_harness):
+    """csrc/resize_tab.h (the tables vtd_preprocess uploads for the Pillow-exact resize kernel) against the oracle's
+    pillow_coeffs -- which the size sweeps of tests/test_oracle_golden.py hold to Pillow itself -- for the BASELINE frame and
+    detector sizes and a seeded sweep of up- and down-scaling ratios: first tap, tap count and every 22-bit weight."""
+    from oracle import port
+    rng = np.random.default_rng(3)
+    pairs = [(1080, 736), (1920, 1312), (2160, 2176), (3840, 3840), (720, 736), (1280, 1312), (480, 640), (640, 640),
+             (360, 320), (540, 480), (1, 32), (2, 64), (3, 256), (5000, 32), (4320, 736), (7680, 1312), (641, 640), (639, 640)]
+    pairs += [(int(rng.integers(1, 4000)), int(rng.integers(1, 70)) * 32) for _ in range(60)]
+    host_harness.hh_resize_tab.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_int, ctypes.c_void_p]
+    for n_in, n_out in pairs:
+        lo_w, cnt_w, kk_w = port.pillow_coeffs(n_in, n_out)
+        ks = kk_w.shape[1]
+        lo = np.zeros(n_out, np.int32)
+        cnt = np.zeros(n_out, np.int32)
+        kk = np.zeros((n_out, ks), np.int32)
+        mx = ctypes.c_int(0)
+        got_ks = host_harness.hh_resize_tab(n_in, n_out, lo.ctypes.data, cnt.ctypes.data, kk.ctypes.data, ks, ctypes.byref(mx))
+        assert got_ks == ks, (n_in, n_out)
+        assert np.array_equal(lo, lo_w) and np.array_equal(cnt, cnt_w), (n_in, n_out)
+        assert np.array_equal(kk, kk_w), (n_in, n_out, int(np.abs(kk - kk_w).max()))
+        assert mx.value == int(cnt_w.max())
+        assert np.all(np.abs(kk.sum(1) - (1 << 22)) <= ks)            # rows sum to 1.0 in 22-bit fixed point, up to rounding

@@ -6,6 +6,7 @@
 // a batch is a fixed sequence of launches with no allocation, no shape logic and no host<->device sync
 // except the one that returns the per-frame box counts before the recogniser is sized.
 #include "common.cuh"
+#include "resize_tab.h"
 #include "../../include/vtd.h"
 
 #include <math.h>
@@ -329,36 +330,11 @@ void reg_dbg_lay(vtd_ctx* c, const char* name, const void* p, int C, int H, int 
   c->dbg[name] = DebugEntry{p, C, H, W, lay, false, per_crop};
 }
 
-// ---- Pillow resize coefficient tables (ImagingResample precompute_coeffs + normalize_coeffs_8bpc) ----
+// ---- Pillow resize coefficient tables: resize_tab.h (host-only, also compiled into the CPU test harness) ----
 int build_tab(vtd_ctx* c, int in_size, int out_size, ResizeTab* t) {
-  const double scale = (double)in_size / (double)out_size;
-  const double fs = scale < 1.0 ? 1.0 : scale;
-  const double support = 1.0 * fs;
-  const int ksize = (int)ceil(support) * 2 + 1;
-  std::vector<int> lo(out_size), cnt(out_size), kk((size_t)out_size * ksize, 0);
-  std::vector<double> w(ksize);
-  const double ss = 1.0 / fs;
-  int maxcnt = 0;
-  for (int xx = 0; xx < out_size; ++xx) {
-    double center = (xx + 0.5) * scale;
-    int xmin = (int)(center - support + 0.5); if (xmin < 0) xmin = 0;
-    int xmax = (int)(center + support + 0.5); if (xmax > in_size) xmax = in_size;
-    int n = xmax - xmin;
-    double ww = 0.0;
-    for (int x = 0; x < n; ++x) {
-      double a = (x + xmin - center + 0.5) * ss;
-      if (a < 0.0) a = -a;
-      double v = a < 1.0 ? 1.0 - a : 0.0;
-      w[x] = v; ww += v;
-    }
-    for (int x = 0; x < n; ++x) {
-      double v = w[x];
-      if (ww != 0.0) v /= ww;
-      kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (double)(1 << 22)) : (int)(0.5 + v * (double)(1 << 22));
-    }
-    lo[xx] = xmin; cnt[xx] = n;
-    if (n > maxcnt) maxcnt = n;
-  }
+  std::vector<int> lo, cnt, kk;
+  int ksize = 0, maxcnt = 0;
+  compute_resize_tab(in_size, out_size, &lo, &cnt, &kk, &ksize, &maxcnt);
   if (t->lo) { cudaFree(t->lo); cudaFree(t->cnt); cudaFree(t->kk); t->lo = t->cnt = t->kk = nullptr; }
   CK(cudaMalloc(&t->lo, out_size * 4)); CK(cudaMalloc(&t->cnt, out_size * 4)); CK(cudaMalloc(&t->kk, kk.size() * 4));
   CK(cudaMemcpyAsync(t->lo, lo.data(), out_size * 4, cudaMemcpyHostToDevice, c->stream));
