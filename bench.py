@@ -143,10 +143,16 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_models():
+    """The oracle's PyTorch modules holding the SAME random-init weights the B200 arm loads (synthetic.random_state_dicts)."""
     import torch
     from oracle import port
+    from video_text_detection_system_b200 import synthetic
     torch.set_num_threads(os.cpu_count() or 1)
-    return port, port.build_dbnet("resnet18", seed=0), port.build_crnn(seed=0)
+    det_sd, rec_sd = synthetic.random_state_dicts(seed=0)
+    det, rec = port.build_dbnet("resnet18", seed=0), port.build_crnn(seed=0)
+    det.load_state_dict(det_sd)
+    rec.load_state_dict(rec_sd)
+    return port, det.eval(), rec.eval()
 
 
 def cpu_frame(port, det, rec, frame, bias):
@@ -241,8 +247,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from oracle import port                       # synthetic workload generators only (frames, planted plane)
-    from video_text_detection_system_b200 import _lib, parallel
+    from video_text_detection_system_b200 import _lib, parallel, synthetic     # the oracle is not imported on this arm
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device visible (there is no CPU fallback)")
@@ -253,8 +258,7 @@ def main():
     B = args.batch
     POOL = 32
     NW = max(1, args.inflight)                    # batches in flight: one context + stream + host thread each
-    det_sd = port.build_dbnet("resnet18", seed=0).state_dict()
-    rec_sd = port.build_crnn(seed=0).state_dict()
+    det_sd, rec_sd = synthetic.random_state_dicts(seed=0)     # random-init weights of the reference architecture
     engines = []
     for _ in range(NW):
         e = _lib.Engine(device=local_rank, backbone=18, dtype=args.dtype, det_h=DET_H, det_w=DET_W, crop_w=CROP_W,
@@ -270,7 +274,7 @@ def main():
     rng = np.random.default_rng(1000 + rank)
     host_pool = torch.from_numpy(rng.integers(0, 256, (POOL, SRC_H, SRC_W, 3), dtype=np.uint8)).pin_memory()
     dev_pool = host_pool.to(dev)
-    bias = torch.from_numpy(port.planted_logit_bias(B, DET_H, DET_W, seed=7 + rank, boxes=BOXES)).to(dev)
+    bias = torch.from_numpy(synthetic.planted_logit_bias(B, DET_H, DET_W, seed=7 + rank, boxes=BOXES)).to(dev)
     frame_bytes = SRC_H * SRC_W * 3
     import ctypes as C
     import queue

@@ -40,6 +40,8 @@ import torch
 import torch.nn as nn
 import torchvision
 
+from video_text_detection_system_b200.synthetic import planted_logit_bias, randomize_bn, synthetic_frames  # noqa: F401
+
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 CHARS = "0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~ "
@@ -127,20 +129,6 @@ def dbnet_forward(net, x: torch.Tensor, logit_bias: Optional[torch.Tensor] = Non
     if return_feats:
         out.update(c2=c2, c3=c3, c4=c4, c5=c5, p2_in=last, p2=p2)
     return out
-
-
-def randomize_bn(module: nn.Module, seed: int) -> None:
-    """Parity value distribution of SURVEY.md 8d: default-init BN is an identity
-    and would hide folding bugs, so give every BN non-trivial statistics."""
-    g = torch.Generator().manual_seed(seed)
-    for m in module.modules():
-        if isinstance(m, nn.BatchNorm2d):
-            n = m.num_features
-            m.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
-            m.running_var.copy_(torch.rand(n, generator=g) + 0.5)
-            with torch.no_grad():
-                m.weight.copy_(torch.rand(n, generator=g) + 0.5)
-                m.bias.copy_(torch.randn(n, generator=g) * 0.1)
 
 
 def build_dbnet(backbone: str = "resnet18", seed: int = 0, random_bn: bool = True) -> OracleDBNet:
@@ -453,33 +441,5 @@ def process_frame(det_net, rec_net, frame: np.ndarray, threshold: float = 0.5,
 # ----------------------------------------------------------------------------
 # Synthetic workloads
 # ----------------------------------------------------------------------------
-def synthetic_frames(n: int, h: int, w: int, seed: int = 0) -> np.ndarray:
-    return np.random.default_rng(seed).integers(0, 256, (n, h, w, 3), dtype=np.uint8)
-
-
-def planted_logit_bias(n: int, det_h: int, det_w: int, seed: int = 0, boxes: int = 50,
-                       inside: float = 8.0, outside: float = -8.0) -> np.ndarray:
-    """Config 3's planted logit plane: `boxes` rotated rectangles per frame on a
-    jittered 10x5 grid, w~U[60,100], h~U[20,36] det-px, angle~U[-15,15] degrees.
-    Returns [n, det_h, det_w] fp32 with +inside / outside values."""
-    rng = np.random.default_rng(seed)
-    out = np.full((n, det_h, det_w), outside, np.float32)
-    gx, gy = 10, 5
-    cw, ch = det_w / gx, det_h / gy
-    for f in range(n):
-        m = np.zeros((det_h, det_w), np.uint8)
-        k = 0
-        for j in range(gy):
-            for i in range(gx):
-                if k >= boxes:
-                    break
-                w = rng.uniform(60, 100)
-                h = rng.uniform(20, 36)
-                a = rng.uniform(-15, 15)
-                cx = (i + 0.5) * cw + rng.uniform(-8, 8)
-                cy = (j + 0.5) * ch + rng.uniform(-8, 8)
-                pts = cv2.boxPoints(((float(cx), float(cy)), (float(w), float(h)), float(a)))
-                cv2.fillPoly(m, [np.round(pts).astype(np.int32)], 1)
-                k += 1
-        out[f][m > 0] = inside
-    return out
+# synthetic_frames, planted_logit_bias and randomize_bn are input generators shared with bench.py's B200 arm: they live in
+# video_text_detection_system_b200/synthetic.py (imported at the top) so that the product side never imports the oracle.

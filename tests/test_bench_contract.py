@@ -62,3 +62,44 @@ def test_hbm_stage_rooflines_from_a_committed_profile():
     assert pre["achieved_gbs"] == pytest.approx(pre["algorithmic_bytes_per_step"] / (pre["ms_per_step"] * 1e-3) / 1e9)
     assert all(0 < r["frac_of_hbm_peak"] < 1 for r in rows)
     assert bench.hbm_stage_rooflines([], 3, 16, 0, 0, 6531.9) == []
+
+
+def test_oracle_is_only_imported_where_it_may_be():
+    """The product package never imports oracle/, and bench.py imports it only inside cpu_models() (the cpu_baseline
+    leg and the reference arm); the B200 arm draws weights, frames and the planted plane from the package's synthetic.py."""
+    import ast
+    import glob
+    pkg = os.path.join(ROOT, "video_text_detection_system_b200")
+    for path in glob.glob(os.path.join(pkg, "*.py")):
+        tree = ast.parse(open(path).read())
+        for n in ast.walk(tree):
+            if isinstance(n, ast.ImportFrom):
+                assert (n.module or "").split(".")[0] != "oracle", path
+            if isinstance(n, ast.Import):
+                assert all(a.name.split(".")[0] != "oracle" for a in n.names), path
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    where = []
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        for n in ast.walk(fn):
+            if isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle":
+                where.append(fn.name)
+    assert where == ["cpu_models"]
+    assert not any(isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n) for n in tree.body)
+
+
+def test_synthetic_workload_is_seeded_and_plants_fifty_boxes():
+    """bench.py's inputs: the random-init state dicts are deterministic and in the reference's key layout, and on the CPU
+    path (oracle) the planted plane yields exactly the workload's 50 boxes per frame with these weights."""
+    from oracle import port
+    from video_text_detection_system_b200 import synthetic
+    a, ar = synthetic.random_state_dicts(seed=0)
+    b, br = synthetic.random_state_dicts(seed=0)
+    assert all(torch.equal(a[k], b[k]) for k in a) and all(torch.equal(ar[k], br[k]) for k in ar)
+    det, rec = port.build_dbnet("resnet18", seed=0), port.build_crnn(seed=0)
+    assert list(det.state_dict()) == list(a) and list(rec.state_dict()) == list(ar)
+    det.load_state_dict(a)
+    rec.load_state_dict(ar)
+    frame = synthetic.synthetic_frames(1, 1080, 1920, seed=5)[0]
+    bias = synthetic.planted_logit_bias(1, 736, 1312, seed=7, boxes=50)
+    regions = port.process_frame(det.eval(), rec.eval(), frame, 0.5, 736, 1312, 128, torch.from_numpy(bias)[None], per_crop=False)
+    assert len(regions) == 50
