@@ -37,9 +37,11 @@ enum {
 };
 
 enum { VTD_FP32 = 0,     /* fp32 activations, CUDA-core FFMA implicit GEMM: the <=1e-3 parity tier */
-       VTD_BF16 = 1 };   /* 16-bit activations, tcgen05/TMEM implicit GEMM fed by TMA: the speed tier.  bfloat16 in
-                            libvtd_b200.so; libvtd_b200_f16.so (-DVTD_HALF_STORAGE, same sources and ABI) stores IEEE
-                            half instead: ~8x smaller rounding error, half's range (profiles/r01_f16_variant.md) */
+       VTD_16BIT = 1,    /* 16-bit activations, fp32 accumulate, tcgen05/TMEM implicit GEMM fed by TMA: the speed tier.  IEEE
+                            half in libvtd_b200.so (maps within 2e-3 of the fp32 reference); libvtd_b200_bf16.so
+                            (-DVTD_BF16_STORAGE, same sources and ABI) stores bfloat16 instead: fp32's range, ~8x the
+                            rounding error (profiles/r01_bf16_error_budget.md) */
+       VTD_BF16 = 1 };   /* round-1 name of VTD_16BIT */
 
 enum { VTD_IDS_STRIDE = 64 }; /* row pitch of the ids_out arrays of the decode / recognise drop-ins */
 
@@ -49,7 +51,7 @@ enum { VTD_PIX_BGR = 0,  /* HxWx3 uint8, B,G,R interleaved (cv2 frames; text_det
 typedef struct vtd_config {
   int32_t device;         /* CUDA ordinal */
   int32_t backbone;       /* 18 or 50  (text_detector.py:16-20; resnet18 per BASELINE configs 1-4) */
-  int32_t dtype;          /* VTD_FP32 | VTD_BF16 */
+  int32_t dtype;          /* VTD_FP32 | VTD_16BIT */
   int32_t det_h, det_w;   /* detector input size, multiples of 32; the reference hard-codes 640x640
                              (text_detector.py:101) */
   int32_t crop_w;         /* recogniser crop width: 128 = reference (text_recognizer.py:118), 100 = BASELINE cfg 3 */
@@ -158,7 +160,10 @@ int  vtd_run_batch(vtd_ctx* ctx, const uint8_t* const* frames, int n, int h, int
                    int frames_on_device, float thr, const float* logit_bias_dev, int recognize,
                    vtd_record* records_host, int* counts_host);
 int  vtd_read_records(vtd_ctx* ctx, int n, vtd_record* records_host, int* counts_host);
-int  vtd_get_records(vtd_ctx* ctx, vtd_record** records_dev, int** counts_dev); /* [max_batch*max_boxes], [max_batch] */
+/* Device pointers of the results: records [max_batch*max_boxes], counts [max_batch].  The counts directly follow the
+ * records (counts_dev == (int*)(records_dev + max_batch*max_boxes)), so a rank's results are one contiguous block of
+ * max_batch*(max_boxes*128 + 4) bytes: one collective gathers them (parallel.gather_packed). */
+int  vtd_get_records(vtd_ctx* ctx, vtd_record** records_dev, int** counts_dev);
 
 /* ---- parity harness: copy a named intermediate to the host as fp32 NCHW.
  * names: "input","c2","c3","c4","c5","p2_in","p2","head","crops","cnn","rnn0","rnn1","logits". */

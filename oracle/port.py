@@ -229,11 +229,25 @@ def preprocess_restated(image: np.ndarray, det_h: int, det_w: int) -> np.ndarray
 # ----------------------------------------------------------------------------
 # Detector post-processing (text_detector.py:143-178)
 # ----------------------------------------------------------------------------
+def unclip_rect(rect, ratio: float):
+    """north_star's "unclip" (an extension: the reference has none): grow a min-area rect by the
+    DB offset d = area * ratio / perimeter on every side, float32 op for op as csrc/box_geom.cuh unclip_rect."""
+    (cx, cy), (w, h), ang = rect
+    w, h, r = np.float32(w), np.float32(h), np.float32(ratio)
+    per = np.float32(2.0) * (w + h)
+    if not (ratio > 1.0) or not (per > 0):
+        return rect
+    d = (w * h) * r / per
+    two_d = np.float32(2.0) * d
+    return (cx, cy), (float(w + two_d), float(h + two_d)), ang
+
+
 def post_process(prob_map: np.ndarray, orig_width: int, orig_height: int, threshold: float,
-                 det_h: Optional[int] = None, det_w: Optional[int] = None) -> List[Dict]:
+                 det_h: Optional[int] = None, det_w: Optional[int] = None, unclip_ratio: float = 1.0) -> List[Dict]:
     """_post_process with 640 -> (det_h, det_w).  The reference hard-codes 640 even
     when the map has another size (tests/test_models.py:51 passes 160x160); that
-    behaviour is reproduced when det_h/det_w are left None (=640)."""
+    behaviour is reproduced when det_h/det_w are left None (=640).  unclip_ratio = 1.0
+    (the default) is the reference verbatim."""
     det_h = 640 if det_h is None else det_h
     det_w = 640 if det_w is None else det_w
     binary_map = (prob_map > threshold).astype(np.uint8) * 255            # :144 strict >
@@ -243,6 +257,8 @@ def post_process(prob_map: np.ndarray, orig_width: int, orig_height: int, thresh
         if cv2.contourArea(contour) < 100:                                  # :150
             continue
         rect = cv2.minAreaRect(contour)
+        if unclip_ratio > 1.0:
+            rect = unclip_rect(rect, unclip_ratio)
         box = cv2.boxPoints(rect).astype(np.intp)                           # :153-155 (np.int0)
         xs, ys = box[:, 0], box[:, 1]
         x1, y1 = max(0, int(np.min(xs))), max(0, int(np.min(ys)))           # :160

@@ -97,6 +97,16 @@ extern "C" int hh_components(const uint8_t* mask, int h, int w, HhComp* out, int
   return count;
 }
 
+// unclip + boxPoints of a min-area rect as the product computes them (box_geom.cuh unclip_rect / box_points)
+extern "C" void hh_unclip_box(const float* rect5, float ratio, float* out_rect5, float* out_box8) {
+  RotRect rr = {rect5[0], rect5[1], rect5[2], rect5[3], rect5[4]};
+  unclip_rect(rr, ratio);
+  out_rect5[0] = rr.cx; out_rect5[1] = rr.cy; out_rect5[2] = rr.w; out_rect5[3] = rr.h; out_rect5[4] = rr.angle;
+  PtF bp[4];
+  box_points(rr, bp);
+  for (int k = 0; k < 4; ++k) { out_box8[2 * k] = bp[k].x; out_box8[2 * k + 1] = bp[k].y; }
+}
+
 // hull of an arbitrary point list given as row extremes (for direct comparison with cv2.convexHull)
 extern "C" int hh_hull_rows(const int* rowmin, const int* rowmax, int y0, int nrows, int* out_xy) {
   std::vector<Pt> hull(2 * nrows + 2);

@@ -70,13 +70,14 @@ def test_bad_config_rejected(lib_built):
             _lib.Engine(**kw)
 
 
-def test_half_storage_variant_builds_and_holds_no_bf16_code():
-    """libvtd_b200_f16.so (-DVTD_HALF_STORAGE, selected with VTD_STORAGE=f16): same exports, tcgen05/TMA present, and
-    not one BF16 conversion or BF16-typed MMA left in its SASS (the shipped library holds hundreds)."""
+def test_storage_variants_hold_only_their_own_16bit_type(lib_built):
+    """The shipped library stores IEEE half in its speed tier: not one BF16 conversion or BF16-typed MMA in its SASS.
+    libvtd_b200_bf16.so (-DVTD_BF16_STORAGE, selected with dtype="bf16" / VTD_STORAGE=bf16): same exports, tcgen05/TMA
+    present, BF16 conversions present."""
     import shutil
     import subprocess
     from video_text_detection_system_b200.build import build_library
-    path = build_library(variant="f16")
+    path = build_library(variant="bf16")
     lib = ctypes.CDLL(path)
     for name in header_functions():
         assert hasattr(lib, name), name
@@ -84,13 +85,22 @@ def test_half_storage_variant_builds_and_holds_no_bf16_code():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     out = subprocess.run([cuobjdump, "-sass", path], capture_output=True, text=True).stdout
-    assert "UTCHMMA" in out and "UTMALDG" in out
-    assert "BF16" not in out and "F16" in out
+    assert "UTCHMMA" in out and "UTMALDG" in out and "BF16" in out
+    shipped = subprocess.run([cuobjdump, "-sass", lib_built], capture_output=True, text=True).stdout
+    assert "BF16" not in shipped and "F16" in shipped
 
 
-def test_dtype_fp16_selects_the_half_storage_library(monkeypatch):
-    """Engine(dtype="fp16") = the speed tier (VTD_BF16 enum value) of libvtd_b200_f16.so; "bf16"/"fp32" use the shipped
-    library; both stay loaded side by side."""
+def test_release_library_reads_no_tuning_environment(lib_built):
+    """The VTD_DBG / VTD_NO_* / VTD_TILE ... experiment switches exist only in -DVTD_DEV builds (csrc/common.cuh dev_env):
+    none of their names survives in the release binary."""
+    blob = open(lib_built, "rb").read()
+    for name in (b"VTD_DBG", b"VTD_NO_HALO", b"VTD_TILE", b"VTD_KPS", b"VTD_CTA2", b"VTD_NO_WIN", b"VTD_TC_STAGES"):
+        assert name not in blob, name
+
+
+def test_dtype_selects_the_storage_library(monkeypatch):
+    """Engine(dtype="fp16") = the speed tier of the shipped library (IEEE half); "bf16" = the speed tier of
+    libvtd_b200_bf16.so; "fp32" / "16bit" take the process default (VTD_STORAGE); both libraries stay loaded side by side."""
     from video_text_detection_system_b200 import _lib
     asked = []
     real = _lib.load_library
@@ -101,16 +111,20 @@ def test_dtype_fp16_selects_the_half_storage_library(monkeypatch):
 
     monkeypatch.setattr(_lib, "load_library", spy)
     monkeypatch.delenv("VTD_STORAGE", raising=False)
-    for dt in ("fp32", "bf16", "fp16", "half"):
+    for dt in ("fp32", "16bit", "fp16", "half", "bf16"):
         if torch.cuda.is_available():
-            _lib.Engine(dtype=dt, det_h=64, det_w=64, max_src_h=64, max_src_w=64)
+            e = _lib.Engine(dtype=dt, det_h=64, det_w=64, max_src_h=64, max_src_w=64)
+            assert e.dtype == {"fp32": "fp32", "16bit": "fp16", "fp16": "fp16", "half": "fp16", "bf16": "bf16"}[dt]
         else:
             with pytest.raises(_lib.VtdError):
                 _lib.Engine(dtype=dt)
-    assert asked == [None, None, "f16", "f16"]
-    a, b = real(""), real("f16")
-    assert a is not b and a is real(None) and a._name.endswith("libvtd_b200.so") and b._name.endswith("libvtd_b200_f16.so")
-    monkeypatch.setenv("VTD_STORAGE", "f16")
+    assert asked == [None, None, "", "", "bf16"]
+    with pytest.raises(ValueError):
+        _lib.Engine(dtype="int8")
+    a, b = real(""), real("bf16")
+    assert a is not b and a is real(None) and a is real("f16")
+    assert a._name.endswith("libvtd_b200.so") and b._name.endswith("libvtd_b200_bf16.so")
+    monkeypatch.setenv("VTD_STORAGE", "bf16")
     assert real(None) is b
 
 

@@ -77,6 +77,43 @@ def test_shard_and_gather_world4_with_idle_and_ragged_ranks(tmp_path, n_frames):
     assert open(out).read() == "ok"
 
 
+def _worker_packed(rank, world, port, n_frames, kmax, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = parallel.shard_indices(n_frames, rank, world)
+        per = parallel.frames_per_rank(n_frames, world)
+        recs = np.zeros((per, kmax), _lib.RECORD_DTYPE)
+        cnts = np.zeros(per, np.int32)
+        for i, g in enumerate(mine):
+            recs[i], cnts[i] = _fake_records(g, kmax)
+        # the library's layout: the counts directly follow the records (vtd_get_records)
+        block = torch.from_numpy(np.concatenate([recs.view(np.uint8).reshape(-1), cnts.view(np.uint8)]))
+        assert block.numel() == parallel.packed_bytes(per, kmax)
+        got = parallel.gather_packed(block, dst=0)
+        if rank == 0:
+            r, c = parallel.split_packed(got, per, kmax)
+            merged = parallel.merge_gathered(r, c, n_frames, kmax, _lib.RECORD_DTYPE)
+            ok = int(c.sum()) == sum(g % (kmax + 1) for g in range(n_frames))
+            for g in range(n_frames):
+                want, cnt = _fake_records(g, kmax)
+                ok = ok and len(merged[g]) == cnt and merged[g].tobytes() == want[:cnt].tobytes()
+            open(out_path, "w").write("ok" if ok else "mismatch")
+        else:
+            assert got is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames", [(2, 8), (2, 7), (4, 9)])
+def test_single_collective_gather_of_packed_blocks(tmp_path, world, n_frames):
+    """bench.py's N>1 path: one collective per step carrying records and counts in one block."""
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_worker_packed, args=(world, _free_port(), n_frames, 5, out), nprocs=world, join=True)
+    assert open(out).read() == "ok"
+
+
 def test_shard_indices_cover_everything():
     for n in (0, 1, 5, 16, 3000):
         for w in (1, 2, 4, 8):

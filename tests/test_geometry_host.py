@@ -163,3 +163,29 @@ def test_resize_coefficient_tables_match_the_oracle(host_harness):
         assert np.array_equal(kk, kk_w), (n_in, n_out, int(np.abs(kk - kk_w).max()))
         assert mx.value == int(cnt_w.max())
         assert np.all(np.abs(kk.sum(1) - (1 << 22)) <= ks)            # rows sum to 1.0 in 22-bit fixed point, up to rounding
+
+
+def test_unclip_matches_the_stated_formula(host_harness):
+    """north_star's unclip (an extension; ratio 1.0 = the reference): the product's unclip_rect + box_points against the
+    oracle's statement of the same formula (d = w*h*ratio / (2(w+h)), float32) followed by cv2.boxPoints, bit for bit,
+    over random rotated rects; ratio <= 1 leaves the rect untouched."""
+    import cv2
+    from oracle import port
+    host_harness.hh_unclip_box.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+    host_harness.hh_unclip_box.restype = None
+    rng = np.random.default_rng(5)
+    for i in range(400):
+        rect = ((float(np.float32(rng.uniform(20, 1200))), float(np.float32(rng.uniform(20, 700)))),
+                (float(np.float32(rng.uniform(5, 300))), float(np.float32(rng.uniform(5, 120)))),
+                float(np.float32(rng.uniform(-90, 0))))
+        for ratio in (1.0, 0.5, 1.5, 2.0):
+            r5 = np.asarray([rect[0][0], rect[0][1], rect[1][0], rect[1][1], rect[2]], np.float32)
+            o5, o8 = np.zeros(5, np.float32), np.zeros(8, np.float32)
+            host_harness.hh_unclip_box(r5.ctypes.data, ratio, o5.ctypes.data, o8.ctypes.data)
+            want = port.unclip_rect(rect, ratio)
+            assert (o5[2], o5[3]) == (np.float32(want[1][0]), np.float32(want[1][1])), (rect, ratio)
+            if ratio <= 1.0:
+                assert np.array_equal(o5, r5)
+            else:
+                assert o5[2] > r5[2] and o5[3] > r5[3]
+            assert np.array_equal(o8.reshape(4, 2), cv2.boxPoints(want)), (rect, ratio)

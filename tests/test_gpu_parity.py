@@ -2,7 +2,7 @@
 (oracle/port.py) and the golden vectors minted from the reference's own code (tests/golden/*.npz).
 
 Tolerances (BASELINE.json north_star): probability/threshold maps <= 1e-3 abs in the fp32 tier, <= 1e-2 in
-bf16; identical masks away from threshold ties; box sets identical as integer sets (IoU >= 0.99 bar);
+the 16-bit speed tier (IEEE half storage in the shipped library); identical masks away from threshold ties; box sets identical as integer sets (IoU >= 0.99 bar);
 bit-exact CTC token ids for the same logits; preprocess bit-exact; crop resize within 1 LSB.
 """
 import json
@@ -15,9 +15,10 @@ import torch
 from conftest import golden_json, load_golden
 
 pytestmark = pytest.mark.gpu
-# VTD_STORAGE=f16 runs the same tests against libvtd_b200_f16.so (IEEE half as the 16-bit storage type of the speed tier)
-HALF_STORAGE = os.environ.get("VTD_STORAGE", "") == "f16"
-STORAGE_16 = torch.float16 if HALF_STORAGE else torch.bfloat16
+# The speed tier the tests run: "fp16" = the shipped library (IEEE half storage).  VTD_TEST_TIER16=bf16 runs the same tests
+# against libvtd_b200_bf16.so (bfloat16 storage), whose looser 640x640 figures are stated in that test.
+T16 = os.environ.get("VTD_TEST_TIER16", "fp16")
+STORAGE_16 = torch.float16 if T16 == "fp16" else torch.bfloat16
 
 
 @pytest.fixture(scope="module")
@@ -80,8 +81,8 @@ def test_preprocess_vs_oracle(E, port, src, det):
     for i in range(2):
         want = port.preprocess(frames[i], det[0], det[1])[0].numpy()      # PIL + torchvision, the reference's own calls
         assert np.array_equal(x[i], want)
-    # bf16 tier: same integers, rounded once
-    engb = E.Engine(det_h=det[0], det_w=det[1], max_batch=2, max_src_h=src[0], max_src_w=src[1], dtype="bf16")
+    # 16-bit tier: same integers, rounded once
+    engb = E.Engine(det_h=det[0], det_w=det[1], max_batch=2, max_src_h=src[0], max_src_w=src[1], dtype=T16)
     engb.preprocess(list(frames))
     xb = engb.debug_tensor("input", 2)
     assert np.array_equal(xb, torch.from_numpy(x).to(STORAGE_16).float().numpy())
@@ -104,7 +105,7 @@ def test_dbnet_golden_fp32(E, port, bb):
     assert np.abs(p2 - g["p2_s"]).max() <= 2e-3 * max(1.0, np.abs(g["p2_s"]).max())
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-3), (T16, 1e-2)])
 def test_dbnet_maps_vs_oracle(E, port, dtype, tol):
     net = port.build_dbnet("resnet18", seed=1)
     h, w = 160, 224
@@ -127,12 +128,12 @@ def test_dbnet_maps_vs_oracle(E, port, dtype, tol):
 
 
 def test_conv_tcgen05_matches_cuda_core_path(E, port):
-    """bf16 tier: tcgen05 implicit GEMM vs the fp32 FFMA tier on the same weights, layer by layer."""
+    """16-bit tier: tcgen05 implicit GEMM vs the fp32 FFMA tier on the same weights, layer by layer."""
     net = port.build_dbnet("resnet18", seed=2)
     h, w = 128, 192
     x = np.random.default_rng(0).standard_normal((2, 3, h, w)).astype(np.float32)
     e32 = E.Engine(backbone=18, det_h=h, det_w=w, max_batch=2, dtype="fp32")
-    e16 = E.Engine(backbone=18, det_h=h, det_w=w, max_batch=2, dtype="bf16")
+    e16 = E.Engine(backbone=18, det_h=h, det_w=w, max_batch=2, dtype=T16)
     for e in (e32, e16):
         e.load_detector(net.state_dict())
     p32, t32 = e32.dbnet_forward(x)
@@ -147,14 +148,14 @@ def test_conv_tcgen05_matches_cuda_core_path(E, port):
 
 
 def test_halo_and_direct_window_layers_vs_oracle(E, port):
-    """bf16 tier at a size where the one-patch-per-tile ("halo") convolutions and the direct-window stem are the ones
+    """16-bit tier at a size where the one-patch-per-tile ("halo") convolutions and the direct-window stem are the ones
     that run: 352x1024 -> stem output 176x512 (four full 128-pixel tiles per row), layer1 / FPN maps 88x256 (8x16 tiles
     with a padded last tile row: 88 = 5.5 x 16), layer2 44x128.  Oracle: the reference's modules on the same input."""
     net = port.build_dbnet("resnet18", seed=3)
     h, w = 352, 1024
     frames = port.synthetic_frames(2, 396, 1152, seed=6)
     x = torch.cat([port.preprocess(f, h, w) for f in frames])
-    eng = E.Engine(backbone=18, det_h=h, det_w=w, max_batch=2, dtype="bf16")
+    eng = E.Engine(backbone=18, det_h=h, det_w=w, max_batch=2, dtype=T16)
     eng.load_detector(net.state_dict())
     p, t = eng.dbnet_forward(x.numpy())
     with torch.no_grad():
@@ -167,7 +168,7 @@ def test_halo_and_direct_window_layers_vs_oracle(E, port):
     assert np.abs(t - ref["threshold"].numpy()).max() <= 1e-2
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-3), ("fp16", 1e-2), ("bf16", 1e-2)])
 def test_config1_640x640_maps_and_boxes_vs_oracle(E, port, dtype, tol):
     """BASELINE configs[0] shape -- the reference's own 640x640 detector input (text_detector.py:101) -- through the
     whole detect path: maps within the tier's tolerance, mask exact, boxes as the reference's post-process finds them on
@@ -186,20 +187,15 @@ def test_config1_640x640_maps_and_boxes_vs_oracle(E, port, dtype, tol):
         ref = port.dbnet_forward(net, x)
     for got, want in ((p, ref["probability"].numpy()[:, 0]), (t, ref["threshold"].numpy()[:, 0])):
         err = np.abs(got - want)
-        if dtype == "fp32":
-            assert err.max() <= tol, err.max()
-        elif HALF_STORAGE:
-            # libvtd_b200_f16.so (VTD_STORAGE=f16): IEEE half as the 16-bit storage type meets the bar outright
-            # (CPU emulation of the rounding points: 1.9e-3 / 2.0e-3, profiles/r01_bf16_error_budget.md)
-            print("f16 640x640: max %.4f" % err.max())
+        print("%s 640x640: max %.2e, pixels over %g: %d of %d" % (dtype, err.max(), tol, int((err > tol).sum()), err.size))
+        if dtype != "bf16":
+            # fp32 tier <= 1e-3; the shipped speed tier (IEEE half storage) meets north_star's 1e-2 outright
+            # (measured 2.0e-3; CPU emulation of the rounding points: profiles/r01_bf16_error_budget.md)
             assert err.max() <= tol, err.max()
         else:
-            # 819 200 pixels per map.  Measured for this net (randomised BN statistics, seed 0): probability map 0.11 % of
-            # the pixels over 1e-2, maximum 1.6e-2; threshold map 0.33 %, maximum 2.0e-2 -- activations are rounded to bf16
-            # after each of ~25 layers and the logits of a random-init net are large.  The bar of 1e-2 is therefore
-            # asserted for 99.5 % of the pixels here, with a hard ceiling of 3e-2 (the smaller 160x224 case above meets 1e-2
-            # outright; the fp32 tier meets 1e-3 everywhere).  DESIGN.md section 2 states the same numbers.
-            print("bf16 640x640: max %.4f, pixels over 1e-2: %d of %d" % (err.max(), int((err > tol).sum()), err.size))
+            # libvtd_b200_bf16.so, the bfloat16-storage BUILD OPTION (not the shipped tier): 819 200 pixels per map, measured
+            # 0.11 % of the probability pixels over 1e-2 (max 1.6e-2), 0.33 % of the threshold pixels (max 2.0e-2) --
+            # eight mantissa bits after each of ~25 layers.  Stated, bounded, and the reason half is what ships.
             assert (err > tol).mean() <= 5e-3 and err.max() <= 3e-2, (err.max(), int((err > tol).sum()))
     assert np.array_equal(m, (p > 0.5).astype(np.uint8))
     # boxes: with the planted plane (random-init maps hold no component of 100 px^2)
@@ -302,7 +298,7 @@ def test_crop_resize_within_one_lsb(E, port):
         assert np.abs(x[i] - want).max() <= 1.0 / 255.0 + 1e-7, i     # <= 1 LSB from the installed wheel
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", 8e-2)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), (T16, 5e-3 if T16 == "fp16" else 4e-2)])
 def test_crnn_logits(E, port, dtype, tol):
     g = load_golden("crnn")
     net = port.build_crnn(seed=0)
@@ -311,6 +307,7 @@ def test_crnn_logits(E, port, dtype, tol):
     out = eng.crnn_forward(g["inputs"])
     ref = g["logits"]
     assert out.shape == ref.shape
+    print("crnn %s: max |dlogit| %.2e of max |logit| %.2f" % (dtype, np.abs(out - ref).max(), np.abs(ref).max()))
     assert np.abs(out - ref).max() <= tol * max(1.0, np.abs(ref).max()), np.abs(out - ref).max()
     if dtype == "fp32":
         crops = [g["crop%d" % i] for i in range(int(g["n"]))]
@@ -321,7 +318,7 @@ def test_crnn_logits(E, port, dtype, tol):
             assert conf[i] == pytest.approx(r["confidence"], abs=2e-3)
 
 
-@pytest.mark.parametrize("dtype,tol", [("fp32", 2e-3), ("bf16", 5e-3)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-5), (T16, 1e-3)])
 def test_crnn_w100_shapes(E, port, dtype, tol):
     """BASELINE configs[2] words the crops as 32x100 (T=24); measured round 1: 6e-8 (fp32) / 2.6e-4 (bf16)."""
     net = port.build_crnn(seed=3)
@@ -332,6 +329,7 @@ def test_crnn_w100_shapes(E, port, dtype, tol):
     with torch.no_grad():
         ref = net(torch.from_numpy(x)).numpy()
     assert out.shape == ref.shape == (5, 24, 97)
+    print("crnn w100 %s: max |dlogit| %.2e" % (dtype, np.abs(out - ref).max()))
     assert np.abs(out - ref).max() <= tol
 
 
@@ -404,8 +402,8 @@ def test_golden_pipeline_frame(E, port):
     g = load_golden("pipeline")
     regions = golden_json(g["regions"])
     from video_text_detection_system_b200 import TextDetector, TextRecognizer
-    D = TextDetector(backbone="resnet18", pretrained=False)
-    R = TextRecognizer(use_transformer=False)
+    D = TextDetector(backbone="resnet18", pretrained=False, dtype="fp32")
+    R = TextRecognizer(use_transformer=False, dtype="fp32")
     R.model.load_state_dict(port.build_crnn(seed=0).state_dict())
     pm = g["planted_map"]
     D.model.forward = lambda x: {"probability": torch.from_numpy(pm)[None, None], "threshold": torch.zeros(1, 1, 640, 640)}

@@ -1,5 +1,6 @@
 """GPU tests of the reference-facing Python surface and of the less common entry points (NV12 ingest, ResNet50,
 4K, crop chunking, concurrent callers).  The oracle (oracle/port.py) is the checker."""
+import os
 import threading
 
 import numpy as np
@@ -7,6 +8,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+T16 = os.environ.get("VTD_TEST_TIER16", "fp16")      # the shipped speed tier (IEEE half storage); bf16 = the build option
 
 
 @pytest.fixture(scope="module")
@@ -50,42 +52,91 @@ def test_nv12_preprocess_matches_cv2_then_reference_transform(E, port):
         assert np.array_equal(x[i], port.preprocess(bgr, dh, dw)[0].numpy())
 
 
-def test_resnet50_bf16_maps_vs_oracle(E, port):
+def test_resnet50_speed_tier_maps_vs_oracle(E, port):
     net = port.build_dbnet("resnet50", seed=4)
     h, w = 192, 256
     x = np.random.default_rng(1).standard_normal((2, 3, h, w)).astype(np.float32)
-    eng = E.Engine(backbone=50, det_h=h, det_w=w, max_batch=2, dtype="bf16")
+    eng = E.Engine(backbone=50, det_h=h, det_w=w, max_batch=2, dtype=T16)
     eng.load_detector(net.state_dict())
     p, t = eng.dbnet_forward(x)
     with torch.no_grad():
         ref = port.dbnet_forward(net, torch.from_numpy(x), return_feats=True)
-    # Random-init ResNet50 with randomised BN statistics has pre-sigmoid logits of std ~30 (94 % of the pixels are
-    # saturated), so a 1 % bf16 error in a logit that crosses zero moves the probability by far more than 1e-2.  The
-    # meaningful bf16 check here is relative error before the sigmoid, plus the share of pixels inside 1e-2.
     p2 = eng.debug_tensor("p2", 2)
     rp2 = ref["p2"].numpy()
-    assert np.abs(p2 - rp2).max() <= 0.03 * np.abs(rp2).max()
-    assert (np.abs(p - ref["probability"].numpy()) <= 1e-2).mean() >= 0.90
-    assert (np.abs(t - ref["threshold"].numpy()) <= 1e-2).mean() >= 0.90
+    ep, et = np.abs(p - ref["probability"].numpy()).max(), np.abs(t - ref["threshold"].numpy()).max()
+    print("R50 %s 192x256: p2 rel %.2e, max |dprob| %.2e, max |dthresh| %.2e" % (T16, np.abs(p2 - rp2).max() / np.abs(rp2).max(), ep, et))
+    over = float(np.mean(np.abs(p - ref["probability"].numpy()) > 1e-2))
+    print("R50 %s 192x256: share of probability pixels over 1e-2: %.2e" % (T16, over))
+    if T16 == "fp16":
+        # The shipped tier, absolute bounds.  A random-init ResNet50 with randomised BN statistics has pre-sigmoid logits of
+        # std ~30 (94 % of the pixels saturated): 53 layers of half rounding leave a relative logit error of ~2.6e-3
+        # (asserted on p2 below), which at a zero crossing of a logit of that size moves the probability by up to 3.4e-2
+        # (measured 3.3e-2 / 3.4e-2).  ResNet18's logits are O(1) and meet 1e-2 outright (tests/test_gpu_tiers.py).
+        assert np.abs(p2 - rp2).max() <= 4e-3 * np.abs(rp2).max()
+        assert ep <= 5e-2 and et <= 5e-2
+        assert over <= 2e-3
+    else:
+        # bfloat16 build option: a 1 % error in a saturated logit that crosses zero moves the probability by more than 1e-2
+        assert np.abs(p2 - rp2).max() <= 0.03 * np.abs(rp2).max()
+        assert (np.abs(p - ref["probability"].numpy()) <= 1e-2).mean() >= 0.90
+        assert (np.abs(t - ref["threshold"].numpy()) <= 1e-2).mean() >= 0.90
 
 
-def test_4k_resnet50_bf16_runs_and_agrees_with_fp32_tier(E, port):
-    """BASELINE config 5 shape: 2160x3840 -> 2176x3840, DBNet-ResNet50, bf16.  Oracle-free (a CPU forward at this
-    size takes minutes): the two tiers of the library must agree within the bf16 tolerance."""
+def test_resnet50_at_the_benched_detector_size_vs_oracle(E, port):
+    """BASELINE configs[4]'s backbone (DBNet-ResNet50) at a size the CPU oracle can afford -- one 1080p frame at 736x1312,
+    the detector size of configs[1..3] -- in the speed tier, with absolute tolerances, through preprocess + detect +
+    box extraction."""
+    net = port.build_dbnet("resnet50", seed=0)
+    H, W, DH, DW = 1080, 1920, 736, 1312
+    frames = port.synthetic_frames(1, H, W, seed=4)
+    # +-1000: the random-init ResNet50's own logits reach +-150, so the planted plane has to be that much larger to decide the mask
+    bias = port.planted_logit_bias(1, DH, DW, seed=5, boxes=50, inside=1000.0, outside=-1000.0)
+    eng = E.Engine(backbone=50, det_h=DH, det_w=DW, max_batch=1, max_boxes=64, dtype=T16, max_src_h=H, max_src_w=W)
+    eng.load_detector(net.state_dict())
+    b = torch.from_numpy(bias).cuda()
+    eng.preprocess(list(frames))
+    eng.detect_maps(1, 0.5, b.data_ptr())
+    p, t, m = eng.read_maps(1)
+    eng.extract_boxes(1, H, W)
+    rec, cnt = eng.read_records(1)
+    assert eng.overflow() == 0
+    with torch.no_grad():
+        ref = port.dbnet_forward(net, port.preprocess(frames[0], DH, DW), torch.from_numpy(bias)[:, None])
+    rp, rt = ref["probability"].numpy()[0, 0], ref["threshold"].numpy()[0, 0]
+    ep, et = float(np.abs(p[0] - rp).max()), float(np.abs(t[0] - rt).max())
+    print("R50 %s 736x1312: max |dprob| %.2e, max |dthresh| %.2e, threshold pixels over 1e-2: %.2e" % (T16, ep, et, float(np.mean(np.abs(t[0] - rt) > 1e-2))))
+    if T16 == "fp16":
+        assert ep <= 1e-2                      # the probability map is decided by the planted plane: exact to rounding
+        assert et <= 6e-2 and np.mean(np.abs(t[0] - rt) > 1e-2) <= 2e-3      # see test_resnet50_speed_tier_maps_vs_oracle
+    want = sorted(tuple(d["bbox"]) for d in port.post_process(rp, W, H, 0.5, DH, DW))
+    got = sorted(tuple(int(v) for v in r["bbox"]) for r in rec[0][:cnt[0]])
+    assert len(want) >= 45 and got == want
+
+
+def test_4k_resnet50_speed_tier_runs_and_agrees_with_fp32_tier(E, port):
+    """BASELINE config 5 shape: 2160x3840 -> 2176x3840, DBNet-ResNet50, 16-bit tier.  Oracle-free (a CPU forward at this
+    size takes minutes; the oracle comparison of this backbone is the 736x1312 test above): the two tiers of the
+    library must agree within the 16-bit tolerance."""
     net = port.build_dbnet("resnet50", seed=0)
     frames = port.synthetic_frames(1, 2160, 3840, seed=9)
     outs = {}
-    for dtype in ("fp32", "bf16"):
+    for dtype in ("fp32", T16):
         eng = E.Engine(backbone=50, det_h=2176, det_w=3840, max_batch=1, dtype=dtype, max_src_h=2160, max_src_w=3840)
         eng.load_detector(net.state_dict())
         eng.preprocess(list(frames))
         eng.detect_maps(1, 0.5)
         outs[dtype] = eng.read_maps(1)
         eng.close()
-    assert np.isfinite(outs["bf16"][0]).all()
-    # logits of the random-init ResNet50 are mostly saturated (see test_resnet50_bf16_maps_vs_oracle)
-    assert (np.abs(outs["fp32"][0] - outs["bf16"][0]) <= 1e-2).mean() >= 0.90
-    assert (np.abs(outs["fp32"][1] - outs["bf16"][1]) <= 1e-2).mean() >= 0.90
+    assert np.isfinite(outs[T16][0]).all()
+    ep, et = np.abs(outs["fp32"][0] - outs[T16][0]).max(), np.abs(outs["fp32"][1] - outs[T16][1]).max()
+    print("4K R50 %s vs fp32 tier: max |dprob| %.2e, max |dthresh| %.2e" % (T16, ep, et))
+    over = float(np.mean(np.abs(outs["fp32"][0] - outs[T16][0]) > 1e-2))
+    print("4K R50 %s vs fp32 tier: share of probability pixels over 1e-2: %.2e" % (T16, over))
+    if T16 == "fp16":
+        assert ep <= 6e-2 and et <= 6e-2 and over <= 2e-3      # see test_resnet50_speed_tier_maps_vs_oracle
+    else:
+        assert (np.abs(outs["fp32"][0] - outs[T16][0]) <= 1e-2).mean() >= 0.90
+        assert (np.abs(outs["fp32"][1] - outs[T16][1]) <= 1e-2).mean() >= 0.90
 
 
 def test_more_crops_than_one_chunk(E, port):
@@ -104,7 +155,7 @@ def test_more_crops_than_one_chunk(E, port):
 def test_text_detector_detect_vs_oracle_and_threads(port):
     from video_text_detection_system_b200 import TextDetector
     sd = port.build_dbnet("resnet18", seed=0).state_dict()
-    D = TextDetector(backbone="resnet18", pretrained=False, det_size=(320, 480))
+    D = TextDetector(backbone="resnet18", pretrained=False, det_size=(320, 480), dtype="fp32")     # exact boxes: parity tier
     D.model.load_state_dict(sd)
     net = port.build_dbnet("resnet18", seed=0)
     import cv2
@@ -142,7 +193,8 @@ def test_text_detector_detect_vs_oracle_and_threads(port):
 
 def test_pipeline_fused_path_vs_oracle(port):
     from video_text_detection_system_b200 import VideoTextPipeline
-    P = VideoTextPipeline(use_transformer_ocr=False, backbone="resnet18", pretrained=False, det_size=(256, 1280))
+    # exact box sets and text: the fp32 parity tier (the default speed tier is covered by tests/test_gpu_tiers.py)
+    P = VideoTextPipeline(use_transformer_ocr=False, backbone="resnet18", pretrained=False, det_size=(256, 1280), dtype="fp32")
     det, rec = port.build_dbnet("resnet18", seed=0), port.build_crnn(seed=0)
     P.detector.model.load_state_dict(det.state_dict())
     P.recognizer.model.load_state_dict(rec.state_dict())

@@ -16,7 +16,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvtd_b200.so")
 
-VTD_FP32, VTD_BF16 = 0, 1
+VTD_FP32, VTD_16BIT = 0, 1
+VTD_BF16 = VTD_16BIT                 # round-1 name of the enum value
 VTD_PIX_BGR, VTD_PIX_NV12 = 0, 1
 STAGE_NAMES = ("preprocess", "head_tail", "boxes", "crop", "lstm0", "lstm1", "ctc")   # vtd_op_info(which=2)
 VTD_IDS_STRIDE = 64
@@ -72,13 +73,14 @@ _libs: Dict[str, object] = {}
 
 
 def load_library(variant: Optional[str] = None):
-    """dlopen libvtd_b200.so (building it first if it is missing and nvcc exists).  variant: "" = the shipped library
-    (bfloat16 speed tier), "f16" = libvtd_b200_f16.so (IEEE half as the 16-bit storage type, same ABI); None = what the
-    environment variable VTD_STORAGE names, default "".  Both may be loaded in one process (Engine(dtype="fp16"))."""
+    """dlopen libvtd_b200.so (building it first if it is missing and nvcc exists).  variant: "" = the shipped library (IEEE
+    half as the 16-bit storage type of the speed tier), "bf16" = libvtd_b200_bf16.so (bfloat16 storage, same ABI); None =
+    what the environment variable VTD_STORAGE names, default "".  Both may be loaded in one process
+    (Engine(dtype="fp16") beside Engine(dtype="bf16"))."""
     global _lib
     if variant is None:
         variant = os.environ.get("VTD_STORAGE", "")
-    variant = "" if variant == "bf16" else variant
+    variant = "" if variant in ("f16", "fp16", "half") else variant
     with _lib_lock:
         if variant in _libs:
             return _libs[variant]
@@ -156,11 +158,21 @@ class Engine:
                  crop_w: int = 128, max_batch: int = 1, max_boxes: int = 256, max_src_h: int = 2160,
                  max_src_w: int = 3840, canonical_ctc: bool = False, unclip_ratio: float = 1.0):
         d = str(dtype).lower()
-        half = d in ("fp16", "f16", "half", "float16")        # the speed tier over IEEE half: the half-storage library
-        self.lib = load_library("f16" if half else None)
+        # "fp16" / "bf16" name the 16-bit storage type of the speed tier and with it the library; "fp32" (the CUDA-core
+        # parity tier) and "16bit" (the speed tier) take the process default (VTD_STORAGE, shipped = half)
+        if d in ("fp16", "f16", "half", "float16"):
+            variant = ""
+        elif d in ("bf16", "bfloat16"):
+            variant = "bf16"
+        elif d in ("fp32", "float32", "0", "16bit", "1"):
+            variant = None
+        else:
+            raise ValueError("dtype must be 'fp16', 'bf16', '16bit' or 'fp32', got %r" % (dtype,))
+        self.lib = load_library(variant)
+        speed = d not in ("fp32", "float32", "0")
         cfg = VtdConfig()
         cfg.device, cfg.backbone = int(device), int(backbone)
-        cfg.dtype = VTD_BF16 if half or d in ("bf16", "bfloat16", "1") else VTD_FP32
+        cfg.dtype = VTD_16BIT if speed else VTD_FP32
         cfg.det_h, cfg.det_w, cfg.crop_w = int(det_h), int(det_w), int(crop_w)
         cfg.max_batch, cfg.max_boxes = int(max_batch), int(max_boxes)
         cfg.max_src_h, cfg.max_src_w = int(max_src_h), int(max_src_w)
@@ -169,7 +181,8 @@ class Engine:
         self.cfg = cfg
         self.det_h, self.det_w, self.crop_w = cfg.det_h, cfg.det_w, cfg.crop_w
         self.max_batch, self.max_boxes = cfg.max_batch, cfg.max_boxes
-        self.dtype = "bf16" if cfg.dtype == VTD_BF16 else "fp32"
+        stored = "bf16" if (variant == "bf16" or (variant is None and os.environ.get("VTD_STORAGE", "") == "bf16")) else "fp16"
+        self.dtype = stored if speed else "fp32"
         self._h = C.c_void_p()
         rc = self.lib.vtd_create(C.byref(self._h), C.byref(cfg))
         if rc != 0:

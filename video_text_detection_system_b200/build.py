@@ -38,13 +38,14 @@ def _stale(target: str, deps) -> bool:
 
 
 def variant_paths(variant: str = ""):
-    """(object directory, library path, extra nvcc flags) of a build variant.  "" = the shipped library (bf16 speed
-    tier); "f16" = the same sources with IEEE half as the 16-bit storage type (-DVTD_HALF_STORAGE, csrc/common.cuh):
-    libvtd_b200_f16.so, selected at load time with VTD_STORAGE=f16."""
-    if variant in ("", "bf16"):
+    """(object directory, library path, extra nvcc flags) of a build variant.  "" (or "f16") = the shipped library, whose
+    16-bit speed tier stores IEEE half; "bf16" = the same sources with bfloat16 as the 16-bit storage type
+    (-DVTD_BF16_STORAGE, csrc/common.cuh): libvtd_b200_bf16.so, selected per Engine with dtype="bf16" or for a whole
+    process with VTD_STORAGE=bf16."""
+    if variant in ("", "f16", "fp16"):
         return OBJ, LIB, []
-    if variant == "f16":
-        return OBJ + "_f16", os.path.join(HERE, "libvtd_b200_f16.so"), ["-DVTD_HALF_STORAGE"]
+    if variant == "bf16":
+        return OBJ + "_bf16", os.path.join(HERE, "libvtd_b200_bf16.so"), ["-DVTD_BF16_STORAGE"]
     raise ValueError("unknown build variant %r" % variant)
 
 
@@ -83,4 +84,4 @@ def build_library(force: bool = False, verbose: bool = False, variant: str = "")
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True, variant="f16" if "--f16" in sys.argv else ""))
+    print(build_library(force="--force" in sys.argv, verbose=True, variant="bf16" if "--bf16" in sys.argv else ""))

@@ -12,9 +12,11 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace vtd;
@@ -86,6 +88,9 @@ struct vtd_ctx {
 
   // frames
   uint8_t* frames_store = nullptr; size_t frame_bytes_cap = 0;
+  // pageable host frames (NumPy arrays of a Python caller) are staged through this pinned buffer by a few copy threads,
+  // so that the host->device copies are real asynchronous DMA instead of the driver's serialised bounce copies
+  uint8_t* host_stage = nullptr; size_t host_stage_bytes = 0; cudaEvent_t host_stage_event = nullptr;
   const uint8_t** store_ptrs_dev = nullptr;    // constant: the staging slots
   const uint8_t** ext_ptrs_dev = nullptr;      // caller-owned device frames of the current batch
   const uint8_t** frame_ptrs_dev = nullptr;    // whichever of the two the current batch uses
@@ -99,6 +104,7 @@ struct vtd_ctx {
   uint8_t* box_work = nullptr; BoxWorkLayout box_lay{};
   vtd_record* records = nullptr; int* counts = nullptr; int* offsets = nullptr;
   int* pinned_int = nullptr;            // [max_batch+2]
+  int overflow_cached = -1;             // overflow flag fetched with the last record read-back (-1: not fetched since the last extraction)
   // arbitrary-size post-process drop-in
   uint8_t* pp_work = nullptr; BoxWorkLayout pp_lay{}; int pp_h = 0, pp_w = 0;
   float* pp_prob = nullptr; uint8_t* pp_mask = nullptr; vtd_record* pp_records = nullptr; int* pp_counts = nullptr;
@@ -373,7 +379,7 @@ int build_detector(vtd_ctx* c, const SD& sd) {
     op.d.stride = 2; op.d.pad = 3; op.d.N = B;
     std::string e;
     op.plan = tc_plan_create_win(c->pre, B, dh + 6, dw + 8, 4, 2, 7, dh / 2, dw / 2, wdev, bdev, o, 1, &e);
-    if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 stem plan: %s (set VTD_NO_WIN=1 to use the CUDA-core stem)", e.c_str());
+    if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 stem plan: %s", e.c_str());
     P.push_back(op);
     a.p = o; a.H = dh / 2; a.W = dw / 2; a.C = 64;
   } else {
@@ -489,7 +495,7 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
   std::vector<Op>& P = c->rec_prog;
   int r;
   Act a; a.p = c->crops; a.H = 32; a.W = cw; a.C = 4;
-  const bool fuse_pools = c->bf16_mode && !getenv("VTD_NO_POOL_FUSION");
+  const bool fuse_pools = c->bf16_mode && !dev_env("VTD_NO_POOL_FUSION");
   struct L { int conv, bn, k, pad; int pool; };   // pool: 0 none, 1 = 2x2 s2, 2 = (2,1) s(2,1)
   const L layers[7] = {{0, 1, 3, 1, 1}, {4, 5, 3, 1, 1}, {8, 9, 3, 1, 0}, {11, 12, 3, 1, 2},
                        {15, 16, 3, 1, 0}, {18, 19, 3, 1, 2}, {22, 23, 2, 0, 0}};
@@ -520,7 +526,7 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
       std::string e;
       op.d.pool = fuse;
       op.plan = tc_plan_create_win(c->crops, B, 34, cw + 4, 8, 1, 3, 32, cw, wdev, bdev, o, 1, &e, fuse);
-      if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 CRNN stem plan: %s (set VTD_NO_WIN=1 to use the CUDA-core stem)", e.c_str());
+      if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 CRNN stem plan: %s", e.c_str());
       P.push_back(op);
       a.p = o; a.H = fuse ? 16 : 32; a.W = fuse == 1 ? cw / 2 : cw; a.C = 64;
       if (fuse) continue;
@@ -665,11 +671,47 @@ int preprocess_locked(vtd_ctx* c, const uint8_t* const* frames, int n, int h, in
     dev_pitch = row_bytes;
     const size_t fb = (size_t)rows * row_bytes;
     if (fb > c->frame_bytes_cap) FAIL(VTD_ERR_CAPACITY, "frame of %zu bytes exceeds the staging slot", fb);
-    for (int i = 0; i < n; ++i) {
-      uint8_t* dst = c->frames_store + (size_t)i * c->frame_bytes_cap;
-      if (!frames[i]) FAIL(VTD_ERR_ARG, "frame %d is a null pointer", i);
-      if (pitch == row_bytes) CK(cudaMemcpyAsync(dst, frames[i], fb, cudaMemcpyHostToDevice, c->stream));
-      else CK(cudaMemcpy2DAsync(dst, row_bytes, frames[i], pitch, row_bytes, rows, cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < n; ++i) if (!frames[i]) FAIL(VTD_ERR_ARG, "frame %d is a null pointer", i);
+    // page-locked frames (cudaHostAlloc / cudaHostRegister / torch pin_memory) go straight to the copy engine
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, frames[0]) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+      for (int i = 0; i < n; ++i) {
+        uint8_t* dst = c->frames_store + (size_t)i * c->frame_bytes_cap;
+        if (pitch == row_bytes) CK(cudaMemcpyAsync(dst, frames[i], fb, cudaMemcpyHostToDevice, c->stream));
+        else CK(cudaMemcpy2DAsync(dst, row_bytes, frames[i], pitch, row_bytes, rows, cudaMemcpyHostToDevice, c->stream));
+      }
+    } else {
+      // pageable frames: copy threads pack frame i into its pinned slot and issue its DMA at once, so the host copy of
+      // frame i+1 overlaps the transfer of frame i
+      const size_t need = fb * (size_t)n;
+      if (c->host_stage_bytes < need) {
+        if (c->host_stage) { cudaFreeHost(c->host_stage); c->host_stage = nullptr; c->host_stage_bytes = 0; }
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&c->host_stage), fb * (size_t)c->cfg.max_batch, cudaHostAllocDefault));
+        c->host_stage_bytes = fb * (size_t)c->cfg.max_batch;
+      }
+      if (!c->host_stage_event) CK(cudaEventCreateWithFlags(&c->host_stage_event, cudaEventDisableTiming));
+      else CK(cudaEventSynchronize(c->host_stage_event));       // the previous batch's DMAs have read the slots
+      const int nthreads = n < 4 ? n : 4;
+      std::atomic<int> next{0};
+      std::atomic<int> failed{0};
+      auto work = [&]() {
+        cudaSetDevice(c->cfg.device);
+        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+          uint8_t* slot = c->host_stage + (size_t)i * fb;
+          if (pitch == row_bytes) memcpy(slot, frames[i], fb);
+          else for (int y = 0; y < rows; ++y) memcpy(slot + (size_t)y * row_bytes, frames[i] + (size_t)y * pitch, row_bytes);
+          if (cudaMemcpyAsync(c->frames_store + (size_t)i * c->frame_bytes_cap, slot, fb, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+            failed.store(1);
+        }
+      };
+      std::vector<std::thread> pool;
+      for (int t = 1; t < nthreads; ++t) pool.emplace_back(work);
+      work();
+      for (std::thread& t : pool) t.join();
+      if (failed.load()) { cudaGetLastError(); FAIL(VTD_ERR_CUDA, "host->device copy of a staged frame failed"); }
+      CK(cudaEventRecord(c->host_stage_event, c->stream));
     }
     c->frame_ptrs_dev = c->store_ptrs_dev;
   } else {
@@ -700,6 +742,7 @@ int extract_locked(vtd_ctx* c, int n, int orig_h, int orig_w) {
   bp.n = n; bp.n_alloc = c->cfg.max_batch; bp.mh = c->cfg.det_h; bp.mw = c->cfg.det_w;
   bp.clip_h = c->cfg.det_h; bp.clip_w = c->cfg.det_w; bp.orig_h = orig_h; bp.orig_w = orig_w;
   bp.kmax = c->cfg.max_boxes; bp.unclip = c->cfg.unclip_ratio;
+  c->overflow_cached = -1;
   StageTimer st(c, ST_BOXES);
   CK(extract_boxes(c->prob, c->mask, bp, c->box_work, c->box_lay, c->records, c->counts, c->stream, &c->lc));
   return VTD_OK;
@@ -732,16 +775,25 @@ int recognize_locked(vtd_ctx* c, int n) {
 }
 
 int read_records_locked(vtd_ctx* c, int n, vtd_record* rh, int* ch) {
+  // the overflow flag rides along with the read-back (same synchronisation): vtd_overflow_flag() then costs nothing
+  CK(cudaMemcpyAsync(c->pinned_int + 1, c->box_work + c->box_lay.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (ch) CK(cudaMemcpyAsync(ch, c->counts, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
   if (rh) CK(cudaMemcpyAsync(rh, c->records, sizeof(vtd_record) * (size_t)n * c->cfg.max_boxes, cudaMemcpyDeviceToHost,
                              c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->overflow_cached = c->pinned_int[1];
   return VTD_OK;
 }
 
+// Serialises the calls on a context and makes its device current for their duration; the caller's current device
+// (torch's, for a Python caller) is put back on the way out.
 struct Guard {
-  vtd_ctx* c; std::lock_guard<std::mutex> lk;
-  explicit Guard(vtd_ctx* ctx) : c(ctx), lk(ctx->mu) { cudaSetDevice(ctx->cfg.device); }
+  vtd_ctx* c; std::lock_guard<std::mutex> lk; int prev = -1;
+  explicit Guard(vtd_ctx* ctx) : c(ctx), lk(ctx->mu) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != ctx->cfg.device) cudaSetDevice(ctx->cfg.device); else prev = -1;
+  }
+  ~Guard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 int make_sd(vtd_ctx* c, const vtd_tensor* t, int n, SD* sd) {
@@ -767,7 +819,7 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   auto bad = [&](int code, const std::string& m) { g_create_error = m; if (out) *out = nullptr; return code; };
   if (!out || !cfg) return bad(VTD_ERR_ARG, "null argument");
   if (cfg->backbone != 18 && cfg->backbone != 50) return bad(VTD_ERR_ARG, "backbone must be 18 or 50");
-  if (cfg->dtype != VTD_FP32 && cfg->dtype != VTD_BF16) return bad(VTD_ERR_ARG, "dtype must be VTD_FP32 or VTD_BF16");
+  if (cfg->dtype != VTD_FP32 && cfg->dtype != VTD_16BIT) return bad(VTD_ERR_ARG, "dtype must be VTD_FP32 or VTD_16BIT");
   if (cfg->det_h <= 0 || cfg->det_w <= 0 || cfg->det_h % 32 || cfg->det_w % 32)
     return bad(VTD_ERR_ARG, "det_h/det_w must be positive multiples of 32");
   if (cfg->crop_w < 16 || cfg->crop_w % 4 || cfg->crop_w / 4 - 1 > 36) return bad(VTD_ERR_ARG, "crop_w must be a multiple of 4 in [16,148]");
@@ -783,18 +835,21 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) return bad(VTD_ERR_CUDA, cudaGetErrorString(e));
   if (prop.major != 10)
     return bad(VTD_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100 (this library is built for sm_100a only)");
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev == cfg->device ? -1 : prev_dev};
   if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return bad(VTD_ERR_CUDA, cudaGetErrorString(e));
 
   vtd_ctx* c = new vtd_ctx();
   c->cfg = *cfg;
   if (!(c->cfg.unclip_ratio > 0.f)) c->cfg.unclip_ratio = 1.0f;
-  c->bf16_mode = cfg->dtype == VTD_BF16;
+  c->bf16_mode = cfg->dtype == VTD_16BIT;      // the 16-bit speed tier (half or bfloat16 storage, common.cuh)
   c->esz = c->bf16_mode ? 2 : 4;
   c->T = cfg->crop_w / 4 - 1;
-  c->use_win = c->bf16_mode && !getenv("VTD_NO_WIN");
-  c->use_tchead = c->bf16_mode && !getenv("VTD_NO_TCHEAD");
-  c->use_tclstm = c->bf16_mode && !getenv("VTD_NO_TCLSTM");
-  c->use_plstm = c->use_tclstm && !getenv("VTD_NO_PLSTM");
+  c->use_win = c->bf16_mode && !dev_env("VTD_NO_WIN");
+  c->use_tchead = c->bf16_mode && !dev_env("VTD_NO_TCHEAD");
+  c->use_tclstm = c->bf16_mode && !dev_env("VTD_NO_TCLSTM");
+  c->use_plstm = c->use_tclstm && !dev_env("VTD_NO_PLSTM");
   long long want = (long long)cfg->max_batch * cfg->max_boxes;
   c->rc = (int)(want < 1024 ? want : 1024);
   auto fail = [&](int code) { g_create_error = c->err; vtd_destroy(c); *out = nullptr; return code; };
@@ -810,8 +865,9 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
       (r = dalloc(c, &c->ext_ptrs_dev, sizeof(void*) * B)) ||
       (r = dev_alloc(c, &c->pre, (size_t)B * (c->use_win ? (size_t)(dh + 6) * (dw + 8) : px) * 4 * c->esz + 4096 /* the stem's row copies overhang */)) || (r = dalloc(c, &c->prob, (size_t)B * px * 4)) ||
       (r = dalloc(c, &c->thresh, (size_t)B * px * 4)) || (r = dalloc(c, &c->mask, (size_t)B * px)) ||
-      (r = dalloc(c, &c->records, sizeof(vtd_record) * (size_t)B * cfg->max_boxes)) ||
-      (r = dalloc(c, &c->counts, sizeof(int) * B)) || (r = dalloc(c, &c->offsets, sizeof(int) * (B + 1))) ||
+      // records and counts are ONE block (counts directly after the records): a rank's results travel in one collective
+      (r = dalloc(c, &c->records, sizeof(vtd_record) * (size_t)B * cfg->max_boxes + sizeof(int) * B)) ||
+      (r = dalloc(c, &c->offsets, sizeof(int) * (B + 1))) ||
       (r = dev_alloc(c, &c->crops, (size_t)c->rc * (c->use_win ? (size_t)34 * (cfg->crop_w + 4) * 8 : (size_t)32 * cfg->crop_w * 4) * c->esz)) ||
       (r = dalloc(c, &c->ids_dev, (size_t)c->rc * VTD_IDS_STRIDE)) || (r = dalloc(c, &c->len_dev, (size_t)c->rc * 4)) ||
       (r = dalloc(c, &c->conf_dev, (size_t)c->rc * 4)) || (r = dalloc(c, &c->list_ptrs, sizeof(void*) * c->rc)) ||
@@ -833,6 +889,7 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   for (int i = 0; i < B; ++i) c->frame_ptrs_pinned[i] = c->frames_store + (size_t)i * c->frame_bytes_cap;
   cudaMemcpy(c->store_ptrs_dev, c->frame_ptrs_pinned, sizeof(void*) * B, cudaMemcpyHostToDevice);
   c->frame_ptrs_dev = c->store_ptrs_dev;
+  c->counts = reinterpret_cast<int*>(c->records + (size_t)B * cfg->max_boxes);
   cudaMemset(c->counts, 0, sizeof(int) * B);
   if ((r = dalloc(c, &c->norm_lut, 768 * sizeof(float)))) return fail(r);
   if (build_normalize_lut(c->norm_lut, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
@@ -855,6 +912,9 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
 
 void vtd_destroy(vtd_ctx* c) {
   if (!c) return;
+  int prev_dev = -1;
+  cudaGetDevice(&prev_dev);
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev == c->cfg.device ? -1 : prev_dev};
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (Op& op : c->det_prog) if (op.plan) tc_plan_destroy(op.plan);
@@ -869,6 +929,8 @@ void vtd_destroy(vtd_ctx* c) {
   if (c->pp_work) { cudaFree(c->pp_work); cudaFree(c->pp_prob); cudaFree(c->pp_mask); cudaFree(c->pp_records); cudaFree(c->pp_counts); }
   if (c->stage_f32) cudaFree(c->stage_f32);
   if (c->list_store) cudaFree(c->list_store);
+  if (c->host_stage) cudaFreeHost(c->host_stage);
+  if (c->host_stage_event) cudaEventDestroy(c->host_stage_event);
   if (c->frame_ptrs_pinned) cudaFreeHost(c->frame_ptrs_pinned);
   if (c->pinned_int) cudaFreeHost(c->pinned_int);
   if (c->ptrs_event) cudaEventDestroy(c->ptrs_event);
@@ -890,6 +952,7 @@ int vtd_time_T(vtd_ctx* c) { return c ? c->T : 0; }
 int vtd_overflow_flag(vtd_ctx* c) {
   if (!c) return 0;
   Guard g(c);
+  if (c->overflow_cached >= 0) return c->overflow_cached;
   int v = 0;
   cudaMemcpyAsync(&v, c->box_work + c->box_lay.overflow, 4, cudaMemcpyDeviceToHost, c->stream);
   cudaStreamSynchronize(c->stream);

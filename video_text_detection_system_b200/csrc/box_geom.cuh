@@ -251,14 +251,16 @@ VTD_HD void box_points(const RotRect& r, PtF pt[4]) {
   pt[3].y = fsub(fmul(2.f, r.cy), pt[1].y);
 }
 
-// Grow a rotated rect DB-style: offset distance = area * (ratio-1)... kept simple: d = w*h*ratio/(2(w+h)) is the
-// published unclip distance (area*ratio/perimeter); the rect grows by d on every side.  ratio<=1 disables it.
+// north_star's "unclip" (an extension; the reference has none): grow a rotated rect DB-style by the published offset
+// d = area * ratio / perimeter on every side.  ratio <= 1 disables it (reference behaviour).  Explicit float32 operations
+// (no FMA contraction), op for op as oracle/port.py unclip_rect states them.
 VTD_HD void unclip_rect(RotRect& r, float ratio) {
   if (!(ratio > 1.0f)) return;
-  float per = 2.f * (r.w + r.h);
-  if (per <= 0.f) return;
-  float d = r.w * r.h * ratio / per;
-  r.w += 2.f * d; r.h += 2.f * d;
+  const float per = fmul(2.f, fadd(r.w, r.h));
+  if (!(per > 0.f)) return;
+  const float d = fmul(fmul(r.w, r.h), ratio) / per;
+  const float two_d = fmul(2.f, d);
+  r.w = fadd(r.w, two_d); r.h = fadd(r.h, two_d);
 }
 
 }  // namespace geom

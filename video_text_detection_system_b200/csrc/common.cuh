@@ -4,16 +4,19 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <string.h>
 
 namespace vtd {
 
-// The 16-bit storage type of the speed tier (activations, weights, tcgen05 A/B operands).  bfloat16 in the shipped
-// build.  -DVTD_HALF_STORAGE builds the same kernels over IEEE half instead (tcgen05 kind::f16 takes either at the same
-// rate): three more mantissa bits, i.e. ~8x smaller rounding error per stored value, at the price of half's range
-// (profiles/r01_bf16_error_budget.md).  The type keeps the name `bf16` throughout the sources in both variants.
-#ifdef VTD_HALF_STORAGE
+// The 16-bit storage type of the speed tier (activations, weights, tcgen05 A/B operands).  IEEE half in the shipped
+// library: ten mantissa bits keep the probability / threshold maps within 2e-3 of the fp32 reference (north_star's bar
+// for the 16-bit tier is 1e-2; bfloat16 measured 1.6e-2 / 2.0e-2 at 640x640, profiles/r01_bf16_error_budget.md), at the
+// same tcgen05 kind::f16 rate and the same bytes.  -DVTD_BF16_STORAGE builds the same kernels over bfloat16 instead
+// (libvtd_b200_bf16.so: fp32's range, for checkpoints whose activations exceed 65504).  The type keeps the name `bf16`
+// throughout the sources in both variants.
+#ifndef VTD_BF16_STORAGE
 typedef __half bf16;
 typedef __half2 bf16x2;
 #define VTD_TMAP_16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -41,6 +44,28 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return f32_to_16(v); }
 
 struct LaunchCounter { long long n = 0; };
+
+// Tuning / experiment switches (VTD_NO_*, VTD_TILE, VTD_DBG ...) exist only in -DVTD_DEV builds; the release library reads
+// no environment variable on the compute path.
+#ifdef VTD_DEV
+inline const char* dev_env(const char* name) { return getenv(name); }
+#define VTD_DBG_BITS(p) ((p).dbg)
+#else
+inline const char* dev_env(const char*) { return nullptr; }
+#define VTD_DBG_BITS(p) 0
+#endif
+
+// Per-device one-time setup (cudaFuncSetAttribute is a per-device attribute; one process may hold contexts on several
+// GPUs): true the first time it is called for the CURRENT device with this flag word.
+struct PerDeviceFlag { unsigned long long mask[2] = {0ull, 0ull}; };
+inline bool first_on_device(PerDeviceFlag& f) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 127;
+  const unsigned long long bit = 1ull << (dev & 63);
+  const unsigned long long old = __atomic_fetch_or(&f.mask[dev >> 6], bit, __ATOMIC_ACQ_REL);
+  return (old & bit) == 0;
+}
 
 // ---- implicit-GEMM convolution description (NHWC activations, [Cout][kh][kw][Cin] weights) ------
 enum { RES_NONE = 0, RES_SAME = 1, RES_UP2 = 2 };          // residual add: same size / nearest-2x upsampled

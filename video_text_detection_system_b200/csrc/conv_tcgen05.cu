@@ -186,8 +186,8 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
   constexpr int NCH = BLOCK_N / 64;                  // 32-column chunks per warp
   const int cbase = half * (BLOCK_N / 2);
   uint4 rv[NCH][4];
-  const bool has_res = p.res_mode != RES_NONE && !(p.dbg & 12);
-  if (p.dbg & 4) valid = false;
+  const bool has_res = p.res_mode != RES_NONE && !(VTD_DBG_BITS(p) & 12);
+  if (VTD_DBG_BITS(p) & 4) valid = false;
   if (has_res && valid) {
     const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + nb * BLOCK_N + cbase);
 #pragma unroll
@@ -315,7 +315,7 @@ __device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUte
       }
     }
   }
-  if (p.dbg & 4) return;
+  if (VTD_DBG_BITS(p) & 4) return;
   // the previous store of this warp must have finished READING the staging block before it is overwritten
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
@@ -657,7 +657,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
               asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                            ::"r"(sa + j * WIN2_SLAB), "l"(src + (size_t)j * p.win_rp), "r"((uint32_t)WIN2_SLAB), "r"(fb) : "memory");
           } else {
-          if (p.dbg & 1) {
+          if (VTD_DBG_BITS(p) & 1) {
             if (p.bres) mbar_arrive(fb); else mbar_expect_tx(fb, (uint32_t)nk * Cfg::B_STAGE_BYTES);
           } else {
             mbar_expect_tx(fb, (uint32_t)nk * step_bytes);
@@ -665,7 +665,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
 #pragma unroll
           for (int j = 0; j < nk; ++j) {
             if (MODE == MODE_WIN) {
-              if (!(p.dbg & 1)) tma_load_5d(sa + j * Cfg::A_BYTES, &maps.a[0], fb, 0, x0, r % p.sdiv, y0 + r / p.sdiv, n0);
+              if (!(VTD_DBG_BITS(p) & 1)) tma_load_5d(sa + j * Cfg::A_BYTES, &maps.a[0], fb, 0, x0, r % p.sdiv, y0 + r / p.sdiv, n0);
               if (!p.bres) tma_load_2d(sb + j * Cfg::B_STAGE_BYTES, &maps.b, fb, r * 32, nb * BLOCK_N);
               ++r;
             } else {
@@ -678,7 +678,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
                 const int py = tyy & 1, px = txx & 1;
                 mi = py * 2 + px; yo = (tyy - py) / 2; xo = (txx - px) / 2;
               }
-              if (!(p.dbg & 1)) tma_load_4d(sa + j * Cfg::A_BYTES, &maps.a[mi], fb, coff + kc * BLOCK_K, x0 + xo, y0 + yo, n0);
+              if (!(VTD_DBG_BITS(p) & 1)) tma_load_4d(sa + j * Cfg::A_BYTES, &maps.a[mi], fb, coff + kc * BLOCK_K, x0 + xo, y0 + yo, n0);
               if (!p.bres)
                 tma_load_2d(sb + j * Cfg::B_STAGE_BYTES, &maps.b, fb, (r * p.KW + sx) * p.Cin + kc * BLOCK_K, nb * BLOCK_N);
               if (++kc == kchunks) { kc = 0; if (++sx == p.KW) { sx = 0; ++r; } }
@@ -771,7 +771,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (ks0 | t | k) ? 1u : 0u);
             }
-          } else if (!(p.dbg & 2)) {
+          } else if (!(VTD_DBG_BITS(p) & 2)) {
 #pragma unroll
             for (int j = 0; j < nk; ++j) {
               const uint64_t ad = (MODE == MODE_WIN && p.win2) ? umma_desc_nosw(sa + j * WIN2_SLAB, 16, 128)
@@ -806,7 +806,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       const int step = (BLOCK_N == 64 ? 2 : 1) * (int)gridDim.x;
       const int groups = (p.out_f32 ? BLOCK_N * 4 : BLOCK_N * 2) / 128;
       const int g0 = BLOCK_N == 64 ? 0 : half * (groups / 2), g1 = BLOCK_N == 64 ? groups : g0 + groups / 2;
-      const bool use_res = p.res_mode != RES_NONE && !(p.dbg & 12);
+      const bool use_res = p.res_mode != RES_NONE && !(VTD_DBG_BITS(p) & 12);
       const uint32_t stg = stg0 + (uint32_t)(warp - 2) * 4096u;
       const uint32_t pstg = stg0 + (uint32_t)NUM_EPI_WARPS * (4096u + (p.res_tma ? 4096u : 0u)) + (uint32_t)(warp - 2) * 2048u;
       const int m0 = q * 32;                              // first pixel of this warp inside the tile
@@ -1394,14 +1394,17 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+int sm_count() {                        // of the CURRENT device (cached per ordinal)
+  static int sms[128] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 127;
+  int v = __atomic_load_n(&sms[dev], __ATOMIC_RELAXED);
+  if (!v) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    __atomic_store_n(&sms[dev], v, __ATOMIC_RELAXED);
   }
-  return sms;
+  return v;
 }
 
 }  // namespace tc
@@ -1435,7 +1438,7 @@ static void fill_common(TcPlan* pl, int N, int Ho, int Wo, int Cout, int Cin, in
   p.KH = p.KW = 1; p.stride = 1; p.pad = 0;
   pick_tile(N, Ho, Wo, &p.lw, &p.lh);
   if (pool) { p.lw = 4; p.lh = Ho >= 8 ? 3 : (Ho >= 4 ? 2 : 1); p.pool = pool; }
-  if (const char* e = pool ? nullptr : getenv("VTD_TILE")) {               // tuning aid: "lw,lh" for layers at least that large
+  if (const char* e = pool ? nullptr : dev_env("VTD_TILE")) {               // tuning aid: "lw,lh" for layers at least that large
     int a = 0, b = 0;
     if (sscanf(e, "%d,%d", &a, &b) == 2 && a + b <= 7 && (1 << a) <= Wo && (1 << b) <= Ho && (128 >> (a + b)) <= (N > 1 ? N : 1)) { p.lw = a; p.lh = b; }
   }
@@ -1466,13 +1469,13 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   // 64 -> 64 3x3 s1 p1 (ResNet layer1): halo mode, see TcParams::halo.  Needs the weights resident (72 KB) and one 64-channel
   // chunk per pixel, tile 8 x 16 x 1 image.
   p.halo = (d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && d.Cin == 64 && d.Cout == 64 && !d.pool && d.Ho >= 8 &&
-            d.Wo >= 8 && !getenv("VTD_NO_HALO") && !getenv("VTD_NO_BRES")) ? 1 : 0;
+            d.Wo >= 8 && !dev_env("VTD_NO_HALO") && !dev_env("VTD_NO_BRES")) ? 1 : 0;
   // any other 3x3 s1 p1 layer whose maps tile into 8 x 16 pixels with little waste: halo mode with streamed weights (2)
-  if (!p.halo && d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && !d.pool && !getenv("VTD_NO_HALO")) {
+  if (!p.halo && d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && !d.pool && !dev_env("VTD_NO_HALO")) {
     const long long covered = (long long)((d.Wo + 7) / 8 * 8) * ((d.Ho + 15) / 16 * 16);
     int mask = 3;                                         // bit 0: N = 128 layers, bit 1: N = 256 layers
-    if (const char* e = getenv("VTD_HALO2")) mask = atoi(e);
-    const int waste = getenv("VTD_HALO_WASTE") ? atoi(getenv("VTD_HALO_WASTE")) : 13;   // percent of padded pixels tolerated
+    if (const char* e = dev_env("VTD_HALO2")) mask = atoi(e);
+    const int waste = dev_env("VTD_HALO_WASTE") ? atoi(dev_env("VTD_HALO_WASTE")) : 13;   // percent of padded pixels tolerated
     if (covered * 100 <= (long long)d.Wo * d.Ho * (100 + waste) && ((bn == 128 && (mask & 1)) || (bn == 256 && (mask & 2)))) p.halo = 2;
   }
   if (p.halo) {
@@ -1484,7 +1487,7 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
     if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(halo patch) failed: " + std::to_string((int)hr)); }
     if (p.halo == 2) {
       int cmask = 3;                                      // CTA pairs: bit 0 N = 128 layers, bit 1 N = 256 layers
-      if (const char* e = getenv("VTD_CTA2")) cmask = atoi(e);
+      if (const char* e = dev_env("VTD_CTA2")) cmask = atoi(e);
       p.cta2 = (p.n_blocks == 1 && !d.out_f32 && p.total_tiles >= 2 && ((bn == 128 && (cmask & 1)) || (bn == 256 && (cmask & 2)))) ? 1 : 0;
       p.b_taps = (bn <= 128 || p.cta2) ? 3 : 1;
       const long long K = 9LL * d.Cin;
@@ -1512,7 +1515,7 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   // CTA pairs for the remaining N = 256 layers with streamed weights (conv_tc2g_kernel): decided here, confirmed in plan_smem
   if (!p.halo && bn == 256 && !(d.out_f32 && d.res_mode != RES_NONE) &&
       (long long)d.KH * d.KW * (d.Cin / 64) * 256 * 128 > 96 * 1024 && p.tiles_x * p.tiles_y * p.tiles_n >= 2 &&
-      !(getenv("VTD_CTA2") && !(atoi(getenv("VTD_CTA2")) & 4))) {
+      !(dev_env("VTD_CTA2") && !(atoi(dev_env("VTD_CTA2")) & 4))) {
     p.cta2 = 2;
     r = encode_weights(enc, &pl->maps.b4, d.w, (long long)d.KH * d.KW * d.Cin, d.Cout, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weight halves) failed: " + std::to_string((int)r)); }
@@ -1549,7 +1552,7 @@ TcPlan* tc_plan_create_win(const void* in, int N, int Hp, int Wp, int cpp, int s
   p.nr = nr; p.sdiv = stride; p.relu = relu; p.bias = bias; p.out = out;
   // DBNet stem: direct windows (see TcParams::win2).  One-row tiles of 128 outputs; the last tile of a row hangs over the
   // right edge (its copies run into the next padded row: the buffer has slack after the last image, see api.cu).
-  p.win2 = (stride == 2 && cpp == 4 && nr == 7 && !pool && Wo >= 128 && !getenv("VTD_NO_WIN2")) ? 1 : 0;
+  p.win2 = (stride == 2 && cpp == 4 && nr == 7 && !pool && Wo >= 128 && !dev_env("VTD_NO_WIN2")) ? 1 : 0;
   if (p.win2) {
     p.lw = 7; p.lh = 0;
     p.tiles_x = (Wo + 127) / 128; p.tiles_y = Ho; p.tiles_n = N;
@@ -1645,7 +1648,7 @@ static void plan_smem(TcPlan* pl) {
   const int ksteps = MODE == MODE_WIN ? p.nr : p.KH * p.KW * (p.Cin / BLOCK_K);
   const int bres_bytes = ksteps * Cfg::B_STAGE_BYTES;
   const bool can_res = (MODE == MODE_CONV || MODE == MODE_WIN) && p.n_blocks == 1 && bres_bytes <= 96 * 1024 &&
-                       !getenv("VTD_NO_BRES");
+                       !dev_env("VTD_NO_BRES");
   p.bres = can_res ? 1 : 0;
   if (MODE == MODE_CONV && p.cta2 == 2) {                 // conv_tc2g_kernel: slots of A box + weight half, store staging
     p.bres = 0; p.kps = 1; p.res_tma = 0; p.epi_tma = 1; p.dbg = 0;
@@ -1674,7 +1677,7 @@ static void plan_smem(TcPlan* pl) {
     const int bslot = p.b_taps * Cfg::B_STAGE_BYTES;
     const int fixed = 1024 + Cfg::TAIL_BYTES;
     p.stages = 2;
-    p.epi_tma = (p.out_f32 && p.res_mode != RES_NONE) || getenv("VTD_NO_TMA_STORE") ? 0 : 1;
+    p.epi_tma = (p.out_f32 && p.res_mode != RES_NONE) || dev_env("VTD_NO_TMA_STORE") ? 0 : 1;
     int bst = (SMEM_TOTAL - fixed - p.stages * HALO_SLOT - (p.epi_tma ? stg : 0)) / bslot;
     if (bst < 3 && p.epi_tma && BN == 256) { p.epi_tma = 0; bst = (SMEM_TOTAL - fixed - p.stages * HALO_SLOT) / bslot; }
     if (bst > 8) bst = 8;
@@ -1682,7 +1685,7 @@ static void plan_smem(TcPlan* pl) {
     else {
       p.b_stages = bst;
       // the residual by TMA as well when its staging still fits
-      if (p.epi_tma && p.res_mode != RES_NONE && !getenv("VTD_NO_TMA_RES") &&
+      if (p.epi_tma && p.res_mode != RES_NONE && !dev_env("VTD_NO_TMA_RES") &&
           (SMEM_TOTAL - fixed - p.stages * HALO_SLOT - 2 * stg) / bslot >= 2) {
         p.res_tma = 1;
         p.b_stages = (SMEM_TOTAL - fixed - p.stages * HALO_SLOT - 2 * stg) / bslot;
@@ -1699,7 +1702,7 @@ static void plan_smem(TcPlan* pl) {
   // the step count, at least 3 slots in the ring); the 3-channel stems (2 MMAs per filter row) take the whole filter.
   int want = MODE == MODE_WIN ? 7 : (BN >= 256 || p.halo ? 1 : 3);
   if (MODE == MODE_LSTM || MODE == MODE_DBHEAD) want = 1;
-  if (const char* e = getenv("VTD_KPS")) { int v = atoi(e); if (v >= 1 && BN < 256) want = v; }
+  if (const char* e = dev_env("VTD_KPS")) { int v = atoi(e); if (v >= 1 && BN < 256) want = v; }
   auto pick = [&](int avail, int* stages_out) {
     int kps = 1;
     for (int c = want; c >= 1; --c) {
@@ -1720,7 +1723,7 @@ static void plan_smem(TcPlan* pl) {
   const int kps_tma = pick(avail - stg_bytes - pool_bytes, &st_tma);
   // the TMA-store epilogue needs 32 KB of staging: take it unless that costs K-step batching or leaves < 3 ring slots
   // (the resident-weight 64-channel 3x3 layers, where the handshake per K step is the larger cost)
-  bool tma = (MODE == MODE_CONV || MODE == MODE_WIN) && !getenv("VTD_NO_TMA_STORE") && kps_tma == kps_plain &&
+  bool tma = (MODE == MODE_CONV || MODE == MODE_WIN) && !dev_env("VTD_NO_TMA_STORE") && kps_tma == kps_plain &&
              st_tma >= (st_plain < 3 ? st_plain : 3);
   if (p.pool && !tma) { p.epi_tma = 0; p.kps = kps_plain; p.stages = st_plain; p.res_tma = 0; p.dbg = 0; pl->smem = 0; return; }   // caller falls back
   if (BN == 256 && tma && st_tma < 4 && st_plain >= 4) tma = false;
@@ -1731,15 +1734,15 @@ static void plan_smem(TcPlan* pl) {
   // residual through TMA as well when another 32 KB leave the ring as deep (and the warp's box is at least 2 px wide
   // for the upsample-add)
   p.res_tma = 0;
-  if (tma && p.res_mode != RES_NONE && !getenv("VTD_NO_TMA_RES") && (p.res_mode != RES_UP2 || p.lw >= 1)) {
+  if (tma && p.res_mode != RES_NONE && !dev_env("VTD_NO_TMA_RES") && (p.res_mode != RES_UP2 || p.lw >= 1)) {
     int st_r = 0;
     if (pick(avail - 2 * stg_bytes - pool_bytes, &st_r) == p.kps && st_r >= (p.halo ? 3 : (p.stages < 4 ? p.stages : 4))) { p.res_tma = 1; p.stages = st_r; }
   }
-  if (const char* e = getenv("VTD_TC_STAGES")) {          // tuning aid: cap the ring depth
+  if (const char* e = dev_env("VTD_TC_STAGES")) {          // tuning aid: cap the ring depth
     int cap = atoi(e);
     if (cap >= 2 && cap < p.stages) p.stages = cap;
   }
-  p.dbg = getenv("VTD_DBG") ? atoi(getenv("VTD_DBG")) : 0;
+  p.dbg = dev_env("VTD_DBG") ? atoi(dev_env("VTD_DBG")) : 0;
   pl->smem = p.stages * (p.win2 ? WIN2_SLOT : p.halo ? HALO_SLOT : p.kps * step_bytes) + (p.bres ? bres_bytes : 0) + (tma ? stg_bytes + pool_bytes : 0) + (p.res_tma ? stg_bytes : 0) + 1024 +
              Cfg::TAIL_BYTES;
 }
@@ -1759,12 +1762,11 @@ static void plan_finalize(TcPlan* pl) {
 template <int BN, int MODE, int KPS = 1>
 static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, const typename ExtraOf<MODE>::type& ex, cudaStream_t s,
                              bool pdl = false) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceFlag attr_done;
+  if (first_on_device(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   const int sms = sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
@@ -1811,11 +1813,10 @@ cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchC
   NoExtra none{0};
   cudaError_t e;
   if (pl->mode == MODE_CONV && p.cta2 == 2) {
-    static bool attrg_done = false;
-    if (!attrg_done) {
+    static PerDeviceFlag attrg_done;
+    if (first_on_device(attrg_done)) {
       cudaError_t ae = cudaFuncSetAttribute(conv_tc2g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (ae != cudaSuccess) return ae;
-      attrg_done = true;
     }
     const int spatial = p.tiles_x * p.tiles_y * p.tiles_n;
     const int pairs = ((spatial + 1) / 2) * p.n_blocks;
@@ -1825,13 +1826,12 @@ cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchC
     return cudaGetLastError();
   }
   if (pl->mode == MODE_CONV && p.cta2) {
-    static bool attr2_done[2] = {false, false};
+    static PerDeviceFlag attr2_done[2];
     const int which = pl->block_n == 256 ? 1 : 0;
-    if (!attr2_done[which]) {
+    if (first_on_device(attr2_done[which])) {
       cudaError_t ae = which ? cudaFuncSetAttribute(conv_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
                              : cudaFuncSetAttribute(conv_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (ae != cudaSuccess) return ae;
-      attr2_done[which] = true;
     }
     const int pairs = (p.total_tiles + 1) / 2;
     const int clusters = pairs < sm_count() / 2 ? pairs : sm_count() / 2;

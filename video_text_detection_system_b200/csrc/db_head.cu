@@ -147,13 +147,11 @@ cudaError_t db_head_tail(const T* feat, const HeadTailWeights& hw, int N, int H4
                          float thr, float* prob, float* thresh, uint8_t* mask, cudaStream_t s, LaunchCounter* lc) {
   if (N <= 0) return cudaSuccess;
   size_t smem = sizeof(float) * (64 * 256 + 64 * (TP + 4) + TP * 16);
-  static bool attr_done[2] = {false, false};
-  const int ti = sizeof(T) == 4 ? 0 : 1;
-  if (!attr_done[ti]) {
+  static PerDeviceFlag attr_done;                 // one flag per instantiation (T)
+  if (first_on_device(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(db_head_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done[ti] = true;
   }
   long long ntiles = (long long)N * H4 * ((W4 + TP - 1) / TP);
   int gx = (int)(ntiles < 148 * 2 ? ntiles : 148 * 2);

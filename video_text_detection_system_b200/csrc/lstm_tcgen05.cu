@@ -365,18 +365,17 @@ void lstm_plan_destroy(LstmPlan* p) { delete p; }
 cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*bf16*/, void* seq_out, int B, int T, cudaStream_t s,
                                  LaunchCounter* lc) {
   if (B <= 0 || T <= 0) return cudaSuccess;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceFlag attr_done;
+  if (first_on_device(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(bilstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   LstmParams p;
   p.xproj = reinterpret_cast<const bf16*>(xproj); p.seq_out = reinterpret_cast<bf16*>(seq_out); p.B = B; p.T = T;
   p.timers = nullptr;
   // 64 sequences per cluster when all clusters are still resident at once: the MMA costs the same (M = 128 either way),
   // the per-step h exchange (DSMEM, ~9 B/cycle/SM measured) and the gate math per CTA halve
-  p.rows = (((B + 63) / 64) * 8 <= tc::sm_count() && !getenv("VTD_LSTM_ROWS128")) ? 64 : 128;
+  p.rows = (((B + 63) / 64) * 8 <= tc::sm_count() && !dev_env("VTD_LSTM_ROWS128")) ? 64 : 128;
   dim3 grid(4, 2, (B + p.rows - 1) / p.rows);
 #ifdef VTD_TIMERS
   if (getenv("VTD_TIMERS")) {

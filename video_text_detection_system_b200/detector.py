@@ -48,7 +48,9 @@ class TextDetector:
         self.max_boxes = max_boxes
         self.unclip_ratio = unclip_ratio
         self.model = DBNet(backbone=backbone, pretrained=pretrained)
-        self.model.dtype_tier = (dtype or os.environ.get("VTD_DTYPE", "fp32")).lower()
+        # the tcgen05 speed tier (16-bit storage: IEEE half) is what the drop-in runs; dtype="fp32" (or VTD_DTYPE=fp32)
+        # selects the CUDA-core <=1e-3 parity tier, dtype="bf16" the bfloat16-storage build of the speed tier
+        self.model.dtype_tier = (dtype or os.environ.get("VTD_DTYPE", "fp16")).lower()
         if model_path:
             self.load_model(model_path)
         self.model.eval()
@@ -94,6 +96,11 @@ class TextDetector:
             eng = self._engine_for(original_height, original_width)
             with self._lock:
                 rec, cnt = eng.run_batch([image], thr=confidence_threshold, recognize=False)
+                over = eng.overflow()
+            if over:
+                # the reference's list is unbounded; here a frame keeps at most max_boxes detections
+                logger.warning("box extraction overflow (flag %d): more than max_boxes=%d detections or candidate "
+                               "slots exhausted; raise max_boxes", over, self.max_boxes)
             dets = records_to_detections(rec[0], int(cnt[0]), with_text=False)
             return dets
         except Exception as e:

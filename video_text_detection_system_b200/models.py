@@ -139,7 +139,7 @@ class DBNet(nn.Module, _EngineOwner):
         self.backbone, in_channels = _resnet_trunk(depth)                 # text_detector.py:17-20
         self.fpn = FeaturePyramidNetwork(in_channels)                     # :22
         self.head = DBHead(256)                                           # :23
-        self.dtype_tier = "fp32"
+        self.dtype_tier = "fp16"                  # the tcgen05 speed tier; "fp32" = CUDA-core parity tier
         if pretrained:
             self._try_load_pretrained(depth)
 
@@ -202,7 +202,7 @@ class CRNN(nn.Module, _EngineOwner):
         self.rnn = nn.LSTM(512, hidden_size, num_layers, batch_first=True, bidirectional=True)   # :26
         self.classifier = nn.Linear(hidden_size * 2, vocab_size)                                 # :27
         self.vocab_size, self.hidden_size, self.num_layers = vocab_size, hidden_size, num_layers
-        self.dtype_tier = "fp32"
+        self.dtype_tier = "fp16"
 
     def load_state_dict(self, *a, **k):
         r = super().load_state_dict(*a, **k)

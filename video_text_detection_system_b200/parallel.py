@@ -59,6 +59,49 @@ def gather_records(records: torch.Tensor, counts: torch.Tensor, dst: int = 0
     return torch.stack(lr), torch.stack(lc)
 
 
+def packed_bytes(frames: int, kmax: int) -> int:
+    """Size of one rank's result block: `frames` x `kmax` records followed by `frames` int32 counts (the layout
+    vtd_get_records documents: the counts directly follow the records in device memory)."""
+    return frames * kmax * RECORD_BYTES + frames * 4
+
+
+def gather_packed(block: torch.Tensor, dst: int = 0, out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """ONE collective per step: every rank contributes its result block (uint8 [packed_bytes]); returns on `dst` the
+    [W, packed_bytes] tensor (written into `out` if given), elsewhere None.  NCCL: all_gather_into_tensor (a single
+    kernel; the payload is ~130 KB per rank, latency-bound); gloo: gather."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if world == 1:
+        if out is not None:
+            out[0].copy_(block)
+            return out
+        return block.unsqueeze(0)
+    if dist.get_backend() == "nccl":
+        if out is None:
+            out = torch.empty((world, block.numel()), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(out, block)
+        return out if rank == dst else None
+    parts = [torch.empty_like(block) for _ in range(world)] if rank == dst else None
+    dist.gather(block.contiguous(), parts, dst=dst)
+    if rank != dst:
+        return None
+    res = torch.stack(parts)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def split_packed(blocks, frames: int, kmax: int) -> Tuple[np.ndarray, np.ndarray]:
+    """[W, packed_bytes] uint8 (tensor or array, host) -> (records [W, frames, kmax*128] uint8, counts [W, frames] int32)."""
+    a = blocks.numpy() if isinstance(blocks, torch.Tensor) else np.asarray(blocks)
+    w = a.shape[0]
+    nrec = frames * kmax * RECORD_BYTES
+    recs = a[:, :nrec].reshape(w, frames, kmax * RECORD_BYTES)
+    cnts = np.ascontiguousarray(a[:, nrec:nrec + frames * 4]).view(np.int32).reshape(w, frames)
+    return recs, cnts
+
+
 def merge_gathered(records: np.ndarray, counts: np.ndarray, n_frames: int, kmax: int, record_dtype) -> List[np.ndarray]:
     """Undo the rank-strided sharding on rank 0: returns, per global frame index, its record array."""
     world, per = counts.shape

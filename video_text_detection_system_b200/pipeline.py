@@ -41,10 +41,16 @@ class VideoTextPipeline:
         # batches kept in flight by process_video: each runs on its own context/stream from an executor thread, so
         # the host->device copy and the latency-bound stages of one batch overlap the convolutions of the other
         self.inflight = int(engine_kwargs.get("inflight", 3))
-        # process_video parks the result dictionaries it has already collected in the collector's permanent
-        # generation (gc.freeze) so that later batches do not pay for re-scanning them: 3.4 -> 1.6 ms of host time
-        # per 16-frame batch at 50 detections per frame.  Undone (gc.unfreeze) before process_video returns.
-        self.freeze_results = bool(engine_kwargs.get("freeze_results", True))
+        # Host-side options, both limited to this object's own work.  pause_gc (default on): the cyclic collector is
+        # paused for the ~1 ms in which a batch's result dictionaries are built (re-entrant, restored on exit).
+        # freeze_results (opt-in, default OFF: it changes process-global collector state, which a host application may
+        # own): process_video parks collected results in the permanent generation (gc.freeze) between batches and undoes
+        # it (gc.unfreeze) before returning.
+        # measurement hook (bench.py): device pointer of an fp32 [batch, det_h, det_w] plane added to the probability logit
+        # (SURVEY.md 8d's planted plane); 0 in production
+        self.logit_bias_dev = 0
+        self.pause_gc = bool(engine_kwargs.get("pause_gc", True))
+        self.freeze_results = bool(engine_kwargs.get("freeze_results", False))
         self._slot_locks = {}
 
     # ---- fused batch path -----------------------------------------------------------------------------
@@ -52,7 +58,8 @@ class VideoTextPipeline:
         """True when a caller replaced detect/recognize/forward (the reference's tests do): fall back to
         the reference's per-frame control flow so the replacements take effect."""
         return ("detect" in vars(self.detector) or "recognize" in vars(self.recognizer)
-                or self.detector._forward_is_patched() or self.recognizer._forward_is_patched())
+                or self.detector._forward_is_patched() or self.recognizer._forward_is_patched()
+                or self.recognizer.use_transformer)      # TrOCR branch: detect on the fused path, recognise per crop list
 
     def _engine(self, src_h: int, src_w: int, n: int, slot: int = 0):
         cap = max(int(self.batch_size), n, 1)
@@ -71,7 +78,14 @@ class VideoTextPipeline:
         h, w = frames[0].shape[:2]
         eng, lock = self._engine(h, w, len(frames), slot)
         with lock:
-            rec, cnt = eng.run_batch(frames, thr=self.confidence_threshold, recognize=True)
+            rec, cnt = eng.run_batch(frames, thr=self.confidence_threshold, recognize=True,
+                                     logit_bias_dev=self.logit_bias_dev)
+            over = eng.overflow()
+        if over:
+            logger.warning("box extraction overflow (flag %d): a frame holds more than max_boxes=%d detections or the "
+                           "candidate slots ran out; raise max_boxes", over, self.detector.max_boxes)
+        if not self.pause_gc:
+            return [records_to_regions(rec[i], int(cnt[i])) for i in range(len(frames))]
         with gc_paused():
             return [records_to_regions(rec[i], int(cnt[i])) for i in range(len(frames))]
 

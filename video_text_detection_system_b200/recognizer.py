@@ -1,8 +1,9 @@
 """TextRecognizer with the reference's call surface (app/ml/models/text_recognizer.py:71-167).
 
-CRNN branch only: crop resize -> conv stack -> 2-layer BiLSTM -> Linear -> softmax -> greedy decode, all in
-libvtd_b200.so.  The TrOCR branch (text_recognizer.py:39-69) is a "next" row: it
-needs downloaded HuggingFace weights; asking for it here logs a warning and uses the CRNN branch.
+CRNN branch: crop resize -> conv stack -> 2-layer BiLSTM -> Linear -> softmax -> greedy decode, all in
+libvtd_b200.so.  The TrOCR branch (text_recognizer.py:39-69) lives in
+transformer_recognizer.py; like the reference's, its constructor raises when no TrOCR weights can be found -- it never
+substitutes the CRNN.
 """
 from __future__ import annotations
 
@@ -26,16 +27,19 @@ class TextRecognizer:
         self.use_transformer = use_transformer
         self.device = "cuda"
         self.crop_w = int(crop_w)
+        self._lock = threading.Lock()
         if use_transformer:
-            logger.warning("TrOCR branch (text_recognizer.py:39-69) is not part of the sm_100a hot path yet; "
-                           "using the CRNN/CTC recogniser")
+            # text_recognizer.py:76-77: the TrOCR branch.  As in the reference, construction fails when the weights are
+            # not to be had (from_pretrained raises offline); no silent substitution of the CRNN.
+            from .transformer_recognizer import TransformerRecognizer
+            self.model = TransformerRecognizer(dtype=dtype)
+            return
         self.vocab = self._build_vocab()
         self.model = CRNN(len(self.vocab))
-        self.model.dtype_tier = (dtype or os.environ.get("VTD_DTYPE", "fp32")).lower()
+        self.model.dtype_tier = (dtype or os.environ.get("VTD_DTYPE", "fp16")).lower()
         if model_path:
             self.load_model(model_path)
         self.model.eval()
-        self._lock = threading.Lock()
 
     def _build_vocab(self) -> Dict[str, int]:
         vocab = {char: i + 1 for i, char in enumerate(CHARS)}          # text_recognizer.py:86-91
@@ -53,12 +57,16 @@ class TextRecognizer:
             raise
 
     def _forward_is_patched(self) -> bool:
-        return "forward" in vars(self.model)
+        return (not self.use_transformer) and "forward" in vars(self.model)
 
     def recognize_batch(self, images: List[np.ndarray]) -> List[Dict[str, Any]]:
+        if self.use_transformer:                                          # text_recognizer.py:103-104
+            return self.model.recognize_batch(images)
         return self._recognize_crnn_batch(images)
 
     def recognize(self, image: np.ndarray) -> Dict[str, Any]:
+        if self.use_transformer:                                          # text_recognizer.py:109-110
+            return self.model.recognize(image)
         return self._recognize_crnn_batch([image])[0]
 
     def _recognize_crnn_batch(self, images: List[np.ndarray]) -> List[Dict[str, Any]]:
