@@ -60,8 +60,13 @@ typedef struct vtd_config {
   int32_t max_src_h, max_src_w; /* largest source frame */
   int32_t canonical_ctc;  /* 0 = reference decode semantics (text_recognizer.py:151-163); 1 = canonical CTC */
   float   unclip_ratio;   /* 1.0 = off = reference behaviour; >1 grows each min-area rect by area*ratio/perimeter */
-  int32_t reserved[4];
+  int32_t flags;          /* VTD_FLAG_* (0 in production) */
+  int32_t reserved[3];
 } vtd_config;
+
+/* Speed tier only: run the DB head as two kernels (3x3 convolutions -> feature map in HBM -> transposed convolutions)
+ * instead of the one-pass kernel.  Same results bit for bit; keeps the intermediate map for vtd_debug_tensor("head"). */
+enum { VTD_FLAG_UNFUSED_HEAD = 1 };
 
 /* One entry of a PyTorch state dict, fp32, C-contiguous, host memory. */
 typedef struct vtd_tensor {

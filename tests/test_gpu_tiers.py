@@ -125,6 +125,40 @@ def test_benched_config_speed_tier_vs_oracle(E, port, crop_w):
     assert same_ids >= 0.9 * n_crops                       # end to end; near-tie argmaxes on random-init weights may flip
 
 
+# ------------------------------------------------------------------------------------- one-pass DB head
+@pytest.mark.parametrize("h,w,n", [(128, 192, 2), (736, 1312, 3), (352, 1024, 1), (64, 64, 2)])
+def test_one_pass_head_equals_two_kernel_head_bit_for_bit(E, port, h, w, n):
+    """Row a4: the fused DB head (3x3 convolutions of both branches, both transposed convolutions, sigmoid and `> thr`
+    in ONE kernel; the 128-channel feature map never reaches HBM) against the two-kernel path of the same library
+    (VTD_FLAG_UNFUSED_HEAD): the same arithmetic in the same order, so probability, threshold and mask must be
+    IDENTICAL -- with and without the planted logit plane, for full and partial batches, odd tile counts (the pair's
+    second CTA repeats the last tile) and maps whose last tile row is half empty (184 = 11.5 x 16), down to 16x16 feature maps (two tiles per image)."""
+    net = port.build_dbnet("resnet18", seed=5)
+    x = np.random.default_rng(h + w).standard_normal((n, 3, h, w)).astype(np.float32)
+    bias = torch.from_numpy((np.random.default_rng(1).standard_normal((n, h, w)) * 4).astype(np.float32)).cuda()
+    outs = []
+    for fuse in (True, False):
+        eng = E.Engine(backbone=18, dtype=T16, det_h=h, det_w=w, max_batch=n, fuse_head=fuse)
+        eng.load_detector(net.state_dict())
+        res = [eng.dbnet_forward(x)]
+        eng.detect_maps(n, 0.3, bias.data_ptr())
+        res.append(eng.read_maps(n))
+        if n > 1:
+            eng.detect_maps(1, 0.7)                          # partial batch
+            res.append(eng.read_maps(1))
+        outs.append(res)
+        eng.close()
+    for a, b in zip(outs[0], outs[1]):
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
+    with torch.no_grad():
+        ref = port.dbnet_forward(net, torch.from_numpy(x))
+    assert np.abs(outs[0][0][0] - ref["probability"].numpy()).max() <= 1e-2
+    assert np.abs(outs[0][0][1] - ref["threshold"].numpy()).max() <= 1e-2
+    p, t, m = outs[0][1]
+    assert np.array_equal(m, (p > 0.3).astype(np.uint8))
+
+
 # ------------------------------------------------------------------------------------- end to end, every tier
 @pytest.mark.parametrize("dtype", ["fp32", "fp16", "bf16"])
 def test_run_batch_every_tier_vs_oracle(E, port, dtype):

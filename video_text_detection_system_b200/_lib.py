@@ -21,6 +21,7 @@ VTD_BF16 = VTD_16BIT                 # round-1 name of the enum value
 VTD_PIX_BGR, VTD_PIX_NV12 = 0, 1
 STAGE_NAMES = ("preprocess", "head_tail", "boxes", "crop", "lstm0", "lstm1", "ctc")   # vtd_op_info(which=2)
 VTD_IDS_STRIDE = 64
+VTD_FLAG_UNFUSED_HEAD = 1
 
 CHARS = "0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~ "
 
@@ -35,7 +36,7 @@ class VtdConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("backbone", C.c_int32), ("dtype", C.c_int32), ("det_h", C.c_int32),
                 ("det_w", C.c_int32), ("crop_w", C.c_int32), ("max_batch", C.c_int32), ("max_boxes", C.c_int32),
                 ("max_src_h", C.c_int32), ("max_src_w", C.c_int32), ("canonical_ctc", C.c_int32),
-                ("unclip_ratio", C.c_float), ("reserved", C.c_int32 * 4)]
+                ("unclip_ratio", C.c_float), ("flags", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class VtdTensor(C.Structure):
@@ -156,7 +157,7 @@ class Engine:
 
     def __init__(self, device: int = 0, backbone: int = 18, dtype: str = "fp32", det_h: int = 640, det_w: int = 640,
                  crop_w: int = 128, max_batch: int = 1, max_boxes: int = 256, max_src_h: int = 2160,
-                 max_src_w: int = 3840, canonical_ctc: bool = False, unclip_ratio: float = 1.0):
+                 max_src_w: int = 3840, canonical_ctc: bool = False, unclip_ratio: float = 1.0, fuse_head: bool = True):
         d = str(dtype).lower()
         # "fp16" / "bf16" name the 16-bit storage type of the speed tier and with it the library; "fp32" (the CUDA-core
         # parity tier) and "16bit" (the speed tier) take the process default (VTD_STORAGE, shipped = half)
@@ -178,6 +179,7 @@ class Engine:
         cfg.max_src_h, cfg.max_src_w = int(max_src_h), int(max_src_w)
         cfg.canonical_ctc = 1 if canonical_ctc else 0
         cfg.unclip_ratio = float(unclip_ratio)
+        cfg.flags = 0 if fuse_head else VTD_FLAG_UNFUSED_HEAD      # parity harness: keep the "head" feature map (same results)
         self.cfg = cfg
         self.det_h, self.det_w, self.crop_w = cfg.det_h, cfg.det_w, cfg.crop_w
         self.max_batch, self.max_boxes = cfg.max_batch, cfg.max_boxes

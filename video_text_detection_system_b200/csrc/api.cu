@@ -34,6 +34,7 @@ struct Op {
   double prof_ms = 0.0; long long prof_n = 0; bool prof_pending = false;
   ConvDesc d{};
   TcPlan* plan = nullptr;
+  bool fused_head = false;      // plan is the one-pass DB head (dbhead_fused_tcgen05): 3x3 convolutions + both tails
   // pool
   const void* pin = nullptr; void* pout = nullptr;
   int H = 0, W = 0, C = 0, kh = 0, kw = 0, sh = 0, sw = 0, ph = 0, pw = 0;
@@ -76,6 +77,8 @@ struct vtd_ctx {
   bool use_win = false, use_tchead = false, use_tclstm = false;   // tcgen05 stems / head tail / LSTM (bf16 tier)
   OutLayout pre_lay{}, crops_lay{};
   TcPlan* head_plan = nullptr;
+  bool head_fused = false;              // the DB head runs as ONE kernel (no feature map in HBM)
+  float cur_thr = 0.5f; const float* cur_bias = nullptr;   // arguments of the detect call in flight (read by the fused head op)
   TcPlan* lstm_plan[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [layer][step parity] (step-wise variant)
   LstmPlan* plstm[2] = {nullptr, nullptr};   // persistent clustered variant (default)
   bool use_plstm = false;
@@ -281,6 +284,7 @@ cudaError_t run_op(vtd_ctx* c, const Op& op, int n) {
     return maxpool_nhwc<float>((const float*)op.pin, (float*)op.pout, n, op.H, op.W, op.C, op.kh, op.kw, op.sh, op.sw,
                                op.ph, op.pw, c->stream, &c->lc);
   }
+  if (op.fused_head) return dbhead_fused_tcgen05(op.plan, n, c->cur_thr, c->cur_bias, c->stream, &c->lc);
   if (op.plan) return conv_tcgen05(op.plan, n, c->stream, &c->lc);
   ConvDesc d = op.d;
   d.N = n;
@@ -444,10 +448,6 @@ int build_detector(vtd_ctx* c, const SD& sd) {
   hm.w.insert(hm.w.end(), ht.w.begin(), ht.w.end());
   hm.b.insert(hm.b.end(), ht.b.begin(), ht.b.end());
   if (hm.Cout != 128) FAIL(VTD_ERR_WEIGHT, "DB head must be 2 x 64 channels");
-  Act hf;
-  if ((r = add_conv(c, &P, hm, B, p2, 1, 1, true, nullptr, RES_NONE, false, &hf))) return r;
-  reg_dbg(c, "head", hf);
-  c->head_feat = hf.p;
   // tail weights: ConvT(64->64,k2,s2)+BN, ConvT(64->1,k2,s2)
   std::vector<float> w1(2 * 256 * 64), b1(2 * 256), w2(2 * 64 * 4), b2(2);
   const char* heads[2] = {"head.probability_head", "head.threshold_head"};
@@ -478,9 +478,28 @@ int build_detector(vtd_ctx* c, const SD& sd) {
       (r = upload_f32(c, b2, &db2)))
     return r;
   c->htw.w1 = dw1; c->htw.b1 = db1; c->htw.w2 = dw2; c->htw.b2 = db2;
+  void* w1b_fused = nullptr;
+  if (c->use_tchead && !(c->cfg.flags & VTD_FLAG_UNFUSED_HEAD)) {
+    // one-pass head: the merged 3x3 convolution, both transposed convolutions, sigmoid and mask in one kernel
+    Op op;
+    op.kind = Op::CONV;
+    ConvDesc& d = op.d;
+    d.in = p2.p; d.N = B; d.H = p2.H; d.W = p2.W; d.Cin = p2.C; d.KH = d.KW = 3; d.stride = 1; d.pad = 1;
+    d.Ho = p2.H; d.Wo = p2.W; d.Cout = 128; d.relu = 1; d.res_mode = RES_NONE; d.out_mode = OUT_NHWC;
+    void* wdev = nullptr; float* bdev = nullptr;
+    if ((r = upload_act_type(c, hm.w, &wdev)) || (r = upload_f32(c, hm.b, &bdev)) || (r = upload_act_type(c, w1, &w1b_fused))) return r;
+    d.w = wdev; d.bias = bdev;
+    std::string e;
+    op.plan = tc_plan_create_headfused(d, w1b_fused, b1.data(), w2.data(), b2.data(), c->prob, c->thresh, c->mask, &e);
+    if (op.plan) { op.fused_head = true; P.push_back(op); c->head_fused = true; return VTD_OK; }
+  }
+  Act hf;
+  if ((r = add_conv(c, &P, hm, B, p2, 1, 1, true, nullptr, RES_NONE, false, &hf))) return r;
+  reg_dbg(c, "head", hf);
+  c->head_feat = hf.p;
   if (c->use_tchead) {
-    void* w1b = nullptr;
-    if ((r = upload_act_type(c, w1, &w1b))) return r;
+    void* w1b = w1b_fused;
+    if (!w1b && (r = upload_act_type(c, w1, &w1b))) return r;
     std::string e;
     c->head_plan = tc_plan_create_dbhead(c->head_feat, B, dh / 4, dw / 4, w1b, b1.data(), w2.data(), b2.data(), c->prob,
                                          c->thresh, c->mask, &e);
@@ -642,7 +661,9 @@ int run_crnn(vtd_ctx* c, int nc) {
 }
 
 int detect_maps_locked(vtd_ctx* c, int n, float thr, const float* logit_bias) {
+  c->cur_thr = thr; c->cur_bias = logit_bias;
   int r = run_prog(c, c->det_prog, n); if (r) return r;
+  if (c->head_fused) return VTD_OK;       // the last op of the program was the whole head
   const int dh = c->cfg.det_h, dw = c->cfg.det_w;
   StageTimer st(c, ST_HEAD_TAIL);
   if (c->head_plan)

@@ -573,8 +573,10 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
   select_kernel<<<dim3(min(cdiv(lay.cap, 256), 148), n), 256, 0, s>>>(ca, cd, mw);
   GeoParams gp{mh, mw, p.clip_h, p.clip_w, p.orig_h, p.orig_w, p.unclip, lay.pool_words};
   static PerDeviceFlag geo_attr;
-  if (first_on_device(geo_attr)) {
-    cudaError_t ge = cudaFuncSetAttribute(geometry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW * GSMEM);
+  {
+    cudaError_t ge = once_per_device(geo_attr, [] {
+      return cudaFuncSetAttribute(geometry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GW * GSMEM);
+    });
     if (ge != cudaSuccess) return ge;
   }
   geometry_kernel<<<dim3(min(cdiv(lay.kc, GW), 32), n), GW * 32, GW * GSMEM, s>>>(mask, labels, prob, ca, cd, gp, pool, pool_used,

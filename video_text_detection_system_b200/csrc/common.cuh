@@ -56,15 +56,21 @@ inline const char* dev_env(const char*) { return nullptr; }
 #endif
 
 // Per-device one-time setup (cudaFuncSetAttribute is a per-device attribute; one process may hold contexts on several
-// GPUs): true the first time it is called for the CURRENT device with this flag word.
+// GPUs, and several host threads may reach a kernel's first launch at once): runs `fn` for the CURRENT device until it
+// has succeeded once; the flag is published only AFTER fn returned, so a concurrent caller either sees it done or
+// repeats the (idempotent) call itself -- it never launches ahead of the attribute.
 struct PerDeviceFlag { unsigned long long mask[2] = {0ull, 0ull}; };
-inline bool first_on_device(PerDeviceFlag& f) {
+template <typename F>
+inline cudaError_t once_per_device(PerDeviceFlag& f, F&& fn) {
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 127;
   const unsigned long long bit = 1ull << (dev & 63);
-  const unsigned long long old = __atomic_fetch_or(&f.mask[dev >> 6], bit, __ATOMIC_ACQ_REL);
-  return (old & bit) == 0;
+  if (__atomic_load_n(&f.mask[dev >> 6], __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+  const cudaError_t e = fn();
+  if (e != cudaSuccess) return e;
+  __atomic_fetch_or(&f.mask[dev >> 6], bit, __ATOMIC_RELEASE);
+  return cudaSuccess;
 }
 
 // ---- implicit-GEMM convolution description (NHWC activations, [Cout][kh][kw][Cin] weights) ------
@@ -97,6 +103,10 @@ TcPlan* tc_plan_create_dbhead(const void* feat, int N, int H4, int W4, const voi
 TcPlan* tc_plan_create_lstm(const void* h_prev, void* h_next, int Bcap, const void* whh, const float* xproj, float* cbuf,
                             void* seq_out, int T, std::string* err);
 cudaError_t dbhead_tcgen05(TcPlan* pl, int n, float thr, const float* logit_bias, cudaStream_t s, LaunchCounter* lc);
+// one-pass DB head (3x3 convolutions of both branches + both transposed convolutions + sigmoid + mask in one kernel)
+TcPlan* tc_plan_create_headfused(const ConvDesc& conv3x3_merged, const void* w1, const float* b1_host, const float* w2_host,
+                                 const float* b2_host, float* prob, float* thresh, uint8_t* mask, std::string* err);
+cudaError_t dbhead_fused_tcgen05(TcPlan* pl, int n, float thr, const float* logit_bias, cudaStream_t s, LaunchCounter* lc);
 cudaError_t lstm_step_tcgen05(const TcPlan* pl, int B, int step, cudaStream_t s, LaunchCounter* lc);
 void tc_plan_destroy(TcPlan*);
 

@@ -1321,6 +1321,325 @@ conv_tc2g_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   }
 }
 
+// ---- one-pass DB head (text_detector.py:58-86 + `> threshold`, :144) -----------------------------------------------------------
+// The whole DBHead of both branches in ONE kernel and one HBM pass: P2 is read once, probability, threshold and mask are
+// written once, and the 128-channel feature map between the 3x3 convolutions and the transposed convolutions never
+// exists in global memory.  Built on the CTA-pair halo convolution above (conv_tc2_kernel<128>: the two branches' 3x3
+// 256->64 convolutions merged into one 256->128 implicit GEMM, BN folded, ReLU):
+//   1. main loop as conv_tc2_kernel<128>: accumulator [128 px x 128 ch] per CTA in TMEM (two buffers, columns 0..255);
+//   2. the 16 epilogue warps add the bias, apply ReLU, round to the 16-bit storage type and write the tile to shared
+//      memory as the K-major SWIZZLE_128B A operand of a second GEMM (one 16 KB slab per branch) -- this IS the feature
+//      map the unfused path stores, bit for bit;
+//   3. ConvTranspose2d(64->64, k2, s2) + BN of one branch is the GEMM [px x 64] x [64 x 256] (256 = 2x2 output
+//      positions x 64 channels): four more tcgen05.mma (cta_group::2, N = 256) into TMEM columns 256..511, issued by
+//      the same MMA warp between the groups of the NEXT tile's convolution MMAs (the tail of tile i overlaps the
+//      convolution of tile i+1; every wait of that warp keeps serving the tail, so the two pipelines cannot deadlock);
+//      W1 (this CTA's 128 rows of each branch, 32 KB) stays resident in shared memory;
+//   4. the epilogue warps read that accumulator: + folded BN shift, ReLU, the second transposed convolution (64 -> 1,
+//      k2, s2: four 64-long dot products per position, fp32 FFMA2, weights in shared memory), + optional logit plane,
+//      sigmoid, `> thr`.  Warp (quarter q, position g = dy*2+dx) owns 32 pixels and one of the four positions: it writes
+//      the 2x2 block of each pixel's 4x4 output block.  The same arithmetic in the same order as MODE_DBHEAD, so the maps
+//      are bit-identical to the unfused path's.
+// Roles per CTA (18 warps): warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warps 2..17 epilogue.
+constexpr int HF_EPI_WARPS = 16;
+constexpr int HF_THREADS = 32 * (2 + HF_EPI_WARPS);
+constexpr int HF_A2_BYTES = 2 * 128 * 128;        // ReLU(feat) of the tile: 2 branches x 128 px x 64 ch x 2 B
+constexpr int HF_W1_BYTES = 2 * 128 * 128;        // this CTA's half of W1: 2 branches x 128 rows x 64 K x 2 B
+constexpr int HF_CONST_BYTES = 4096;              // b1 [2][256] + w2 [2][64][4] fp32
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(HF_THREADS, 1)
+dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const __grid_constant__ HeadConsts ex) {
+  constexpr int BLOCK_N = 128, HALF_N = 64;
+  constexpr int BSLAB = HALF_N * 128;                    // one tap of this CTA's weight half
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t ring = (raw + 1023u) & ~1023u;
+  uint8_t* ring_ptr = smem_raw + (ring - raw);
+  const int a_st = p.stages, b_st = p.b_stages, taps = p.b_taps;
+  const uint32_t bslot = (uint32_t)taps * BSLAB;
+  const uint32_t bring = ring + a_st * HALO_SLOT;
+  const uint32_t a2_0 = bring + b_st * bslot;            // 1024-aligned: HALO_SLOT and bslot are multiples of 1024
+  const uint32_t w1_0 = a2_0 + HF_A2_BYTES;
+  const uint32_t const_0 = w1_0 + HF_W1_BYTES;
+  float* head_s = reinterpret_cast<float*>(ring_ptr + (const_0 - ring));                 // [2][256 b1 + 256 w2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (const_0 - ring) + HF_CONST_BYTES);
+  const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * 4, bfull0 = aempty0 + 8 * 4, bempty0 = bfull0 + 8 * 8;
+  const uint32_t tfull0 = bempty0 + 8 * 8, tempty0 = tfull0 + 8 * 2;
+  const uint32_t a2full = tempty0 + 8 * 2, a2empty = a2full + 8, d2full = a2empty + 8, d2empty = d2full + 8, w1full = d2empty + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  for (int i = threadIdx.x; i < 2 * 512; i += HF_THREADS) {
+    const int hd = i >> 9, r = i & 511;
+    head_s[i] = r < 256 ? ex.b1[hd][r] : (&ex.w2[hd][0][0])[r - 256];
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < a_st; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
+    for (int i = 0; i < b_st; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * HF_EPI_WARPS); }
+    mbar_init(a2full, 2 * HF_EPI_WARPS); mbar_init(a2empty, 1);
+    mbar_init(d2full, 1); mbar_init(d2empty, 2 * HF_EPI_WARPS);
+    mbar_init(w1full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[1]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b4) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // both CTAs' barriers exist before anyone signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kchunks = p.Cin / BLOCK_K;
+  const int tgroups = 9 / taps;
+  const int total_tiles = p.total_tiles;
+  const int npairs = (total_tiles + 1) >> 1;
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int my_pairs = cluster_id < npairs ? (npairs - cluster_id + nclusters - 1) / nclusters : 0;   // tiles this CTA computes
+  auto my_tile = [&](int pair) { const int t = 2 * pair + (int)rank; return t < total_tiles ? t : total_tiles - 1; };   // odd tail: the peer repeats the last tile
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (my_pairs > 0) {
+      if (elect_one()) {
+        // W1: rows rank*128.. of each branch's [256 x 64] matrix; both CTAs' loads complete on the leader's barrier
+        if (rank == 0) mbar_expect_tx(w1full, 2u * HF_W1_BYTES);
+        tma_load_2d_2sm(w1_0, &maps.b, w1full, 0, (int)rank * 128);
+        tma_load_2d_2sm(w1_0 + 128 * 128, &maps.b, w1full, 0, 256 + (int)rank * 128);
+      }
+      __syncwarp();
+    }
+    int as_ = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+    for (int pair = cluster_id; pair < npairs; pair += nclusters) {
+      int t = my_tile(pair);
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int x0 = tx * 8, y0 = ty * 16, n0 = t;
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(aempty0 + 8 * as_, aph ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(afull0 + 8 * as_, 2u * HALO_BYTES);
+          tma_load_4d_2sm(ring + as_ * HALO_SLOT, &maps.a[1], afull0 + 8 * as_, kc * BLOCK_K, x0 - 1, y0 - 1, n0);
+        }
+        __syncwarp();
+        if (++as_ == a_st) { as_ = 0; aph ^= 1; }
+        for (int tg = 0; tg < tgroups; ++tg) {
+          mbar_wait(bempty0 + 8 * bs, bph ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(bfull0 + 8 * bs, 2u * bslot);
+            tma_load_4d_2sm(bring + bs * bslot, &maps.b4, bfull0 + 8 * bs, 0, (int)rank * HALF_N, kc, tg * taps);
+          }
+          __syncwarp();
+          if (++bs == b_st) { bs = 0; bph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && my_pairs > 0) {
+      const uint32_t idesc = (1u << 4) | (VTD_UMMA_AB_FMT << 7) | (VTD_UMMA_AB_FMT << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (VTD_UMMA_AB_FMT << 7) | (VTD_UMMA_AB_FMT << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t d2_tmem = tmem_base + 256u;
+      // tail pipeline: use u = 2 * tile + branch of the D2 accumulator.  MMA2(u) may be issued once the tile's A operand
+      // is in shared memory (branch 0: a2full) and the epilogue has drained the previous use of D2 (d2empty).
+      const int n_uses = 2 * my_pairs;
+      int u = 0;
+      bool w1_ready = false;
+      auto serve_tail = [&]() -> bool {                          // non-blocking; whole warp converged; true if it issued
+        if (u >= n_uses) return false;
+        const int tile = u >> 1, br = u & 1;
+        bool ok = mbar_test(d2empty, (uint32_t)((u & 1) ^ 1));
+        if (br == 0) ok = ok && mbar_test(a2full, (uint32_t)(tile & 1));
+        if (!w1_ready) ok = ok && mbar_test(w1full, 0);
+        if (!__all_sync(0xffffffffu, ok)) return false;
+        w1_ready = true;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint64_t ad = umma_desc<128>(a2_0 + (uint32_t)br * (128u * 128u));
+          const uint64_t bd = umma_desc<128>(w1_0 + (uint32_t)br * (128u * 128u));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_2sm(d2_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc2, k ? 1u : 0u);
+          umma_commit_2sm(d2full);
+          if (br == 1) umma_commit_2sm(a2empty);                 // both branches have read the tile's A operand
+        }
+        __syncwarp();
+        ++u;
+        return true;
+      };
+      auto wait_serving = [&](uint32_t bar, uint32_t parity) {   // a blocking wait that keeps the tail pipeline moving
+        uint32_t spins = 0;
+        while (!__any_sync(0xffffffffu, mbar_test(bar, parity))) {
+          if (!serve_tail() && ++spins == (1u << 28)) __trap();
+        }
+      };
+      int as_ = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t accph = 0;
+      for (int pair = cluster_id; pair < npairs; pair += nclusters) {
+        wait_serving(tempty0 + 8 * acc, accph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          wait_serving(afull0 + 8 * as_, aph);
+          const uint32_t sa = ring + as_ * HALO_SLOT;
+          int fr = 0, fs = 0;
+          for (int tg = 0; tg < tgroups; ++tg) {
+            wait_serving(bfull0 + 8 * bs, bph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint64_t ad0 = umma_desc_sw128(sa + (uint32_t)(fr * HALO_PW + fs) * 128u, HALO_PW * 128u);
+              const uint64_t bd0 = umma_desc<128>(bring + bs * bslot);
+              for (int tt = 0; tt < taps; ++tt)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_2sm(d_tmem, ad0 + (uint64_t)(tt * 8 + k * 2), bd0 + (uint64_t)(tt * (BSLAB >> 4) + k * 2), idesc,
+                               (kc | tg | tt | k) ? 1u : 0u);
+              umma_commit_2sm(bempty0 + 8 * bs);
+              if (tg == tgroups - 1) {
+                umma_commit_2sm(aempty0 + 8 * as_);
+                if (kc == kchunks - 1) umma_commit_2sm(tfull0 + 8 * acc);
+              }
+            }
+            __syncwarp();
+            serve_tail();                                          // the previous tile's transposed convolutions, in between
+            if (taps == 3) ++fr; else if (++fs == 3) { fs = 0; ++fr; }
+            if (++bs == b_st) { bs = 0; bph ^= 1; }
+          }
+          if (++as_ == a_st) { as_ = 0; aph ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; accph ^= 1; }
+      }
+      uint32_t spins = 0;
+      while (u < n_uses) { if (!serve_tail() && ++spins == (1u << 28)) __trap(); }      // drain
+    }
+  } else {
+    // ===================== epilogue (16 warps) =====================
+    const int q = warp & 3;                               // TMEM lane quarter
+    const int sub = (warp - 2) >> 2;                      // 0..3: 32-column slice of the conv tile / output position g
+    const int m = q * 32 + lane;
+    const int xx = m & 7, yy = (m >> 3) & 15;
+    uint32_t tempty_l, a2full_l, d2empty_l;               // the leader's barriers, cluster addresses (own when rank == 0)
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(tempty_l) : "r"(tempty0), "r"(0u));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a2full_l) : "r"(a2full), "r"(0u));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(d2empty_l) : "r"(d2empty), "r"(0u));
+    const int Wd = 4 * p.Wo, Hd = 4 * p.Ho;
+    const int dy = sub >> 1, dx = sub & 1;
+    int it = 0;
+    for (int pair = cluster_id; pair < npairs; pair += nclusters, ++it) {
+      int t = my_tile(pair);
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int ox = tx * 8 + xx, oy = ty * 16 + yy, n = t;
+      const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
+      const int acc = it & 1;
+      // ---- step 1: conv accumulator -> bias, ReLU, 16-bit -> A operand of the transposed-convolution GEMM
+      mbar_wait(tfull0 + 8 * acc, (uint32_t)((it >> 1) & 1));
+      mbar_wait(a2empty, (uint32_t)((it & 1) ^ 1));       // the previous tile's MMA2s have read the slabs
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + sub * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float* bias = p.bias + sub * 32;
+        uint4 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j)), b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j + 4));
+          bf16x2 h0 = pack2(fmaxf(__uint_as_float(v[8 * j]) + b0.x, 0.f), fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f));
+          bf16x2 h1 = pack2(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f));
+          bf16x2 h2 = pack2(fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f));
+          bf16x2 h3 = pack2(fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f));
+          o[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
+        // slab = branch (sub >> 1); row = pixel m (128 bytes = the branch's 64 channels); 16-byte chunk c of the row at c ^ (m & 7)
+        const uint32_t row = a2_0 + (uint32_t)(sub >> 1) * (128u * 128u) + (uint32_t)m * 128u;
+        const uint32_t sw = (uint32_t)(m & 7);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t c = (uint32_t)((sub & 1) * 4 + j);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((c ^ sw) << 4)), "r"(o[j].x), "r"(o[j].y),
+                       "r"(o[j].z), "r"(o[j].w) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the tensor core's reads
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_l + 8 * acc) : "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(a2full_l) : "memory");
+      }
+      // ---- steps 2, 3: per branch, ConvT1 accumulator -> +shift, ReLU -> ConvT2 -> (+logit plane) -> sigmoid -> maps
+#pragma unroll 1
+      for (int br = 0; br < 2; ++br) {
+        mbar_wait(d2full, (uint32_t)br);                   // use u = 2 * it + br: parity u & 1 = br
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float* hs = head_s + br * 512;
+        float o4[4];
+        const float b2 = ex.b2[br];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o4[k] = b2;
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)(sub * 64 + ch * 32), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const float* b1 = hs + sub * 64 + ch * 32;
+          const float4* w2 = reinterpret_cast<const float4*>(hs + 256) + ch * 32;
+          float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float2 h = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                  *reinterpret_cast<const float2*>(b1 + j));
+            h.x = fmaxf(h.x, 0.f); h.y = fmaxf(h.y, 0.f);
+            const float4 w0 = w2[j], w1 = w2[j + 1];
+            a01 = __ffma2_rn(make_float2(h.x, h.x), make_float2(w0.x, w0.y), a01);
+            a23 = __ffma2_rn(make_float2(h.x, h.x), make_float2(w0.z, w0.w), a23);
+            a01 = __ffma2_rn(make_float2(h.y, h.y), make_float2(w1.x, w1.y), a01);
+            a23 = __ffma2_rn(make_float2(h.y, h.y), make_float2(w1.z, w1.w), a23);
+          }
+          o4[0] += a01.x; o4[1] += a01.y; o4[2] += a23.x; o4[3] += a23.y;
+        }
+        // D2 has been read: the next MMA2 may overwrite it while the stores below drain
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(d2empty_l) : "memory");
+        if (valid) {
+          float* __restrict__ outp = br == 0 ? p.prob : p.thresh;
+#pragma unroll
+          for (int dy2 = 0; dy2 < 2; ++dy2) {
+            float v0 = o4[dy2 * 2 + 0], v1 = o4[dy2 * 2 + 1];
+            const size_t oidx = ((size_t)n * Hd + 4 * oy + 2 * dy + dy2) * Wd + 4 * ox + 2 * dx;
+            if (br == 0 && p.logit_bias) {
+              const float2 lb = __ldg(reinterpret_cast<const float2*>(p.logit_bias + oidx));
+              v0 += lb.x; v1 += lb.y;
+            }
+            v0 = 1.0f / (1.0f + expf(-v0)); v1 = 1.0f / (1.0f + expf(-v1));
+            *reinterpret_cast<float2*>(outp + oidx) = make_float2(v0, v1);
+            if (br == 0)
+              *reinterpret_cast<uint16_t*>(p.mask + oidx) = (uint16_t)((v0 > ex.thr ? 1u : 0u) | (v1 > ex.thr ? 0x100u : 0u));
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // nobody exits while the peer may still address its memory
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 
 // tile shape: BN x BH x BW = 128, all powers of two, least padding; ties prefer wider rows
@@ -1636,6 +1955,74 @@ TcPlan* tc_plan_create_lstm(const void* h_prev, void* h_next, int Bcap, const vo
   return pl;
 }
 
+// One-pass DB head plan (dbhead_fused_kernel).  d = the merged 3x3 256->128 convolution of the two branches (input P2,
+// folded BN bias, ReLU); w1: [2][256][64] 16-bit (rows (dy,dx,co)), b1/w2/b2 host fp32 as for tc_plan_create_dbhead.
+// Returns nullptr (err set) when the shape does not tile into 8 x 16 patches with little waste: the caller then keeps the
+// two-kernel path (convolution -> feature map -> MODE_DBHEAD).
+TcPlan* tc_plan_create_headfused(const ConvDesc& d, const void* w1, const float* b1_host, const float* w2_host,
+                                 const float* b2_host, float* prob, float* thresh, uint8_t* mask, std::string* err) {
+  auto fail = [&](const std::string& m) -> TcPlan* { if (err) *err = m; return nullptr; };
+  if (d.KH != 3 || d.KW != 3 || d.stride != 1 || d.pad != 1 || d.Cout != 128 || d.Cin % 64 != 0 || d.Ho < 8 || d.Wo < 8)
+    return fail("not the merged 3x3 head convolution");
+  const long long covered = (long long)((d.Wo + 7) / 8 * 8) * ((d.Ho + 15) / 16 * 16);
+  if (covered * 100 > (long long)d.Wo * d.Ho * 113) return fail("map does not tile into 8 x 16 patches");
+  if (dev_env("VTD_NO_HEAD_FUSION")) return fail("disabled");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available from the driver");
+  TcPlan* pl = new TcPlan();
+  memset(&pl->maps, 0, sizeof(pl->maps));
+  pl->mode = MODE_CONV;
+  fill_common(pl, d.N, d.Ho, d.Wo, d.Cout, d.Cin, 128);
+  TcParams& p = pl->p;
+  p.KH = p.KW = 3; p.stride = 1; p.pad = 1; p.relu = 1; p.bias = d.bias;
+  p.halo = 2; p.cta2 = 1; p.b_taps = 3; p.stages = 2; p.b_stages = 4;
+  p.lw = 3; p.lh = 4;
+  p.tiles_x = (d.Wo + 7) / 8; p.tiles_y = (d.Ho + 15) / 16; p.tiles_n = d.N; p.n_blocks = 1;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  p.prob = prob; p.thresh = thresh; p.mask = mask;
+  if (p.total_tiles < 2) { delete pl; return fail("fewer than two tiles"); }
+  memcpy(pl->hc.b1, b1_host, sizeof(pl->hc.b1));
+  memcpy(pl->hc.w2, w2_host, sizeof(pl->hc.w2));
+  memcpy(pl->hc.b2, b2_host, sizeof(pl->hc.b2));
+  CUresult hr = encode_act4d(enc, &pl->maps.a[1], d.in, d.Cin, d.W, d.H, d.N, d.Cin, (long long)d.W * d.Cin,
+                             (long long)d.H * d.W * d.Cin, HALO_PW, HALO_PH, 1);
+  if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(halo patch) failed: " + std::to_string((int)hr)); }
+  {
+    const long long K = 9LL * d.Cin;
+    cuuint64_t dims[4] = {64, (cuuint64_t)d.Cout, (cuuint64_t)(d.Cin / 64), 9};
+    cuuint64_t strides[3] = {(cuuint64_t)K * 2, 128, (cuuint64_t)d.Cin * 2};
+    cuuint32_t box[4] = {64, 64, 1, 3};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    hr = enc(&pl->maps.b4, VTD_TMAP_16, 4, const_cast<void*>(d.w), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(weights by tap) failed: " + std::to_string((int)hr)); }
+  }
+  hr = encode_weights(enc, &pl->maps.b, w1, 64, 512, 64, 128, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (hr != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(W1) failed: " + std::to_string((int)hr)); }
+  pl->smem = p.stages * HALO_SLOT + p.b_stages * (3 * 64 * 128) + HF_A2_BYTES + HF_W1_BYTES + HF_CONST_BYTES + 512 + 1024;
+  return pl;
+}
+
+cudaError_t dbhead_fused_tcgen05(TcPlan* pl, int n, float thr, const float* logit_bias, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return cudaSuccess;
+  TcParams p = pl->p;
+  p.N = n < pl->p.N ? n : pl->p.N;
+  p.tiles_n = p.N;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  p.logit_bias = logit_bias;
+  pl->hc.thr = thr;
+  static PerDeviceFlag attr_done;
+  cudaError_t e = once_per_device(attr_done, [] {
+    return cudaFuncSetAttribute(dbhead_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (e != cudaSuccess) return e;
+  const int pairs = (p.total_tiles + 1) / 2;
+  const int clusters = pairs < sm_count() / 2 ? pairs : sm_count() / 2;
+  dbhead_fused_kernel<<<2 * clusters, HF_THREADS, pl->smem, s>>>(pl->maps, p, pl->hc);
+  if (lc) lc->n++;
+  return cudaGetLastError();
+}
+
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
 constexpr int SMEM_TOTAL = 227 * 1024;      // dynamic shared memory a CTA may use
@@ -1763,9 +2150,10 @@ template <int BN, int MODE, int KPS = 1>
 static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, const typename ExtraOf<MODE>::type& ex, cudaStream_t s,
                              bool pdl = false) {
   static PerDeviceFlag attr_done;
-  if (first_on_device(attr_done)) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+  {
+    cudaError_t e = once_per_device(attr_done, [] {
+      return cudaFuncSetAttribute(conv_tc_kernel<BN, MODE, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
     if (e != cudaSuccess) return e;
   }
   const int sms = sm_count();
@@ -1814,8 +2202,10 @@ cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchC
   cudaError_t e;
   if (pl->mode == MODE_CONV && p.cta2 == 2) {
     static PerDeviceFlag attrg_done;
-    if (first_on_device(attrg_done)) {
-      cudaError_t ae = cudaFuncSetAttribute(conv_tc2g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    {
+      cudaError_t ae = once_per_device(attrg_done, [] {
+        return cudaFuncSetAttribute(conv_tc2g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      });
       if (ae != cudaSuccess) return ae;
     }
     const int spatial = p.tiles_x * p.tiles_y * p.tiles_n;
@@ -1828,9 +2218,11 @@ cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchC
   if (pl->mode == MODE_CONV && p.cta2) {
     static PerDeviceFlag attr2_done[2];
     const int which = pl->block_n == 256 ? 1 : 0;
-    if (first_on_device(attr2_done[which])) {
-      cudaError_t ae = which ? cudaFuncSetAttribute(conv_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                             : cudaFuncSetAttribute(conv_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    {
+      cudaError_t ae = once_per_device(attr2_done[which], [which] {
+        return which ? cudaFuncSetAttribute(conv_tc2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                     : cudaFuncSetAttribute(conv_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      });
       if (ae != cudaSuccess) return ae;
     }
     const int pairs = (p.total_tiles + 1) / 2;

@@ -148,9 +148,10 @@ cudaError_t db_head_tail(const T* feat, const HeadTailWeights& hw, int N, int H4
   if (N <= 0) return cudaSuccess;
   size_t smem = sizeof(float) * (64 * 256 + 64 * (TP + 4) + TP * 16);
   static PerDeviceFlag attr_done;                 // one flag per instantiation (T)
-  if (first_on_device(attr_done)) {
-    cudaError_t e = cudaFuncSetAttribute(db_head_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+  {
+    cudaError_t e = once_per_device(attr_done, [smem] {
+      return cudaFuncSetAttribute(db_head_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
     if (e != cudaSuccess) return e;
   }
   long long ntiles = (long long)N * H4 * ((W4 + TP - 1) / TP);

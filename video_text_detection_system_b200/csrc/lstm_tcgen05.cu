@@ -366,8 +366,10 @@ cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*bf16*/,
                                  LaunchCounter* lc) {
   if (B <= 0 || T <= 0) return cudaSuccess;
   static PerDeviceFlag attr_done;
-  if (first_on_device(attr_done)) {
-    cudaError_t e = cudaFuncSetAttribute(bilstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
+  {
+    cudaError_t e = once_per_device(attr_done, [] {
+      return cudaFuncSetAttribute(bilstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM);
+    });
     if (e != cudaSuccess) return e;
   }
   LstmParams p;
