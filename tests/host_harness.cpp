@@ -75,12 +75,16 @@ extern "C" int hh_components(const uint8_t* mask, int h, int w, HhComp* out, int
     c.start = i;
     int x0 = i % w, y0 = i / w;
     c.external = (x0 == 0 || y0 == 0) ? 1 : (outside[i - 1] ? 1 : 0);
-    c.area2 = trace_outer_area2(fg, x0, y0, 8LL * n, nullptr);
     int nrows = ymax - ymin + 1;
+    // per-row extremes collected from the border trace itself, as the box extraction kernel does (every row extreme of an
+    // 8-connected component lies on its outer border); cross-checked against the flood fill's extremes
     rowmin.assign(nrows, 1 << 30); rowmax.assign(nrows, -1);
+    c.area2 = trace_outer_visit(fg, x0, y0, 8LL * n, nullptr, [&](int vx, int vy) {
+      rowmin[vy - ymin] = std::min(rowmin[vy - ymin], vx); rowmax[vy - ymin] = std::max(rowmax[vy - ymin], vx);
+    });
     for (int j : pix) {
       int jy = j / w - ymin, jx = j % w;
-      rowmin[jy] = std::min(rowmin[jy], jx); rowmax[jy] = std::max(rowmax[jy], jx);
+      if (jx < rowmin[jy] || jx > rowmax[jy]) return -2;        // a component pixel outside the traced extremes: cannot happen
     }
     hull.resize(2 * nrows + 2);
     int nh = hull_from_rows(rowmin.data(), rowmax.data(), ymin, nrows, hull.data());

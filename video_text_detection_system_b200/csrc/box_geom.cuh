@@ -48,8 +48,11 @@ struct PtF { float x, y; };
 VTD_HD int trace_dx(int s) { return (int)((0x901Au >> (2 * (s & 7))) & 3u) - 1; }   // {1,1,0,-1,-1,-1,0,1}
 VTD_HD int trace_dy(int s) { return (int)((0xA901u >> (2 * (s & 7))) & 3u) - 1; }   // {0,-1,-1,-1,0,1,1,1}
 
-template <class Fg>
-VTD_HD long long trace_outer_area2(const Fg& fg, int x0, int y0, long long max_steps, long long* steps_out) {
+// `visit(x, y)` is called once for every border pixel in visiting order (a pixel the border passes twice is visited
+// twice): the box extraction kernel collects the per-row extremes of the component from it (every row extreme of an
+// 8-connected component lies on its outer border).
+template <class Fg, class Visit>
+VTD_HD long long trace_outer_visit(const Fg& fg, int x0, int y0, long long max_steps, long long* steps_out, const Visit& visit) {
   int s = 4, s_end = 4;
   int x1 = x0, y1 = y0;
   do {
@@ -57,10 +60,11 @@ VTD_HD long long trace_outer_area2(const Fg& fg, int x0, int y0, long long max_s
     x1 = x0 + trace_dx(s); y1 = y0 + trace_dy(s);
   } while (!fg(x1, y1) && s != s_end);
   if (steps_out) *steps_out = 0;
-  if (s == s_end) return 0;                 // isolated pixel
+  if (s == s_end) { visit(x0, y0); return 0; }       // isolated pixel
   long long area2 = 0, steps = 0;
   int x3 = x0, y3 = y0;
   for (;;) {
+    visit(x3, y3);
     int ddx, ddy;
     for (;;) {
       ++s;
@@ -77,6 +81,13 @@ VTD_HD long long trace_outer_area2(const Fg& fg, int x0, int y0, long long max_s
   }
   if (steps_out) *steps_out = steps;
   return area2;
+}
+
+struct NoVisit { VTD_HD void operator()(int, int) const {} };
+
+template <class Fg>
+VTD_HD long long trace_outer_area2(const Fg& fg, int x0, int y0, long long max_steps, long long* steps_out) {
+  return trace_outer_visit(fg, x0, y0, max_steps, steps_out, NoVisit());
 }
 
 // ---- convex hull from per-row extremes ------------------------------------------------------------

@@ -4,26 +4,26 @@
 // findContours(RETR_EXTERNAL) -> contourArea -> minAreaRect -> boxPoints plus the reference's own
 // truncate / clip / scale / size-filter / mean-probability arithmetic, without leaving the device.
 //
-// Pipeline per plane (all kernels take a batch of planes in blockIdx.z / a flat frame index):
-//   1. ccl_rows      : every pixel gets the raster index of the start of its row run (runs of
-//                      foreground AND of background: background is labelled too, 4-connected, so the
-//                      RETR_EXTERNAL nesting rule can be decided without tracing hole borders).
-//   2. ccl_merge     : one union per pair of touching runs in adjacent rows (8-connectivity for
-//                      foreground, 4 for background), lock-free union-find with atomicMin => the root
-//                      of a component is its raster-first pixel, which is where cv::findContours
-//                      starts the outer border.
-//   3. ccl_flatten   : label[i] = root(i).
-//   4. mark_outside  : background roots that reach the frame.
-//   5. collect_roots : one slot per foreground component (bbox seed, external flag).
-//   6. run_extents   : per row run, atomics into the slot's bbox.
-//   7. select        : external && bbox can hold area >= 100  -> candidate list.
-//   8. geometry      : one thread per candidate: outer border trace (area + per-row extremes), convex
-//                      hull, rotating calipers, boxPoints, truncation, AABB, clip, scale, size filter
-//                      (csrc/box_geom.cuh, shared with the CPU unit-test harness).
-//   9. confidence    : one warp per surviving box, mean of the probability plane over the box.
-//  10. pack          : order by raster start index, keep the first kmax, write vtd_record.
-// HBM traffic is a handful of passes over the u8 mask / int32 label plane; everything after step 6
-// touches O(#components) data.
+// Run-length connected components: a text mask is a few dozen blobs on an empty background, i.e. a few runs per row,
+// so nothing here is per-pixel except ONE read of the u8 mask -- there is no label plane.
+//   1. runs      : one warp per row turns the mask row into its list of runs (start x of every run of equal pixels,
+//                  foreground AND background: background is labelled too, 4-connected, so the RETR_EXTERNAL nesting
+//                  rule can be decided without tracing hole borders).  Run id = row * cap_row + index.
+//   2. merge     : one warp per row; every run looks up the runs of the row above that touch it (binary search in
+//                  that row's sorted starts; 8-connectivity for foreground, 4 for background) and unites with the ones
+//                  of its colour: lock-free union-find with atomicMin => the root of a component is its raster-first
+//                  run, whose first pixel is where cv::findContours starts the outer border.
+//   3. flatten   : par[run] = root; background runs on the frame mark their root "outside"; every foreground root
+//                  takes a component slot (bbox seeded with its own run).
+//   4. extents   : every foreground run folds its extent into its component's bbox; the root decides "external"
+//                  (the background run left of the first pixel belongs to a region that reaches the frame).
+//   5. select    : external && bbox can hold area >= 100  -> candidate list.
+//   6. geometry  : one warp per candidate: the candidate's window of the mask is bit-packed into shared memory; the
+//                  outer border trace (area + per-row extremes), convex hull, rotating calipers, boxPoints, truncation,
+//                  AABB, clip, scale and size filter run on one lane (csrc/box_geom.cuh, shared with the CPU unit-test
+//                  harness); the warp then reduces the mean probability over the box.
+//   7. pack      : order by raster start index, keep the first kmax, write vtd_record.
+// HBM traffic: the mask once (1 B/px) plus O(#runs); everything after step 1 touches O(#runs) data.
 #include "common.cuh"
 #include "box_geom.cuh"
 #include "../../include/vtd.h"
@@ -33,150 +33,123 @@ namespace {
 
 using namespace geom;
 
-__device__ __forceinline__ int uf_find(const int* __restrict__ L, int a) {
-  int p = L[a];
-  while (p != a) { a = p; p = L[a]; }
+constexpr int ID_MASK = 0x3fffffff;      // run id inside a plane (< 2^30)
+constexpr int OUT_BIT = 0x40000000;      // on a background ROOT: the region touches the frame
+constexpr int RW = 8;                    // rows (warps) per CTA of the row kernels
+
+struct RunTabs {
+  uint16_t* run_x;   // [n][mh][cap_row] start x of every run, ascending
+  int* nruns;        // [n][mh] (count << 1) | colour of run 0 (1 = foreground); colours alternate along a row
+  int* par;          // [n][mh][cap_row] union-find parent (plane-relative run id); roots may carry OUT_BIT
+  int* slot_of;      // [n][mh][cap_row] component slot, written at foreground roots only
+  int cap_row;       // mw + 1
+};
+
+__device__ __forceinline__ int uf_find(const int* par, int a) {
+  int p = __ldcg(par + a) & ID_MASK;
+  while (p != a) { a = p; p = __ldcg(par + a) & ID_MASK; }
   return a;
 }
 
-__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+// roots only ever decrease (atomicMin), so a stale read is still an ancestor and the loop below repairs itself
+__device__ __forceinline__ void uf_union(int* par, int a, int b) {
   bool done;
   do {
-    a = uf_find(L, a);
-    b = uf_find(L, b);
-    if (a < b) { int old = atomicMin(L + b, a); done = (old == b); b = old; }
-    else if (b < a) { int old = atomicMin(L + a, b); done = (old == a); a = old; }
+    a = uf_find(par, a);
+    b = uf_find(par, b);
+    if (a < b) { int old = atomicMin(par + b, a); done = (old == b); b = old; }
+    else if (b < a) { int old = atomicMin(par + a, b); done = (old == a); a = old; }
     else done = true;
   } while (!done);
 }
 
-// ---- 1. row runs.  One CTA per (row, plane); thread t owns a contiguous chunk of the row.
-constexpr int RT = 256;
-__global__ void __launch_bounds__(RT) ccl_rows_kernel(const uint8_t* __restrict__ mask, int* __restrict__ labels,
-                                                      int mh, int mw) {
-  __shared__ int carry[RT];
-  const int y = blockIdx.x;
-  const size_t plane = (size_t)blockIdx.y * mh * mw;
-  const uint8_t* m = mask + plane + (size_t)y * mw;
-  int* L = labels + plane + (size_t)y * mw;
-  const int per = (mw + RT - 1) / RT;
-  const int x0 = threadIdx.x * per, x1 = min(x0 + per, mw);
-  // last run start inside my chunk (or -1 if my chunk continues the run that enters it)
-  int last = -1;
-  for (int x = x0; x < x1; ++x) {
-    bool start = (x == 0) || ((m[x] != 0) != (m[x - 1] != 0));
-    if (start) last = x;
-  }
-  carry[threadIdx.x] = last;
-  __syncthreads();
-  // inclusive max-scan of `last` over threads
-  for (int off = 1; off < RT; off <<= 1) {
-    int v = carry[threadIdx.x];
-    int o = threadIdx.x >= off ? carry[threadIdx.x - off] : -1;
-    __syncthreads();
-    carry[threadIdx.x] = max(v, o);
-    __syncthreads();
-  }
-  int cur = threadIdx.x > 0 ? carry[threadIdx.x - 1] : 0;
-  for (int x = x0; x < x1; ++x) {
-    bool start = (x == 0) || ((m[x] != 0) != (m[x - 1] != 0));
-    if (start) cur = x;
-    L[x] = y * mw + cur;
-  }
-}
-
-// ---- 2. merge runs of adjacent rows
-// Four pixels per thread: the two mask rows come in as 32-bit words (plus the byte left and right of them), so a pixel
-// costs ~1.5 loads instead of 5; the union rules are the per-pixel ones, unchanged.
-__device__ __forceinline__ void ccl_merge_px(const uint8_t* __restrict__ m, int* L, int mw, int x, int i, bool f, bool n, bool w,
-                                             bool nw, bool ne, bool e) {
-  if (f) {
-    if (n) {
-      if (!w || !nw) uf_union(L, i, i - mw);
-    } else {
-      if (x > 0 && nw && !w) uf_union(L, i, i - mw - 1);
-      if (x + 1 < mw && ne && !e) uf_union(L, i, i - mw + 1);
+// ---- 1. mask row -> runs.  Lane l of the warp takes the 32-pixel words l, l+32, ... of the row; a word's run starts are
+// the set bits of  bits ^ (bits << 1 | last bit of the previous word); a warp scan of the counts gives every start its slot.
+__device__ __forceinline__ uint32_t mask_word(const uint8_t* __restrict__ m, int x0, int mw, bool vec) {
+  uint32_t bits = 0;
+  if (vec && x0 + 32 <= mw) {
+    const uint4* q = reinterpret_cast<const uint4*>(m + x0);
+    const uint4 a = __ldg(q), b = __ldg(q + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t v = w[i];
+      v |= v >> 4; v |= v >> 2; v |= v >> 1;                     // any bit of a byte -> its bit 0
+      bits |= ((((v & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
     }
   } else {
-    if (!n) {
-      if (w || nw || x == 0) uf_union(L, i, i - mw);
+    for (int i = 0; i < 32 && x0 + i < mw; ++i) bits |= (m[x0 + i] != 0 ? 1u : 0u) << i;
+  }
+  return bits;
+}
+
+__global__ void __launch_bounds__(RW * 32) runs_kernel(const uint8_t* __restrict__ mask, RunTabs rt, int mh, int mw) {
+  const int lane = threadIdx.x & 31, y = blockIdx.x * RW + (threadIdx.x >> 5), f = blockIdx.y;
+  if (y >= mh) return;
+  const size_t row = (size_t)f * mh + y;
+  const uint8_t* m = mask + row * mw;
+  uint16_t* rx = rt.run_x + row * rt.cap_row;
+  int* par = rt.par + row * rt.cap_row;
+  const bool vec = (mw & 15) == 0;
+  const int words = (mw + 31) >> 5;
+  const int id0 = y * rt.cap_row;
+  int base = 0;
+  uint32_t carry = 0;                                            // last pixel of the previous word (warp-uniform)
+  int c0 = 0;
+  for (int w0 = 0; w0 < words; w0 += 32) {
+    const int w = w0 + lane;
+    const bool live = w < words;
+    const uint32_t bits = live ? mask_word(m, w * 32, mw, vec) : 0u;
+    const int nvalid = live ? min(32, mw - w * 32) : 0;
+    uint32_t prev = __shfl_up_sync(0xffffffffu, bits >> 31, 1);
+    if (lane == 0) prev = carry;
+    if (w == 0) { prev = (~bits) & 1u; c0 = (int)(bits & 1u); }  // x = 0 always starts a run
+    uint32_t t = bits ^ ((bits << 1) | (prev & 1u));
+    if (nvalid < 32) t &= nvalid > 0 ? ((1u << nvalid) - 1u) : 0u;
+    const int cnt = __popc(t);
+    int inc = cnt;                                               // inclusive scan over the lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    int k = base + inc - cnt;
+    while (t) {
+      const int b = __ffs(t) - 1;
+      t &= t - 1;
+      rx[k] = (uint16_t)(w * 32 + b);
+      par[k] = id0 + k;
+      ++k;
     }
+    base += __shfl_sync(0xffffffffu, inc, 31);
+    // last VALID pixel of the round's last live word (words beyond the row are dead lanes)
+    const int last_lane = min(31, words - 1 - w0);
+    const uint32_t lb = (bits >> ((nvalid > 0 ? nvalid : 1) - 1)) & 1u;
+    carry = __shfl_sync(0xffffffffu, lb, last_lane);
+  }
+  c0 = __shfl_sync(0xffffffffu, c0, 0);
+  if (lane == 0) rt.nruns[row] = (base << 1) | c0;
+}
+
+// ---- 2. unite the runs of row y with the touching runs of row y-1
+__global__ void __launch_bounds__(RW * 32) merge_kernel(RunTabs rt, int mh, int mw) {
+  const int lane = threadIdx.x & 31, y = blockIdx.x * RW + (threadIdx.x >> 5) + 1, f = blockIdx.y;
+  if (y >= mh) return;
+  const size_t row = (size_t)f * mh + y;
+  const int nc_ = rt.nruns[row], nu_ = rt.nruns[row - 1];
+  const int nc = nc_ >> 1, c0 = nc_ & 1, nu = nu_ >> 1, u0 = nu_ & 1;
+  const uint16_t* xs = rt.run_x + row * rt.cap_row;
+  const uint16_t* xu = xs - rt.cap_row;
+  int* par = rt.par + (size_t)f * mh * rt.cap_row;
+  for (int k = lane; k < nc; k += 32) {
+    const int fg = c0 ^ (k & 1);
+    const int s = xs[k], e = (k + 1 < nc ? (int)xs[k + 1] : mw) - 1;
+    const int lo = fg ? max(s - 1, 0) : s, hi = fg ? min(e + 1, mw - 1) : e;   // 8-connected foreground, 4-connected background
+    int a = 0, b = nu - 1;                                       // the run of the row above that holds pixel lo
+    while (a < b) { const int mid = (a + b + 1) >> 1; if ((int)xu[mid] <= lo) a = mid; else b = mid - 1; }
+    int j = a;
+    if ((u0 ^ (j & 1)) != fg) ++j;                               // colours alternate: every second run is mine
+    for (; j < nu && (int)xu[j] <= hi; j += 2) uf_union(par, y * rt.cap_row + k, (y - 1) * rt.cap_row + j);
   }
 }
 
-__global__ void ccl_merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__ labels, int mh, int mw) {
-  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y + 1;
-  if (x0 >= mw || y >= mh) return;
-  const size_t plane = (size_t)blockIdx.z * mh * mw;
-  const uint8_t* m = mask + plane;
-  int* L = labels + plane;
-  const int i0 = y * mw + x0;
-  uint8_t cur[6], up[6];                                  // pixels x0-1 .. x0+4 of rows y and y-1 (out of frame: see below)
-  if ((mw & 3) == 0 && x0 + 4 <= mw) {
-    const uint32_t c4 = *reinterpret_cast<const uint32_t*>(m + i0), u4 = *reinterpret_cast<const uint32_t*>(m + i0 - mw);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { cur[k + 1] = (uint8_t)(c4 >> (8 * k)); up[k + 1] = (uint8_t)(u4 >> (8 * k)); }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool in = x0 + k < mw;
-      cur[k + 1] = in ? m[i0 + k] : 0; up[k + 1] = in ? m[i0 + k - mw] : 0;
-    }
-  }
-  cur[0] = x0 > 0 ? m[i0 - 1] : 0; up[0] = x0 > 0 ? m[i0 - mw - 1] : 0;
-  cur[5] = x0 + 4 < mw ? m[i0 + 4] : 0; up[5] = x0 + 4 < mw ? m[i0 + 4 - mw] : 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int x = x0 + k;
-    if (x >= mw) break;
-    const bool f = cur[k + 1] != 0;
-    const bool w = x > 0 ? (cur[k] != 0) : !f;              // out of frame == "other class"
-    const bool nw = x > 0 ? (up[k] != 0) : !f;
-    ccl_merge_px(m, L, mw, x, i0 + k, f, up[k + 1] != 0, w, nw, up[k + 2] != 0, cur[k + 2] != 0);
-  }
-}
-// NOTE on the foreground NE rule: when N is background and NE is foreground, pixel E (if foreground)
-// sees NE as its N with a background NW and performs the union itself; only when E is background does
-// this pixel have to do it.
-
-// Four pixels per thread (16-byte load/store); pixels of one run carry the same label after ccl_rows/ccl_merge, so a
-// run costs one root chase per 4 pixels instead of four.
-__global__ void ccl_flatten_plane_kernel(int* __restrict__ labels, int plane_px) {
-  int* L = labels + (size_t)blockIdx.y * plane_px;
-  if (plane_px & 3) {                                   // planes not 16-byte aligned: scalar
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane_px; i += gridDim.x * blockDim.x) L[i] = uf_find(L, i);
-    return;
-  }
-  const int quads = plane_px >> 2;
-  for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += gridDim.x * blockDim.x) {
-    int4 l = reinterpret_cast<const int4*>(L)[qd];
-    int4 r;
-    r.x = uf_find(L, l.x);
-    r.y = l.y == l.x ? r.x : uf_find(L, l.y);
-    r.z = l.z == l.y ? r.y : uf_find(L, l.z);
-    r.w = l.w == l.z ? r.z : uf_find(L, l.w);
-    reinterpret_cast<int4*>(L)[qd] = r;
-  }
-}
-
-// ---- 4. background roots connected to the frame
-__global__ void mark_outside_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ labels,
-                                    uint8_t* __restrict__ outside, int mh, int mw) {
-  const size_t plane = (size_t)blockIdx.y * mh * mw;
-  const int per = 2 * (mh + mw);
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per; t += gridDim.x * blockDim.x) {
-    int x, y;
-    if (t < mw) { x = t; y = 0; }
-    else if (t < 2 * mw) { x = t - mw; y = mh - 1; }
-    else if (t < 2 * mw + mh) { x = 0; y = t - 2 * mw; }
-    else { x = mw - 1; y = t - 2 * mw - mh; }
-    int i = y * mw + x;
-    if (mask[plane + i] == 0) outside[plane + labels[plane + i]] = 1;
-  }
-}
-
-// ---- 5. component slots
 struct CompArrays {
   int* start;     // [n][cap] raster index of the component's first pixel
   int* xmin;      // [n][cap]
@@ -187,52 +160,74 @@ struct CompArrays {
   int cap;
 };
 
-__global__ void collect_roots_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ labels,
-                                     const uint8_t* __restrict__ outside, int* __restrict__ slot_plane,
-                                     CompArrays ca, int mh, int mw) {
-  const int f = blockIdx.y;
-  const int plane_px = mh * mw;
-  const size_t plane = (size_t)f * plane_px;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane_px; i += gridDim.x * blockDim.x) {
-    if (mask[plane + i] == 0 || labels[plane + i] != i) continue;
-    int s = atomicAdd(ca.count + f, 1);
-    slot_plane[plane + i] = s;
-    if (s >= ca.cap) continue;
-    int x = i % mw, y = i / mw;
-    size_t o = (size_t)f * ca.cap + s;
-    ca.start[o] = i;
-    ca.xmin[o] = x; ca.xmax[o] = x; ca.ymax[o] = y;
-    // RETR_EXTERNAL: the pixel left of the raster-first pixel is background; the component is top-level
-    // iff that background region reaches the (zero-padded) frame.
-    ca.external[o] = (x == 0 || y == 0) ? 1 : (int)outside[plane + labels[plane + i - 1]];
-  }
-}
-
-// ---- 6. bbox of every component from its row runs
-__global__ void run_extents_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ labels,
-                                   const int* __restrict__ slot_plane, CompArrays ca, int mh, int mw) {
-  const int f = blockIdx.y;
-  const int plane_px = mh * mw;
-  const size_t plane = (size_t)f * plane_px;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plane_px; i += gridDim.x * blockDim.x) {
-    if (mask[plane + i] == 0) continue;
-    int x = i % mw;
-    bool rs = (x == 0) || mask[plane + i - 1] == 0;
-    bool re = (x == mw - 1) || mask[plane + i + 1] == 0;
-    if (!rs && !re) continue;
-    int s = slot_plane[plane + labels[plane + i]];
-    if (s >= ca.cap) continue;
-    size_t o = (size_t)f * ca.cap + s;
-    if (rs && x < ca.xmin[o]) atomicMin(ca.xmin + o, x);
-    if (re) {
-      if (x > ca.xmax[o]) atomicMax(ca.xmax + o, x);
-      int y = i / mw;
-      if (y > ca.ymax[o]) atomicMax(ca.ymax + o, y);
+// ---- 3. flatten; frame-touching background roots; component slots
+__global__ void __launch_bounds__(RW * 32) flatten_kernel(RunTabs rt, CompArrays ca, int mh, int mw) {
+  const int lane = threadIdx.x & 31, y = blockIdx.x * RW + (threadIdx.x >> 5), f = blockIdx.y;
+  if (y >= mh) return;
+  const size_t row = (size_t)f * mh + y;
+  const int nc_ = rt.nruns[row];
+  const int nc = nc_ >> 1, c0 = nc_ & 1;
+  const uint16_t* xs = rt.run_x + row * rt.cap_row;
+  const size_t plane = (size_t)f * mh * rt.cap_row;
+  int* par = rt.par + plane;
+  for (int k = lane; k < nc; k += 32) {
+    const int id = y * rt.cap_row + k;
+    const int fg = c0 ^ (k & 1);
+    const int s = xs[k], e = (k + 1 < nc ? (int)xs[k + 1] : mw) - 1;
+    const int r = uf_find(par, id);
+    if (r != id) par[id] = r;                                    // roots keep their word (it may carry OUT_BIT)
+    if (!fg) {
+      if (y == 0 || y == mh - 1 || s == 0 || e == mw - 1) atomicOr(par + r, OUT_BIT);
+    } else if (r == id) {
+      const int slot = atomicAdd(ca.count + f, 1);
+      rt.slot_of[plane + id] = slot;
+      if (slot < ca.cap) {
+        const size_t o = (size_t)f * ca.cap + slot;
+        ca.start[o] = y * mw + s;
+        ca.xmin[o] = s; ca.xmax[o] = e; ca.ymax[o] = y;
+      }
     }
   }
 }
 
-// ---- 7. candidates
+// ---- 4. bbox of every component from its runs; RETR_EXTERNAL flag
+__global__ void __launch_bounds__(RW * 32) extents_kernel(RunTabs rt, CompArrays ca, int mh, int mw) {
+  const int lane = threadIdx.x & 31, y = blockIdx.x * RW + (threadIdx.x >> 5), f = blockIdx.y;
+  if (y >= mh) return;
+  const size_t row = (size_t)f * mh + y;
+  const int nc_ = rt.nruns[row];
+  const int nc = nc_ >> 1, c0 = nc_ & 1;
+  const uint16_t* xs = rt.run_x + row * rt.cap_row;
+  const size_t plane = (size_t)f * mh * rt.cap_row;
+  const int* par = rt.par + plane;
+  for (int kk = lane; 2 * kk + (c0 ^ 1) < nc; kk += 32) {        // foreground runs: k = c0 ? 0,2,4.. : 1,3,5..
+    const int k = 2 * kk + (c0 ^ 1);
+    const int id = y * rt.cap_row + k;
+    const int s = xs[k], e = (k + 1 < nc ? (int)xs[k + 1] : mw) - 1;
+    const int r = __ldcg(par + id) & ID_MASK;                    // flattened: the root itself
+    const int slot = rt.slot_of[plane + r];
+    if (slot >= ca.cap) continue;
+    const size_t o = (size_t)f * ca.cap + slot;
+    if (r != id) {
+      if (s < ca.xmin[o]) atomicMin(ca.xmin + o, s);
+      if (e > ca.xmax[o]) atomicMax(ca.xmax + o, e);
+      if (y > ca.ymax[o]) atomicMax(ca.ymax + o, y);
+    } else {
+      // RETR_EXTERNAL: the pixel left of the raster-first pixel is background; the component is top-level iff that
+      // background region reaches the (zero-padded) frame.
+      int ext = 1;
+      if (s > 0 && y > 0) {
+        const int pl = __ldcg(par + id - 1);
+        const int rl = pl & ID_MASK;
+        const int word = rl == id - 1 ? pl : __ldcg(par + rl);
+        ext = (word & OUT_BIT) ? 1 : 0;
+      }
+      ca.external[o] = ext;
+    }
+  }
+}
+
+// ---- 5. candidates
 struct CandArrays {
   int* slot;      // [n][kc]
   int* count;     // [n]
@@ -253,7 +248,7 @@ __global__ void select_kernel(CompArrays ca, CandArrays cd, int mw) {
   }
 }
 
-// ---- 8. geometry of one candidate
+// ---- 6. geometry of one candidate
 struct TmpBox {
   int valid;
   int start;
@@ -269,19 +264,15 @@ struct GeoParams {
   int pool_words;           // per-plane scratch pool size, 4-byte words
 };
 
-// One WARP per candidate.  The candidate's bounding box of the mask (+1 px border) is staged in shared memory, so
-// the inherently sequential outer-border trace runs against ~25-cycle shared-memory probes instead of L2 round
-// trips; per-row extremes come from the label plane in parallel (lanes stride over x); lane 0 then runs the hull /
-// rotating-calipers arithmetic (O(#rows), scratch in shared memory), and the whole warp reduces the mean
-// probability of the resulting box.  Components too large for the per-warp budget fall back to global scratch.
-#ifdef VTD_TIMERS
-__device__ int getenv_timers = 1;
-#endif
+// One WARP per candidate.  The candidate's window of the mask (bbox + 1 px, columns rounded out to 32) is bit-packed into
+// shared memory, one word per 32 pixels, so the inherently sequential outer-border trace probes a register-speed bit
+// test instead of L2; the trace itself yields the per-row extremes; lane 0 then runs the hull / rotating-calipers
+// arithmetic (O(#rows), scratch in shared memory), and the whole warp reduces the mean probability of the resulting
+// box.  Components too large for the per-warp budget fall back to the global mask and global scratch.
 constexpr int GW = 4;                    // candidates (warps) per CTA
 constexpr int GSMEM = 16 * 1024;         // shared-memory bytes per candidate
 
 __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __restrict__ mask,
-                                                           const int* __restrict__ labels,
                                                            const float* __restrict__ prob, CompArrays ca, CandArrays cd,
                                                            GeoParams gp, int* __restrict__ pool,
                                                            int* __restrict__ pool_used, TmpBox* __restrict__ tmp,
@@ -290,12 +281,8 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.y;
   const int nc = min(cd.count[f], cd.kc);
-  // a fixed, small grid walks the candidate list (the capacity is 1024 per plane, a frame has ~50: one CTA per
-  // capacity slot spent most of the kernel scheduling 4096 CTAs of 64 KB that exit at once)
+  // a fixed, small grid walks the candidate list (the capacity is 1024 per plane, a frame has ~50)
   for (int c = blockIdx.x * GW + warp; c < nc; c += gridDim.x * GW) {
-#ifdef VTD_TIMERS
-  const long long gt0 = clock64(); long long gt1 = 0, gt2 = 0, gt3 = 0, gt4 = 0, gt5 = 0;
-#endif
   TmpBox& tb = tmp[(size_t)f * cd.kc + c];
   if (lane == 0) tb.valid = 0;
   const int s = cd.slot[(size_t)f * cd.kc + c];
@@ -305,15 +292,16 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   const int x0 = start % mw, y0 = start / mw;
   const int xmin = ca.xmin[o], xmax = ca.xmax[o];
   const int nrows = ca.ymax[o] - y0 + 1;
-  const int rw = xmax - xmin + 3, rh = nrows + 2;          // staged region incl. 1 px border
-  const int bx0 = xmin - 1, by0 = y0 - 1;
-  const int mask_bytes = (rw * rh + 15) & ~15;
+  const int by0 = y0 - 1, rh = nrows + 2;
+  const int bx0 = (xmin - 1) & ~31;                          // window origin, a multiple of 32 (-32 when xmin == 0)
+  const int wpr = ((xmax + 1 - bx0) >> 5) + 1;               // words per window row
+  const long long words = (long long)wpr * rh;
   const int scratch_words = 12 * nrows + 16;
-  const bool use_smem = mask_bytes + 4 * scratch_words <= GSMEM;
-  uint8_t* sm_mask = gsm + warp * GSMEM;
+  const bool use_smem = words * 4 + 4LL * scratch_words <= GSMEM;
+  uint32_t* bitsm = reinterpret_cast<uint32_t*>(gsm + warp * GSMEM);
   int* scr;
   if (use_smem) {
-    scr = reinterpret_cast<int*>(sm_mask + mask_bytes);
+    scr = reinterpret_cast<int*>(bitsm + words);
   } else {
     int off = 0;
     if (lane == 0) off = atomicAdd(pool_used + f, scratch_words);
@@ -326,82 +314,45 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   Pt* hull = reinterpret_cast<Pt*>(scr + 2 * nrows);
   float* fl = reinterpret_cast<float*>(scr + 2 * nrows + 2 * (2 * nrows + 2));
   const uint8_t* m = mask + (size_t)f * mh * mw;
-  const int* L = labels + (size_t)f * mh * mw;
 
   if (use_smem) {
-    // membership of THIS component (label == raster index of its first pixel), bbox + 1 px border.  Foreground pixels
-    // 8-adjacent to a pixel of the component belong to the component, so the outer-border trace sees the same
-    // neighbourhood in this plane as in the mask.  Rows are fetched 4 at a time: 4 x ceil(rw/32) independent loads in
-    // flight per lane instead of one dependent L2 round trip per element.
-    for (int yy = 0; yy < rh; yy += 4) {
-      for (int xx = lane; xx < rw; xx += 32) {
-        const int gx = bx0 + xx;
-        int v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int gy = by0 + yy + k;
-          v[k] = (yy + k < rh && (unsigned)gx < (unsigned)mw && (unsigned)gy < (unsigned)mh) ? L[(size_t)gy * mw + gx] : -1;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (yy + k < rh) sm_mask[(yy + k) * rw + xx] = v[k] == start ? (uint8_t)1 : (uint8_t)0;
+    const bool vec = (mw & 15) == 0;
+    for (int idx = lane; idx < (int)words; idx += 32) {
+      const int r = idx / wpr, wi = idx - r * wpr;
+      const int gy = by0 + r, gx = bx0 + 32 * wi;
+      uint32_t wbits = 0;
+      if ((unsigned)gy < (unsigned)mh && gx < mw) {
+        if (gx >= 0) wbits = mask_word(m + (size_t)gy * mw, gx, mw, vec);
       }
+      bitsm[idx] = wbits;
     }
-    __syncwarp();
-    // per-row extremes: one lane per row, scanning shared memory
-    for (int r = lane; r < nrows; r += 32) {
-      const uint8_t* row = sm_mask + (r + 1) * rw + 1;        // x = xmin at offset 0
-      const int wd = xmax - xmin + 1;
-      int lo = 0, hi = wd - 1;
-      while (lo < wd && !row[lo]) ++lo;
-      while (hi >= 0 && !row[hi]) --hi;
-      rowmin[r] = lo < wd ? xmin + lo : (1 << 30);
-      rowmax[r] = hi >= 0 ? xmin + hi : -1;
-    }
-  } else {
-  // per-row extremes of THIS component (label == raster index of its first pixel)
-  for (int r = 0; r < nrows; ++r) {
-    int lo = 1 << 30, hi = -1;
-    const int* row = L + (size_t)(y0 + r) * mw;
-    for (int x = xmin + lane; x <= xmax; x += 32)
-      if (row[x] == start) { lo = min(lo, x); hi = max(hi, x); }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-    }
-    if (lane == 0) { rowmin[r] = lo; rowmax[r] = hi; }
   }
-  }
+  for (int r = lane; r < nrows; r += 32) { rowmin[r] = 1 << 30; rowmax[r] = -1; }
   __syncwarp();
 
-#ifdef VTD_TIMERS
-  gt1 = clock64();
-#endif
   int ok = 0;
   if (lane == 0) {
     do {
-      auto fg_s = [&](int x, int y) -> bool { return sm_mask[(y - by0) * rw + (x - bx0)] != 0; };
+      auto fg_s = [&](int x, int y) -> bool {
+        const int xx = x - bx0;
+        return (bitsm[(y - by0) * wpr + (xx >> 5)] >> (xx & 31)) & 1u;
+      };
       auto fg_g = [&](int x, int y) -> bool {
-        return (unsigned)x < (unsigned)mw && (unsigned)y < (unsigned)mh && m[y * mw + x] != 0;
+        return (unsigned)x < (unsigned)mw && (unsigned)y < (unsigned)mh && m[(size_t)y * mw + x] != 0;
+      };
+      auto visit = [&](int x, int y) {
+        const int r = y - y0;
+        if (x < rowmin[r]) rowmin[r] = x;
+        if (x > rowmax[r]) rowmax[r] = x;
       };
       const long long max_steps = 8LL * mw * mh;
-      long long area2 = use_smem ? trace_outer_area2(fg_s, x0, y0, max_steps, nullptr)
-                                 : trace_outer_area2(fg_g, x0, y0, max_steps, nullptr);
-#ifdef VTD_TIMERS
-      gt2 = clock64();
-#endif
+      long long area2 = use_smem ? trace_outer_visit(fg_s, x0, y0, max_steps, nullptr, visit)
+                                 : trace_outer_visit(fg_g, x0, y0, max_steps, nullptr, visit);
       if (area2 < 0) area2 = -area2;
       if (area2 < 200) break;                  // cv2.contourArea(contour) < 100 -> skip (text_detector.py:150)
       int nh = hull_from_rows(rowmin, rowmax, y0, nrows, hull);
-#ifdef VTD_TIMERS
-      gt3 = clock64();
-#endif
       if (nh < 3) break;
       RotRect rr = min_area_rect(hull, nh, fl, fl + nh, fl + 2 * nh);
-#ifdef VTD_TIMERS
-      gt4 = clock64();
-#endif
       unclip_rect(rr, gp.unclip);
       PtF bp[4];
       box_points(rr, bp);
@@ -458,12 +409,6 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     res = (float)(acc / ((double)h * (double)w));
   }
-#ifdef VTD_TIMERS
-  gt5 = clock64();
-  if (lane == 0 && f == 0 && c < 2 && getenv_timers)
-    printf("GEOM c=%d rw=%d rh=%d nrows=%d | stage+extremes %lld trace %lld hull %lld calipers %lld rest+conf %lld total %lld\n", c, rw, rh,
-           nrows, gt1 - gt0, gt2 - gt1, gt3 - gt2, gt4 - gt3, gt5 - gt4, gt5 - gt0);
-#endif
   if (lane == 0) { tb.conf = res; __threadfence_block(); tb.valid = 1; }
   __syncwarp();
   }
@@ -514,15 +459,17 @@ inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 }  // namespace
 
 size_t box_work_bytes(int n, int mh, int mw, int kc, BoxWorkLayout* lay) {
-  const size_t px = (size_t)mh * mw;
   const int cap = ((mh + 1) / 2) * ((mw + 1) / 2) + 1;     // 8-connected components cannot be denser
   const int pool_words = 256 * mh * 12 + 4096;
+  const int cap_row = mw + 1;                               // a row of mw pixels has at most mw runs
+  const size_t nrun = (size_t)n * mh * cap_row;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-  lay->cap = cap; lay->kc = kc; lay->pool_words = pool_words;
-  lay->labels = take(px * n * 4);
-  lay->slot_plane = take(px * n * 4);
-  lay->outside = take(px * n);
+  lay->cap = cap; lay->kc = kc; lay->pool_words = pool_words; lay->cap_row = cap_row;
+  lay->run_x = take(nrun * 2);
+  lay->nruns = take((size_t)n * mh * 4);
+  lay->par = take(nrun * 4);
+  lay->slot_of = take(nrun * 4);
   lay->comp = take((size_t)n * cap * 4 * 5);
   lay->cand_slot = take((size_t)n * kc * 4);
   lay->tmp = take((size_t)n * kc * sizeof(TmpBox));
@@ -541,10 +488,13 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
                           LaunchCounter* lc) {
   if (p.n <= 0) return cudaSuccess;
   const int n = p.n, mh = p.mh, mw = p.mw;
-  const size_t px = (size_t)mh * mw;
-  int* labels = reinterpret_cast<int*>(work + lay.labels);
-  int* slot_plane = reinterpret_cast<int*>(work + lay.slot_plane);
-  uint8_t* outside = work + lay.outside;
+  if (mw > 65535 || (long long)mh * lay.cap_row > ID_MASK) return cudaErrorInvalidValue;
+  RunTabs rt;
+  rt.run_x = reinterpret_cast<uint16_t*>(work + lay.run_x);
+  rt.nruns = reinterpret_cast<int*>(work + lay.nruns);
+  rt.par = reinterpret_cast<int*>(work + lay.par);
+  rt.slot_of = reinterpret_cast<int*>(work + lay.slot_of);
+  rt.cap_row = lay.cap_row;
   CompArrays ca;
   int* comp = reinterpret_cast<int*>(work + lay.comp);
   const size_t cs = (size_t)p.n_alloc * lay.cap;
@@ -561,15 +511,12 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
   int* overflow = reinterpret_cast<int*>(work + lay.overflow);
   cudaError_t e;
   if ((e = cudaMemsetAsync(work + lay.zero_begin, 0, lay.zero_end - lay.zero_begin, s)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(outside, 0, px * n, s)) != cudaSuccess) return e;
 
-  ccl_rows_kernel<<<dim3(mh, n), RT, 0, s>>>(mask, labels, mh, mw);
-  if (mh > 1) ccl_merge_kernel<<<dim3(cdiv(cdiv(mw, 4), 128), mh - 1, n), 128, 0, s>>>(mask, labels, mh, mw);
-  const int gx = min(cdiv((long long)px, 256), 148 * 8);
-  ccl_flatten_plane_kernel<<<dim3(min(cdiv((long long)px / 4 + 1, 256), 148 * 8), n), 256, 0, s>>>(labels, (int)px);
-  mark_outside_kernel<<<dim3(cdiv(2 * (mh + mw), 256), n), 256, 0, s>>>(mask, labels, outside, mh, mw);
-  collect_roots_kernel<<<dim3(gx, n), 256, 0, s>>>(mask, labels, outside, slot_plane, ca, mh, mw);
-  run_extents_kernel<<<dim3(gx, n), 256, 0, s>>>(mask, labels, slot_plane, ca, mh, mw);
+  const dim3 rows(cdiv(mh, RW), n);
+  runs_kernel<<<rows, RW * 32, 0, s>>>(mask, rt, mh, mw);
+  if (mh > 1) merge_kernel<<<dim3(cdiv(mh - 1, RW), n), RW * 32, 0, s>>>(rt, mh, mw);
+  flatten_kernel<<<rows, RW * 32, 0, s>>>(rt, ca, mh, mw);
+  extents_kernel<<<rows, RW * 32, 0, s>>>(rt, ca, mh, mw);
   select_kernel<<<dim3(min(cdiv(lay.cap, 256), 148), n), 256, 0, s>>>(ca, cd, mw);
   GeoParams gp{mh, mw, p.clip_h, p.clip_w, p.orig_h, p.orig_w, p.unclip, lay.pool_words};
   static PerDeviceFlag geo_attr;
@@ -579,10 +526,10 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
     });
     if (ge != cudaSuccess) return ge;
   }
-  geometry_kernel<<<dim3(min(cdiv(lay.kc, GW), 32), n), GW * 32, GW * GSMEM, s>>>(mask, labels, prob, ca, cd, gp, pool, pool_used,
-                                                                        tmp, overflow);
+  geometry_kernel<<<dim3(min(cdiv(lay.kc, GW), 32), n), GW * 32, GW * GSMEM, s>>>(mask, prob, ca, cd, gp, pool, pool_used, tmp,
+                                                                                  overflow);
   pack_kernel<<<n, 256, 0, s>>>(cd, tmp, reinterpret_cast<vtd_record*>(records), counts, p.kmax, overflow);
-  if (lc) lc->n += (mh > 1 ? 9 : 8);
+  if (lc) lc->n += (mh > 1 ? 7 : 6);
   return cudaGetLastError();
 }
 

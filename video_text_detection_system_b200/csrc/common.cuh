@@ -168,9 +168,9 @@ struct BoxParams {
   float unclip;
 };
 struct BoxWorkLayout {       // byte offsets into one device workspace (see boxes.cu)
-  size_t labels, slot_plane, outside, comp, cand_slot, tmp, pool, zero_begin, comp_count, cand_count, pool_used,
+  size_t run_x, nruns, par, slot_of, comp, cand_slot, tmp, pool, zero_begin, comp_count, cand_count, pool_used,
       zero_end, overflow;
-  int cap, kc, pool_words;
+  int cap, kc, pool_words, cap_row;
 };
 size_t box_work_bytes(int n_alloc, int mh, int mw, int kc, BoxWorkLayout* lay);
 cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParams& p, uint8_t* work,

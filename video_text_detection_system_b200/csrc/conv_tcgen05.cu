@@ -1480,6 +1480,10 @@ dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const
         }
       };
       int as_ = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t accph = 0;
+      // p.kps (here: groups in flight, 0 = unlimited): the tensor pipe executes in issue order, so a tail MMA waits behind
+      // every convolution group already issued; bounding the run-ahead bounds that wait (the weight ring still prefetches)
+      const int max_ahead = p.kps;
+      int gslot = 0; uint32_t gph = 0; int gcount = 0;          // slot / phase of the group issued max_ahead groups ago
       for (int pair = cluster_id; pair < npairs; pair += nclusters) {
         wait_serving(tempty0 + 8 * acc, accph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1490,6 +1494,12 @@ dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const
           int fr = 0, fs = 0;
           for (int tg = 0; tg < tgroups; ++tg) {
             wait_serving(bfull0 + 8 * bs, bph);
+            if (max_ahead > 0) {
+              if (gcount >= max_ahead) {                           // the group issued max_ahead groups ago has left the tensor pipe
+                wait_serving(bempty0 + 8 * gslot, gph);
+                if (++gslot == b_st) { gslot = 0; gph ^= 1; }
+              } else ++gcount;
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
               const uint64_t ad0 = umma_desc_sw128(sa + (uint32_t)(fr * HALO_PW + fs) * 128u, HALO_PW * 128u);
@@ -1571,12 +1581,21 @@ dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_l + 8 * acc) : "memory");
+        // a2full publishes shared-memory writes to the pair's tensor cores: release.  tempty / d2empty only say "my
+        // tcgen05.ld have completed" (tcgen05.wait::ld + fence above): relaxed -- a release here would also wait for
+        // every global store of the previous branch to be performed (19 % of the kernel's stall samples, ncu).
         asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(a2full_l) : "memory");
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_l + 8 * acc) : "memory");
       }
       // ---- steps 2, 3: per branch, ConvT1 accumulator -> +shift, ReLU -> ConvT2 -> (+logit plane) -> sigmoid -> maps
 #pragma unroll 1
       for (int br = 0; br < 2; ++br) {
+        float2 lbv[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        if (br == 0 && p.logit_bias && valid) {            // requested before the wait: the L2 / DRAM latency hides behind the MMAs
+#pragma unroll
+          for (int dy2 = 0; dy2 < 2; ++dy2)
+            lbv[dy2] = __ldg(reinterpret_cast<const float2*>(p.logit_bias + ((size_t)n * Hd + 4 * oy + 2 * dy + dy2) * Wd + 4 * ox + 2 * dx));
+        }
         mbar_wait(d2full, (uint32_t)br);                   // use u = 2 * it + br: parity u & 1 = br
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const float* hs = head_s + br * 512;
@@ -1609,7 +1628,7 @@ dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0)
-          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(d2empty_l) : "memory");
+          asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(d2empty_l) : "memory");
         if (valid) {
           float* __restrict__ outp = br == 0 ? p.prob : p.thresh;
 #pragma unroll
@@ -1617,7 +1636,7 @@ dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const
             float v0 = o4[dy2 * 2 + 0], v1 = o4[dy2 * 2 + 1];
             const size_t oidx = ((size_t)n * Hd + 4 * oy + 2 * dy + dy2) * Wd + 4 * ox + 2 * dx;
             if (br == 0 && p.logit_bias) {
-              const float2 lb = __ldg(reinterpret_cast<const float2*>(p.logit_bias + oidx));
+              const float2 lb = lbv[dy2];
               v0 += lb.x; v1 += lb.y;
             }
             v0 = 1.0f / (1.0f + expf(-v0)); v1 = 1.0f / (1.0f + expf(-v1));
@@ -1976,6 +1995,9 @@ TcPlan* tc_plan_create_headfused(const ConvDesc& d, const void* w1, const float*
   TcParams& p = pl->p;
   p.KH = p.KW = 3; p.stride = 1; p.pad = 1; p.relu = 1; p.bias = d.bias;
   p.halo = 2; p.cta2 = 1; p.b_taps = 3; p.stages = 2; p.b_stages = 4;
+  p.kps = 0;                                              // convolution groups in flight ahead of a tail MMA (0 = unlimited)
+  if (const char* e = dev_env("VTD_HF_BST")) { int v = atoi(e); if (v >= 2 && v <= 4) p.b_stages = v; }
+  if (const char* e = dev_env("VTD_HF_AHEAD")) { int v = atoi(e); if (v >= 0 && v <= p.b_stages) p.kps = v; }
   p.lw = 3; p.lh = 4;
   p.tiles_x = (d.Wo + 7) / 8; p.tiles_y = (d.Ho + 15) / 16; p.tiles_n = d.N; p.n_blocks = 1;
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
