@@ -48,39 +48,77 @@ struct PtF { float x, y; };
 VTD_HD int trace_dx(int s) { return (int)((0x901Au >> (2 * (s & 7))) & 3u) - 1; }   // {1,1,0,-1,-1,-1,0,1}
 VTD_HD int trace_dy(int s) { return (int)((0xA901u >> (2 * (s & 7))) & 3u) - 1; }   // {0,-1,-1,-1,0,1,1,1}
 
+// Bit helpers (device intrinsics / portable host loops).
+VTD_HD int lowest_set(unsigned v) {              // index of the lowest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  int i = 0; while (!((v >> i) & 1u)) ++i; return i;
+#endif
+}
+VTD_HD int highest_set(unsigned v) {             // index of the highest set bit, v != 0
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz((int)v);
+#else
+  int i = 31; while (!((v >> i) & 1u)) --i; return i;
+#endif
+}
+
+// The trace works on NEIGHBOURHOOD CODES: nbr(x, y) returns 8 bits, bit s set iff the neighbour of (x, y) in direction s
+// is foreground (pixels outside the image are background).  One code per border pixel replaces the probe-by-probe search
+// for the next border pixel -- on the device the code comes from three bit-rows of a shared-memory window (csrc/boxes.cu),
+// six independent loads instead of a chain of dependent ones.
 // `visit(x, y)` is called once for every border pixel in visiting order (a pixel the border passes twice is visited
 // twice): the box extraction kernel collects the per-row extremes of the component from it (every row extreme of an
 // 8-connected component lies on its outer border).
-template <class Fg, class Visit>
-VTD_HD long long trace_outer_visit(const Fg& fg, int x0, int y0, long long max_steps, long long* steps_out, const Visit& visit) {
-  int s = 4, s_end = 4;
-  int x1 = x0, y1 = y0;
-  do {
-    s = (s - 1) & 7;
-    x1 = x0 + trace_dx(s); y1 = y0 + trace_dy(s);
-  } while (!fg(x1, y1) && s != s_end);
+template <class Nbr, class Visit>
+VTD_HD long long trace_outer_nbr(const Nbr& nbr, int x0, int y0, long long max_steps, long long* steps_out, const Visit& visit) {
   if (steps_out) *steps_out = 0;
-  if (s == s_end) { visit(x0, y0); return 0; }       // isolated pixel
+  unsigned code = nbr(x0, y0);
+  // first neighbour in the order NW, N, NE, E, SE, S, SW (directions 3, 2, 1, 0, 7, 6, 5); W is never consulted:
+  // rotate the code so that direction 3 is bit 7 ... direction 4 is bit 0, and take the highest set bit above bit 0
+  const unsigned r0 = (((code << 4) | (code >> 4)) & 0xFEu);
+  if (r0 == 0) { visit(x0, y0); return 0; }      // isolated pixel
+  int s = (highest_set(r0) - 4) & 7;
+  const int x1 = x0 + trace_dx(s), y1 = y0 + trace_dy(s);
   long long area2 = 0, steps = 0;
   int x3 = x0, y3 = y0;
   for (;;) {
     visit(x3, y3);
-    int ddx, ddy;
-    for (;;) {
-      ++s;
-      ddx = trace_dx(s); ddy = trace_dy(s);
-      if (fg(x3 + ddx, y3 + ddy)) break;
-    }
-    s &= 7;
+    // next border pixel: the first foreground neighbour in the order s+1, s+2, ... (the pixel we came from is one)
+    const unsigned rot = ((code | (code << 8)) >> ((s + 1) & 7)) & 0xFFu;
+    s = (s + 1 + lowest_set(rot)) & 7;
+    const int ddx = trace_dx(s), ddy = trace_dy(s);
     const int x4 = x3 + ddx, y4 = y3 + ddy;
     area2 += (long long)(x3 * ddy - ddx * y3);          // == x3*y4 - x4*y3 (consecutive border pixels are 8-neighbours)
     ++steps;
     if ((x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) || steps >= max_steps) break;
     x3 = x4; y3 = y4;
     s = (s + 4) & 7;
+    code = nbr(x3, y3);
   }
   if (steps_out) *steps_out = steps;
   return area2;
+}
+
+// neighbourhood code from a pixel predicate (host harness; device fallback on the global mask)
+template <class Fg>
+struct NbrFromFg {
+  const Fg& fg;
+  VTD_HD unsigned operator()(int x, int y) const {
+    unsigned n = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int s = 0; s < 8; ++s) n |= (fg(x + trace_dx(s), y + trace_dy(s)) ? 1u : 0u) << s;
+    return n;
+  }
+};
+
+template <class Fg, class Visit>
+VTD_HD long long trace_outer_visit(const Fg& fg, int x0, int y0, long long max_steps, long long* steps_out, const Visit& visit) {
+  const NbrFromFg<Fg> nbr{fg};
+  return trace_outer_nbr(nbr, x0, y0, max_steps, steps_out, visit);
 }
 
 struct NoVisit { VTD_HD void operator()(int, int) const {} };
@@ -97,8 +135,10 @@ VTD_HD long long trace_outer_area2(const Fg& fg, int x0, int y0, long long max_s
 // convex vertices in the cyclic order cv::convexHull(points, clockwise=false) returns them: starting
 // at the right-most point (largest y among ties), then towards larger y (down the image), the
 // left-most point, the top, and back.  `hull` needs room for 2*nrows+2 points.  Returns the count.
-VTD_HD long long cross3(const Pt& o, const Pt& a, const Pt& b) {
-  return (long long)(a.x - o.x) * (b.y - o.y) - (long long)(a.y - o.y) * (b.x - o.x);
+// 32-bit on purpose (the chain below is one lane's dependent sequence on the device): exact while the coordinates stay
+// below 2^15, which extract_boxes() enforces (planes of at most 16384 x 16384 pixels)
+VTD_HD int cross3(const Pt& o, const Pt& a, const Pt& b) {
+  return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x);
 }
 
 VTD_HD int hull_from_rows(const int* rowmin, const int* rowmax, int y0, int nrows, Pt* hull) {

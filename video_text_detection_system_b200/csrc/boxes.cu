@@ -265,12 +265,70 @@ struct GeoParams {
 };
 
 // One WARP per candidate.  The candidate's window of the mask (bbox + 1 px, columns rounded out to 32) is bit-packed into
-// shared memory, one word per 32 pixels, so the inherently sequential outer-border trace probes a register-speed bit
-// test instead of L2; the trace itself yields the per-row extremes; lane 0 then runs the hull / rotating-calipers
+// shared memory, one word per 32 pixels; the inherently sequential outer-border trace then takes ONE neighbourhood code
+// per border pixel from three bit-rows (six independent shared-memory loads + a funnel shift each) instead of probing
+// neighbour after neighbour; the trace itself yields the per-row extremes; lane 0 then runs the hull / rotating-calipers
 // arithmetic (O(#rows), scratch in shared memory), and the whole warp reduces the mean probability of the resulting
 // box.  Components too large for the per-warp budget fall back to the global mask and global scratch.
 constexpr int GW = 4;                    // candidates (warps) per CTA
 constexpr int GSMEM = 16 * 1024;         // shared-memory bytes per candidate
+
+struct NbrBits {                          // neighbourhood code from the bit-packed window (each row ends in a zero word)
+  const uint32_t* bits; int bx0, by0, wpr;
+  __device__ __forceinline__ unsigned operator()(int x, int y) const {
+    const int xx = x - bx0 - 1;           // window bit of pixel x-1
+    const int sh = xx & 31;
+    const uint32_t* r = bits + (y - by0 - 1) * wpr + (xx >> 5);       // row y-1
+    const uint32_t t0 = r[0], t1 = r[1], m0 = r[wpr], m1 = r[wpr + 1], b0 = r[2 * wpr], b1 = r[2 * wpr + 1];
+    const uint32_t t = __funnelshift_r(t0, t1, sh) & 7u, m = __funnelshift_r(m0, m1, sh) & 7u, b = __funnelshift_r(b0, b1, sh) & 7u;
+    // directions: 0 E, 1 NE, 2 N, 3 NW, 4 W, 5 SW, 6 S, 7 SE; bit 0 of t/m/b is column x-1, bit 2 is x+1
+    return (m >> 2) | ((t >> 2) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) | (b << 5);
+  }
+};
+
+// Everything one candidate needs after its window is staged; runs on lane 0.  Returns 1 when the box survives.
+template <class Nbr>
+__device__ __forceinline__ int candidate_geometry(const Nbr& nbr, int* rowmin, int* rowmax, Pt* hull, float* fl, int x0, int y0,
+                                                  int nrows, int start, const GeoParams& gp, TmpBox& tb) {
+  const int mw = gp.mw, mh = gp.mh;
+  auto visit = [&](int x, int y) {
+    const int r = y - y0;
+    if (x < rowmin[r]) rowmin[r] = x;
+    if (x > rowmax[r]) rowmax[r] = x;
+  };
+  long long area2 = trace_outer_nbr(nbr, x0, y0, 8LL * mw * mh, nullptr, visit);
+  if (area2 < 0) area2 = -area2;
+  if (area2 < 200) return 0;                  // cv2.contourArea(contour) < 100 -> skip (text_detector.py:150)
+  const int nh = hull_from_rows(rowmin, rowmax, y0, nrows, hull);
+  if (nh < 3) return 0;
+  RotRect rr = min_area_rect(hull, nh, fl, fl + nh, fl + 2 * nh);
+  unclip_rect(rr, gp.unclip);
+  PtF bp[4];
+  box_points(rr, bp);
+  int xs[4], ys[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {               // np.int0: truncation toward zero (text_detector.py:155)
+    xs[k] = (int)bp[k].x; ys[k] = (int)bp[k].y;
+    tb.poly[2 * k] = xs[k]; tb.poly[2 * k + 1] = ys[k];
+  }
+  int bx1 = min(min(xs[0], xs[1]), min(xs[2], xs[3])), bx2 = max(max(xs[0], xs[1]), max(xs[2], xs[3]));
+  int by1 = min(min(ys[0], ys[1]), min(ys[2], ys[3])), by2 = max(max(ys[0], ys[1]), max(ys[2], ys[3]));
+  bx1 = max(0, bx1); by1 = max(0, by1);                       // :160
+  bx2 = min(gp.clip_w, bx2); by2 = min(gp.clip_h, by2);       // :161
+  const int X1 = (int)((double)((long long)bx1 * gp.orig_w) / (double)gp.clip_w);   // :163-166
+  const int Y1 = (int)((double)((long long)by1 * gp.orig_h) / (double)gp.clip_h);
+  const int X2 = (int)((double)((long long)bx2 * gp.orig_w) / (double)gp.clip_w);
+  const int Y2 = (int)((double)((long long)by2 * gp.orig_h) / (double)gp.clip_h);
+  if (!(X2 - X1 > 10 && Y2 - Y1 > 10)) return 0;              // :168
+  tb.bbox[0] = X1; tb.bbox[1] = Y1; tb.bbox[2] = X2; tb.bbox[3] = Y2;
+  // :169-170  prob_map[y1*640//oh : y2*640//oh, x1*640//ow : x2*640//ow]  (numpy slice clamps to the plane)
+  const long long cy0 = (long long)Y1 * gp.clip_h / gp.orig_h, cy1 = (long long)Y2 * gp.clip_h / gp.orig_h;
+  const long long cx0 = (long long)X1 * gp.clip_w / gp.orig_w, cx1 = (long long)X2 * gp.clip_w / gp.orig_w;
+  tb.cy0 = (int)min(cy0, (long long)mh); tb.cy1 = (int)min(cy1, (long long)mh);
+  tb.cx0 = (int)min(cx0, (long long)mw); tb.cx1 = (int)min(cx1, (long long)mw);
+  tb.start = start;
+  return 1;
+}
 
 __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __restrict__ mask,
                                                            const float* __restrict__ prob, CompArrays ca, CandArrays cd,
@@ -283,6 +341,9 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   const int nc = min(cd.count[f], cd.kc);
   // a fixed, small grid walks the candidate list (the capacity is 1024 per plane, a frame has ~50)
   for (int c = blockIdx.x * GW + warp; c < nc; c += gridDim.x * GW) {
+#ifdef VTD_TIMERS
+  const long long gt0 = clock64(); long long gt1 = 0, gt2 = 0;
+#endif
   TmpBox& tb = tmp[(size_t)f * cd.kc + c];
   if (lane == 0) tb.valid = 0;
   const int s = cd.slot[(size_t)f * cd.kc + c];
@@ -294,93 +355,53 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
   const int nrows = ca.ymax[o] - y0 + 1;
   const int by0 = y0 - 1, rh = nrows + 2;
   const int bx0 = (xmin - 1) & ~31;                          // window origin, a multiple of 32 (-32 when xmin == 0)
-  const int wpr = ((xmax + 1 - bx0) >> 5) + 1;               // words per window row
+  const int wpr = ((xmax + 1 - bx0) >> 5) + 2;               // words per window row, the last one always zero
   const long long words = (long long)wpr * rh;
   const int scratch_words = 12 * nrows + 16;
   const bool use_smem = words * 4 + 4LL * scratch_words <= GSMEM;
-  uint32_t* bitsm = reinterpret_cast<uint32_t*>(gsm + warp * GSMEM);
-  int* scr;
-  if (use_smem) {
-    scr = reinterpret_cast<int*>(bitsm + words);
-  } else {
-    int off = 0;
-    if (lane == 0) off = atomicAdd(pool_used + f, scratch_words);
-    off = __shfl_sync(0xffffffffu, off, 0);
-    if (off + scratch_words > gp.pool_words) { if (lane == 0) atomicExch(overflow, 1); continue; }
-    scr = pool + (size_t)f * gp.pool_words + off;
-  }
-  int* rowmin = scr;
-  int* rowmax = scr + nrows;
-  Pt* hull = reinterpret_cast<Pt*>(scr + 2 * nrows);
-  float* fl = reinterpret_cast<float*>(scr + 2 * nrows + 2 * (2 * nrows + 2));
   const uint8_t* m = mask + (size_t)f * mh * mw;
-
+  int ok = 0;
   if (use_smem) {
+    uint32_t* bitsm = reinterpret_cast<uint32_t*>(gsm + warp * GSMEM);
+    int* scr = reinterpret_cast<int*>(bitsm + words);
+    int* rowmin = scr;
+    int* rowmax = scr + nrows;
+    Pt* hull = reinterpret_cast<Pt*>(scr + 2 * nrows);
+    float* fl = reinterpret_cast<float*>(scr + 2 * nrows + 2 * (2 * nrows + 2));
     const bool vec = (mw & 15) == 0;
     for (int idx = lane; idx < (int)words; idx += 32) {
       const int r = idx / wpr, wi = idx - r * wpr;
       const int gy = by0 + r, gx = bx0 + 32 * wi;
       uint32_t wbits = 0;
-      if ((unsigned)gy < (unsigned)mh && gx < mw) {
-        if (gx >= 0) wbits = mask_word(m + (size_t)gy * mw, gx, mw, vec);
-      }
+      if (wi + 1 < wpr && (unsigned)gy < (unsigned)mh && gx >= 0 && gx < mw) wbits = mask_word(m + (size_t)gy * mw, gx, mw, vec);
       bitsm[idx] = wbits;
     }
+    for (int r = lane; r < nrows; r += 32) { rowmin[r] = 1 << 30; rowmax[r] = -1; }
+    __syncwarp();
+#ifdef VTD_TIMERS
+    gt1 = clock64();
+#endif
+    if (lane == 0) ok = candidate_geometry(NbrBits{bitsm, bx0, by0, wpr}, rowmin, rowmax, hull, fl, x0, y0, nrows, start, gp, tb);
+  } else {
+    int off = 0;
+    if (lane == 0) off = atomicAdd(pool_used + f, scratch_words);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (off + scratch_words > gp.pool_words) { if (lane == 0) atomicExch(overflow, 1); continue; }
+    int* scr = pool + (size_t)f * gp.pool_words + off;
+    int* rowmin = scr;
+    int* rowmax = scr + nrows;
+    Pt* hull = reinterpret_cast<Pt*>(scr + 2 * nrows);
+    float* fl = reinterpret_cast<float*>(scr + 2 * nrows + 2 * (2 * nrows + 2));
+    for (int r = lane; r < nrows; r += 32) { rowmin[r] = 1 << 30; rowmax[r] = -1; }
+    __syncwarp();
+    auto fg_g = [&](int x, int y) -> bool {
+      return (unsigned)x < (unsigned)mw && (unsigned)y < (unsigned)mh && m[(size_t)y * mw + x] != 0;
+    };
+    if (lane == 0) ok = candidate_geometry(NbrFromFg<decltype(fg_g)>{fg_g}, rowmin, rowmax, hull, fl, x0, y0, nrows, start, gp, tb);
   }
-  for (int r = lane; r < nrows; r += 32) { rowmin[r] = 1 << 30; rowmax[r] = -1; }
-  __syncwarp();
-
-  int ok = 0;
-  if (lane == 0) {
-    do {
-      auto fg_s = [&](int x, int y) -> bool {
-        const int xx = x - bx0;
-        return (bitsm[(y - by0) * wpr + (xx >> 5)] >> (xx & 31)) & 1u;
-      };
-      auto fg_g = [&](int x, int y) -> bool {
-        return (unsigned)x < (unsigned)mw && (unsigned)y < (unsigned)mh && m[(size_t)y * mw + x] != 0;
-      };
-      auto visit = [&](int x, int y) {
-        const int r = y - y0;
-        if (x < rowmin[r]) rowmin[r] = x;
-        if (x > rowmax[r]) rowmax[r] = x;
-      };
-      const long long max_steps = 8LL * mw * mh;
-      long long area2 = use_smem ? trace_outer_visit(fg_s, x0, y0, max_steps, nullptr, visit)
-                                 : trace_outer_visit(fg_g, x0, y0, max_steps, nullptr, visit);
-      if (area2 < 0) area2 = -area2;
-      if (area2 < 200) break;                  // cv2.contourArea(contour) < 100 -> skip (text_detector.py:150)
-      int nh = hull_from_rows(rowmin, rowmax, y0, nrows, hull);
-      if (nh < 3) break;
-      RotRect rr = min_area_rect(hull, nh, fl, fl + nh, fl + 2 * nh);
-      unclip_rect(rr, gp.unclip);
-      PtF bp[4];
-      box_points(rr, bp);
-      int xs[4], ys[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {             // np.int0: truncation toward zero (text_detector.py:155)
-        xs[k] = (int)bp[k].x; ys[k] = (int)bp[k].y;
-        tb.poly[2 * k] = xs[k]; tb.poly[2 * k + 1] = ys[k];
-      }
-      int bx1 = min(min(xs[0], xs[1]), min(xs[2], xs[3])), bx2 = max(max(xs[0], xs[1]), max(xs[2], xs[3]));
-      int by1 = min(min(ys[0], ys[1]), min(ys[2], ys[3])), by2 = max(max(ys[0], ys[1]), max(ys[2], ys[3]));
-      bx1 = max(0, bx1); by1 = max(0, by1);                       // :160
-      bx2 = min(gp.clip_w, bx2); by2 = min(gp.clip_h, by2);       // :161
-      int X1 = (int)((double)((long long)bx1 * gp.orig_w) / (double)gp.clip_w);   // :163-166
-      int Y1 = (int)((double)((long long)by1 * gp.orig_h) / (double)gp.clip_h);
-      int X2 = (int)((double)((long long)bx2 * gp.orig_w) / (double)gp.clip_w);
-      int Y2 = (int)((double)((long long)by2 * gp.orig_h) / (double)gp.clip_h);
-      if (!(X2 - X1 > 10 && Y2 - Y1 > 10)) break;                 // :168
-      tb.bbox[0] = X1; tb.bbox[1] = Y1; tb.bbox[2] = X2; tb.bbox[3] = Y2;
-      // :169-170  prob_map[y1*640//oh : y2*640//oh, x1*640//ow : x2*640//ow]  (numpy slice clamps to the plane)
-      long long cy0 = (long long)Y1 * gp.clip_h / gp.orig_h, cy1 = (long long)Y2 * gp.clip_h / gp.orig_h;
-      long long cx0 = (long long)X1 * gp.clip_w / gp.orig_w, cx1 = (long long)X2 * gp.clip_w / gp.orig_w;
-      tb.cy0 = (int)min(cy0, (long long)mh); tb.cy1 = (int)min(cy1, (long long)mh);
-      tb.cx0 = (int)min(cx0, (long long)mw); tb.cx1 = (int)min(cx1, (long long)mw);
-      tb.start = start;
-      ok = 1;
-    } while (false);
-  }
+#ifdef VTD_TIMERS
+  gt2 = clock64();
+#endif
   ok = __shfl_sync(0xffffffffu, ok, 0);
   if (!ok) continue;
   // mean probability inside the box (np.mean of the slice; empty slice -> nan)
@@ -409,6 +430,11 @@ __global__ void __launch_bounds__(GW * 32) geometry_kernel(const uint8_t* __rest
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     res = (float)(acc / ((double)h * (double)w));
   }
+#ifdef VTD_TIMERS
+  if (lane == 0 && f == 0 && c < 3)
+    printf("GEOM c=%d wpr=%d rh=%d nrows=%d smem=%d | stage %lld lane0 %lld conf %lld total %lld\n", c, wpr, rh, nrows, (int)use_smem,
+           gt1 - gt0, gt2 - gt1, clock64() - gt2, clock64() - gt0);
+#endif
   if (lane == 0) { tb.conf = res; __threadfence_block(); tb.valid = 1; }
   __syncwarp();
   }
@@ -488,7 +514,7 @@ cudaError_t extract_boxes(const float* prob, const uint8_t* mask, const BoxParam
                           LaunchCounter* lc) {
   if (p.n <= 0) return cudaSuccess;
   const int n = p.n, mh = p.mh, mw = p.mw;
-  if (mw > 65535 || (long long)mh * lay.cap_row > ID_MASK) return cudaErrorInvalidValue;
+  if (mw > 16384 || mh > 16384 || (long long)mh * lay.cap_row > ID_MASK) return cudaErrorInvalidValue;   // 32-bit hull arithmetic, 16-bit run starts
   RunTabs rt;
   rt.run_x = reinterpret_cast<uint16_t*>(work + lay.run_x);
   rt.nruns = reinterpret_cast<int*>(work + lay.nruns);
