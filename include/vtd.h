@@ -66,7 +66,11 @@ typedef struct vtd_config {
 
 /* Speed tier only: run the DB head as two kernels (3x3 convolutions -> feature map in HBM -> transposed convolutions)
  * instead of the one-pass kernel.  Same results bit for bit; keeps the intermediate map for vtd_debug_tensor("head"). */
-enum { VTD_FLAG_UNFUSED_HEAD = 1 };
+enum { VTD_FLAG_UNFUSED_HEAD = 1,
+/* Test aid: every device buffer of the context is allocated between two canary pages; vtd_check_guards() reports how
+ * many canary bytes the kernels have overwritten (out-of-bounds WRITES next to a buffer; compute-sanitizer is not
+ * available on every pool).  Costs 8 KB per buffer, nothing at run time. */
+       VTD_FLAG_GUARD_ALLOCS = 2 };
 
 /* One entry of a PyTorch state dict, fp32, C-contiguous, host memory. */
 typedef struct vtd_tensor {
@@ -100,6 +104,7 @@ int64_t vtd_launch_count(vtd_ctx* ctx);             /* kernels launched by this 
 int  vtd_overflow_flag(vtd_ctx* ctx);               /* !=0: the last box extraction exceeded max_boxes / scratch */
 int  vtd_time_T(vtd_ctx* ctx);                      /* CRNN sequence length T = crop_w/4 - 1 */
 int  vtd_abi_version(void);
+int  vtd_check_guards(vtd_ctx* ctx, int64_t* bad_bytes_out); /* VTD_FLAG_GUARD_ALLOCS contexts; synchronises the stream */
 
 /* ---- weights: replaces load_state_dict (text_detector.py:106-113, text_recognizer.py:93-100).
  * Folds eval-mode BatchNorm (eps 1e-5) into the convolutions and repacks to the kernels' layouts. */

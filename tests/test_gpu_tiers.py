@@ -277,6 +277,35 @@ def test_canonical_ctc_vs_textbook_collapse(E):
     assert got[0][0, :got[1][0]].tolist() == [5, 7]
 
 
+# ------------------------------------------------------------------------------------- out-of-bounds writes: canary pages
+@pytest.mark.parametrize("bb,dtype,h,w,sh,sw,boxes", [(18, "fp16", 736, 1312, 1080, 1920, 50), (18, "fp16", 160, 320, 180, 360, 4),
+                                                     (18, "fp32", 160, 320, 180, 360, 4), (50, "fp16", 352, 1024, 396, 1152, 20),
+                                                     (18, "bf16", 256, 1280, 288, 1440, 10)])
+def test_no_kernel_writes_outside_its_buffers(E, port, bb, dtype, h, w, sh, sw, boxes):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_closed_on_pool.txt), so the memcheck evidence
+    is the library's own: with VTD_FLAG_GUARD_ALLOCS every device buffer of the context (activations of every layer, TMA
+    store targets, the run tables of the box extraction, crops, sequences, logits, records) sits between two canary
+    pages; after whole-path batches -- full and partial -- not one canary byte may have changed."""
+    from video_text_detection_system_b200 import synthetic
+    det_sd, rec_sd = synthetic.random_state_dicts(seed=0, backbone="resnet50" if bb == 50 else "resnet18")
+    n = 3
+    frames = synthetic.synthetic_frames(n, sh, sw, seed=2)
+    amp = 1000.0 if bb == 50 else 8.0
+    bias = torch.from_numpy(synthetic.planted_logit_bias(n, h, w, seed=3, boxes=boxes, inside=amp, outside=-amp)).cuda()
+    eng = E.Engine(backbone=bb, dtype=dtype, det_h=h, det_w=w, max_batch=n, max_boxes=64, max_src_h=sh, max_src_w=sw,
+                   guard_allocs=True)
+    eng.load_detector(det_sd)
+    eng.load_recognizer(rec_sd)
+    assert eng.check_guards() == 0
+    r, c = eng.run_batch(list(frames), thr=0.5, recognize=True, logit_bias_dev=bias.data_ptr())
+    assert c.sum() > 0 and eng.check_guards() == 0
+    r, c = eng.run_batch(list(frames[:1]), thr=0.5, recognize=True, logit_bias_dev=bias.data_ptr())     # partial batch
+    assert eng.check_guards() == 0
+    r, c = eng.run_batch(list(frames), thr=0.5, recognize=True)            # no plane: the random texture, thousands of components
+    assert eng.check_guards() == 0
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------- two devices, one process
 def test_contexts_on_two_devices_in_one_process(E, port):
     """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a second context on another GPU must get its own

@@ -22,6 +22,7 @@ VTD_PIX_BGR, VTD_PIX_NV12 = 0, 1
 STAGE_NAMES = ("preprocess", "head_tail", "boxes", "crop", "lstm0", "lstm1", "ctc")   # vtd_op_info(which=2)
 VTD_IDS_STRIDE = 64
 VTD_FLAG_UNFUSED_HEAD = 1
+VTD_FLAG_GUARD_ALLOCS = 2
 
 CHARS = "0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~ "
 
@@ -63,7 +64,7 @@ _u8pp = C.POINTER(C.c_void_p)
 def exported_symbols() -> List[str]:
     """Every entry point include/vtd.h declares."""
     return ["vtd_create", "vtd_destroy", "vtd_last_error", "vtd_set_stream", "vtd_stream", "vtd_sync",
-            "vtd_launch_count", "vtd_overflow_flag", "vtd_time_T", "vtd_abi_version", "vtd_load_detector",
+            "vtd_launch_count", "vtd_overflow_flag", "vtd_time_T", "vtd_abi_version", "vtd_check_guards", "vtd_load_detector",
             "vtd_load_recognizer", "vtd_preprocess", "vtd_detect_maps", "vtd_get_maps", "vtd_read_maps",
             "vtd_dbnet_forward", "vtd_extract_boxes", "vtd_postprocess_map", "vtd_recognize_boxes",
             "vtd_recognize_crops", "vtd_crnn_forward", "vtd_ctc_decode", "vtd_run_batch", "vtd_read_records",
@@ -101,6 +102,7 @@ def load_library(variant: Optional[str] = None):
         lib.vtd_overflow_flag.argtypes = [vp]
         lib.vtd_time_T.argtypes = [vp]
         lib.vtd_abi_version.argtypes = []
+        lib.vtd_check_guards.argtypes = [vp, C.POINTER(C.c_int64)]
         lib.vtd_load_detector.argtypes = [vp, C.POINTER(VtdTensor), i32]
         lib.vtd_load_recognizer.argtypes = [vp, C.POINTER(VtdTensor), i32]
         lib.vtd_preprocess.argtypes = [vp, _u8pp, i32, i32, i32, i32, i32, i32]
@@ -157,7 +159,7 @@ class Engine:
 
     def __init__(self, device: int = 0, backbone: int = 18, dtype: str = "fp32", det_h: int = 640, det_w: int = 640,
                  crop_w: int = 128, max_batch: int = 1, max_boxes: int = 256, max_src_h: int = 2160,
-                 max_src_w: int = 3840, canonical_ctc: bool = False, unclip_ratio: float = 1.0, fuse_head: bool = True):
+                 max_src_w: int = 3840, canonical_ctc: bool = False, unclip_ratio: float = 1.0, fuse_head: bool = True, guard_allocs: bool = False):
         d = str(dtype).lower()
         # "fp16" / "bf16" name the 16-bit storage type of the speed tier and with it the library; "fp32" (the CUDA-core
         # parity tier) and "16bit" (the speed tier) take the process default (VTD_STORAGE, shipped = half)
@@ -180,6 +182,8 @@ class Engine:
         cfg.canonical_ctc = 1 if canonical_ctc else 0
         cfg.unclip_ratio = float(unclip_ratio)
         cfg.flags = 0 if fuse_head else VTD_FLAG_UNFUSED_HEAD      # parity harness: keep the "head" feature map (same results)
+        if guard_allocs:
+            cfg.flags |= VTD_FLAG_GUARD_ALLOCS                     # test aid: canary pages around every device buffer
         self.cfg = cfg
         self.det_h, self.det_w, self.crop_w = cfg.det_h, cfg.det_w, cfg.crop_w
         self.max_batch, self.max_boxes = cfg.max_batch, cfg.max_boxes
@@ -223,6 +227,12 @@ class Engine:
 
     def overflow(self) -> int:
         return int(self.lib.vtd_overflow_flag(self._h))
+
+    def check_guards(self) -> int:
+        """Canary bytes overwritten so far (guard_allocs=True contexts): 0 = no kernel wrote outside its buffers."""
+        bad = C.c_int64(0)
+        self._check(self.lib.vtd_check_guards(self._h, C.byref(bad)))
+        return int(bad.value)
 
     # ---- weights
     def load_detector(self, state_dict):

@@ -65,6 +65,9 @@ struct vtd_ctx {
   bool profiling = false;
   StageProf stage_prof[ST_COUNT];
   std::vector<void*> allocs;
+  // VTD_FLAG_GUARD_ALLOCS: every arena allocation sits between two canary pages, checked by vtd_check_guards()
+  struct Guarded { uint8_t* user; size_t bytes; };
+  std::vector<Guarded> guarded;
   size_t esz = 4;                       // activation element size
   bool bf16_mode = false;
   int T = 0;                            // CRNN sequence length
@@ -149,8 +152,22 @@ namespace {
     return code;                                          \
   } while (0)
 
+constexpr size_t GUARD_BYTES = 4096;
+constexpr int GUARD_PATTERN = 0xA5;
+
 int dev_alloc(vtd_ctx* c, void** p, size_t bytes) {
   if (bytes == 0) bytes = 256;
+  if (c->cfg.flags & VTD_FLAG_GUARD_ALLOCS) {
+    const size_t padded = (bytes + 255) & ~(size_t)255;          // the tail canary starts right after the (rounded) buffer
+    uint8_t* base = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&base), padded + 2 * GUARD_BYTES));
+    c->allocs.push_back(base);
+    CK(cudaMemset(base, GUARD_PATTERN, GUARD_BYTES));
+    CK(cudaMemset(base + GUARD_BYTES + bytes, GUARD_PATTERN, padded - bytes + GUARD_BYTES));
+    *p = base + GUARD_BYTES;
+    c->guarded.push_back({base + GUARD_BYTES, bytes});
+    return VTD_OK;
+  }
   CK(cudaMalloc(p, bytes));
   c->allocs.push_back(*p);
   return VTD_OK;
@@ -978,6 +995,34 @@ int vtd_overflow_flag(vtd_ctx* c) {
   cudaMemcpyAsync(&v, c->box_work + c->box_lay.overflow, 4, cudaMemcpyDeviceToHost, c->stream);
   cudaStreamSynchronize(c->stream);
   return v;
+}
+
+int vtd_check_guards(vtd_ctx* c, int64_t* bad_bytes) {
+  if (!c || !bad_bytes) return VTD_ERR_ARG;
+  Guard g(c);
+  *bad_bytes = 0;
+  if (!(c->cfg.flags & VTD_FLAG_GUARD_ALLOCS)) FAIL(VTD_ERR_STATE, "context was not created with VTD_FLAG_GUARD_ALLOCS");
+  CK(cudaStreamSynchronize(c->stream));
+  std::vector<uint8_t> h(2 * GUARD_BYTES + 256);
+  int first = -1;
+  for (size_t i = 0; i < c->guarded.size(); ++i) {
+    const vtd_ctx::Guarded& a = c->guarded[i];
+    const size_t padded = (a.bytes + 255) & ~(size_t)255;
+    const size_t tail = padded - a.bytes + GUARD_BYTES;
+    CK(cudaMemcpy(h.data(), a.user - GUARD_BYTES, GUARD_BYTES, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h.data() + GUARD_BYTES, a.user + a.bytes, tail, cudaMemcpyDeviceToHost));
+    int64_t bad = 0;
+    for (size_t k = 0; k < GUARD_BYTES + tail; ++k) bad += h[k] != GUARD_PATTERN;
+    if (bad && first < 0) first = (int)i;
+    *bad_bytes += bad;
+  }
+  if (*bad_bytes) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%lld canary bytes overwritten; first damaged allocation: #%d of %zu (%zu bytes)", (long long)*bad_bytes,
+             first, c->guarded.size(), c->guarded[first].bytes);
+    c->err = buf;
+  }
+  return VTD_OK;
 }
 
 int vtd_load_detector(vtd_ctx* c, const vtd_tensor* t, int n) {
