@@ -164,6 +164,25 @@ int  vtd_crnn_forward(vtd_ctx* ctx, const float* x_nchw_host, int n, float* logi
 int  vtd_ctc_decode(vtd_ctx* ctx, const float* x_host, int B, int T, int V, int is_prob,
                     uint8_t* ids_out, int* len_out, float* conf_out);
 
+/* ---- stage 4b', the reference's OTHER recogniser: TransformerRecognizer (text_recognizer.py:39-69), i.e. TrOCRProcessor +
+ * VisionEncoderDecoderModel.generate(max_length=50), greedy.  Speed tier only.  Weights: the HuggingFace state dict of the
+ * VisionEncoderDecoderModel (keys "encoder.*", "decoder.model.decoder.*", "decoder.output_projection.weight"; ViT encoder
+ * with 64-wide heads, TrOCR decoder whose cross-attention reads the encoder width).  crops_per_chunk: crops processed
+ * together (1..128; buffers are sized for it). */
+int  vtd_load_trocr(vtd_ctx* ctx, const vtd_tensor* tensors, int n, int crops_per_chunk);
+/* info8 = {image size, encoder tokens, encoder width, decoder width, vocabulary, max positions, crops per chunk, decoder layers} */
+int  vtd_trocr_info(vtd_ctx* ctx, int32_t* info8);
+/* recognize / recognize_batch drop-in: host BGR crops -> resize 384x384 (Pillow bilinear, as the processor), BGR->RGB, /255,
+ * (x-0.5)/0.5 -> encoder -> greedy decode.  ids_out [n_crops][max_length] (int32, starts with the decoder start token, ends
+ * with EOS, padded with the pad token as generate() pads); len_out [n_crops] (optional). */
+int  vtd_trocr_generate_crops(vtd_ctx* ctx, const uint8_t* const* crops, const int* h, const int* w, const int* pitch,
+                              int n_crops, int max_length, int32_t* ids_out, int* len_out);
+/* Parity harness on processor output: pixel_values [n,3,S,S] fp32 host.  Any of the outputs may be NULL:
+ * enc_out [n][tokens][encoder width] (last_hidden_state), logits_out [n][L][vocabulary] for the teacher-forced
+ * decoder_ids [n][L], ids_out [n][max_length] / len_out [n] = greedy generate. */
+int  vtd_trocr_forward(vtd_ctx* ctx, const float* pixel_values, int n, const int32_t* decoder_ids, int L, int max_length,
+                       float* enc_out, float* logits_out, int32_t* ids_out, int* len_out);
+
 /* ---- whole path in one call: preprocess -> detect -> boxes -> recognise (pipeliine.py:93-139).
  * records_host [n*max_boxes] / counts_host [n] may be NULL to leave results on the device. */
 int  vtd_run_batch(vtd_ctx* ctx, const uint8_t* const* frames, int n, int h, int w, int pitch, int pixfmt,

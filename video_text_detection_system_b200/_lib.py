@@ -67,7 +67,8 @@ def exported_symbols() -> List[str]:
             "vtd_launch_count", "vtd_overflow_flag", "vtd_time_T", "vtd_abi_version", "vtd_check_guards", "vtd_load_detector",
             "vtd_load_recognizer", "vtd_preprocess", "vtd_detect_maps", "vtd_get_maps", "vtd_read_maps",
             "vtd_dbnet_forward", "vtd_extract_boxes", "vtd_postprocess_map", "vtd_recognize_boxes",
-            "vtd_recognize_crops", "vtd_crnn_forward", "vtd_ctc_decode", "vtd_run_batch", "vtd_read_records",
+            "vtd_recognize_crops", "vtd_crnn_forward", "vtd_ctc_decode", "vtd_load_trocr", "vtd_trocr_info",
+            "vtd_trocr_generate_crops", "vtd_trocr_forward", "vtd_run_batch", "vtd_read_records",
             "vtd_get_records", "vtd_debug_tensor", "vtd_set_profiling", "vtd_op_count", "vtd_op_info"]
 
 
@@ -116,6 +117,10 @@ def load_library(variant: Optional[str] = None):
         lib.vtd_recognize_crops.argtypes = [vp, _u8pp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, vp, vp, vp, vp]
         lib.vtd_crnn_forward.argtypes = [vp, vp, i32, vp]
         lib.vtd_ctc_decode.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
+        lib.vtd_load_trocr.argtypes = [vp, C.POINTER(VtdTensor), i32, i32]
+        lib.vtd_trocr_info.argtypes = [vp, C.POINTER(C.c_int32)]
+        lib.vtd_trocr_generate_crops.argtypes = [vp, _u8pp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i32, vp, vp]
+        lib.vtd_trocr_forward.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
         lib.vtd_run_batch.argtypes = [vp, _u8pp, i32, i32, i32, i32, i32, i32, f32, vp, i32, vp, vp]
         lib.vtd_read_records.argtypes = [vp, i32, vp, vp]
         lib.vtd_get_records.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
@@ -388,6 +393,58 @@ class Engine:
                                                  lens.ctypes.data, conf.ctypes.data,
                                                  logits.ctypes.data if want_logits else None))
         return ids, lens, conf, logits
+
+    # ---- transformer recogniser (TrOCR branch)
+    def load_trocr(self, state_dict, crops_per_chunk: int = 32):
+        """state_dict: HuggingFace VisionEncoderDecoderModel.state_dict() (ViT encoder + TrOCR decoder)."""
+        arr, keep = _state_dict_to_tensors(state_dict)
+        self._check(self.lib.vtd_load_trocr(self._h, arr, len(arr), int(crops_per_chunk)))
+        info = (C.c_int32 * 8)()
+        self._check(self.lib.vtd_trocr_info(self._h, info))
+        self.trocr = dict(zip(("image", "tokens", "enc_width", "dec_width", "vocab", "max_positions", "crops_per_chunk", "dec_layers"),
+                              [int(v) for v in info]))
+
+    def trocr_generate_crops(self, crops: Sequence[np.ndarray], max_length: int = 50) -> Tuple[np.ndarray, np.ndarray]:
+        """BGR uint8 crops -> (ids [n, max_length] int32 padded as generate() pads, lengths [n])."""
+        n = len(crops)
+        keep = []
+        ptrs = (C.c_void_p * n)()
+        hs, ws, ps = (C.c_int * n)(), (C.c_int * n)(), (C.c_int * n)()
+        for i, im in enumerate(crops):
+            if not isinstance(im, np.ndarray) or im.ndim != 3 or im.shape[2] != 3 or im.size == 0 or im.dtype != np.uint8:
+                raise ValueError("crop %d is not a non-empty HxWx3 uint8 array" % i)
+            if im.strides[2] != 1 or im.strides[1] != 3 or im.strides[0] < 3 * im.shape[1]:
+                im = np.ascontiguousarray(im)
+            keep.append(im)
+            ptrs[i], hs[i], ws[i], ps[i] = im.ctypes.data, im.shape[0], im.shape[1], im.strides[0]
+        ids = np.zeros((n, max_length), np.int32)
+        lens = np.zeros(n, np.int32)
+        self._check(self.lib.vtd_trocr_generate_crops(self._h, C.cast(ptrs, _u8pp), hs, ws, ps, n, int(max_length),
+                                                      ids.ctypes.data, lens.ctypes.data))
+        return ids, lens
+
+    def trocr_forward(self, pixel_values: np.ndarray, decoder_ids: Optional[np.ndarray] = None, max_length: int = 0,
+                      want_encoder: bool = False):
+        """Parity harness on processor output [n,3,S,S] fp32: returns (encoder states or None, teacher-forced logits
+        [n,L,V] or None, greedy ids [n,max_length] or None, lengths or None)."""
+        x = np.ascontiguousarray(pixel_values, dtype=np.float32)
+        n = x.shape[0]
+        info = self.trocr
+        enc = np.empty((n, info["tokens"], info["enc_width"]), np.float32) if want_encoder else None
+        logits = dids = None
+        L = 0
+        if decoder_ids is not None:
+            dids = np.ascontiguousarray(decoder_ids, dtype=np.int32)
+            L = dids.shape[1]
+            logits = np.empty((n, L, info["vocab"]), np.float32)
+        ids = np.zeros((n, max_length), np.int32) if max_length else None
+        lens = np.zeros(n, np.int32) if max_length else None
+        self._check(self.lib.vtd_trocr_forward(self._h, x.ctypes.data, n, dids.ctypes.data if dids is not None else None, L,
+                                               int(max_length), enc.ctypes.data if enc is not None else None,
+                                               logits.ctypes.data if logits is not None else None,
+                                               ids.ctypes.data if ids is not None else None,
+                                               lens.ctypes.data if lens is not None else None))
+        return enc, logits, ids, lens
 
     def crnn_forward(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32)

@@ -129,6 +129,7 @@ struct vtd_ctx {
   // crop-list drop-in staging
   uint8_t* list_store = nullptr; size_t list_cap = 0;
   const uint8_t** list_ptrs = nullptr; int* list_meta = nullptr;   // device: [rc] ptrs, [3*rc] h,w,pitch
+  void* trocr = nullptr;                // TrocrState (trocr_host.inc): the transformer recogniser, when loaded
 };
 
 namespace {
@@ -825,6 +826,29 @@ int read_records_locked(vtd_ctx* c, int n, vtd_record* rh, int* ch) {
 
 // Serialises the calls on a context and makes its device current for their duration; the caller's current device
 // (torch's, for a Python caller) is put back on the way out.
+#include "trocr_host.inc"
+
+TrocrState* trocr_of(vtd_ctx* c) {
+  if (!c->trocr) c->trocr = new TrocrState();
+  return static_cast<TrocrState*>(c->trocr);
+}
+
+void trocr_free(vtd_ctx* c) {
+  if (!c->trocr) return;
+  TrocrState* t = static_cast<TrocrState*>(c->trocr);
+  auto kill = [](Op& o) { if (o.plan) tc_plan_destroy(o.plan); o.plan = nullptr; };
+  kill(t->patch_op); kill(t->lm);
+  for (auto& e : t->el) { kill(e.qkv); kill(e.proj); kill(e.fc1); kill(e.fc2); }
+  for (auto& d : t->dl) { kill(d.qkv); kill(d.so); kill(d.cq); kill(d.co); kill(d.fc1); kill(d.fc2); kill(d.ckv); }
+  if (t->pinned) cudaFreeHost(t->pinned);
+  if (t->crop_store) cudaFree(t->crop_store);
+  if (t->tmp) cudaFree(t->tmp);
+  if (t->tab_dev) cudaFree(t->tab_dev);
+  if (t->px_stage) cudaFree(t->px_stage);
+  delete t;
+  c->trocr = nullptr;
+}
+
 struct Guard {
   vtd_ctx* c; std::lock_guard<std::mutex> lk; int prev = -1;
   explicit Guard(vtd_ctx* ctx) : c(ctx), lk(ctx->mu) {
@@ -960,6 +984,7 @@ void vtd_destroy(vtd_ctx* c) {
   for (int l = 0; l < 2; ++l) if (c->xproj_op[l].plan) tc_plan_destroy(c->xproj_op[l].plan);
   if (c->fc_op.plan) tc_plan_destroy(c->fc_op.plan);
   if (c->head_plan) tc_plan_destroy(c->head_plan);
+  trocr_free(c);
   for (int l = 0; l < 2; ++l) if (c->plstm[l]) lstm_plan_destroy(c->plstm[l]);
   for (int l = 0; l < 2; ++l) for (int pp = 0; pp < 2; ++pp) if (c->lstm_plan[l][pp]) tc_plan_destroy(c->lstm_plan[l][pp]);
   for (void* p : c->allocs) cudaFree(p);
@@ -1260,6 +1285,121 @@ int vtd_ctc_decode(vtd_ctx* c, const float* x, int B, int T, int V, int is_prob,
   cleanup();
   if (e != cudaSuccess) { c->err = std::string("vtd_ctc_decode: ") + cudaGetErrorString(e); rc = VTD_ERR_CUDA; }
   return rc;
+}
+
+int vtd_load_trocr(vtd_ctx* c, const vtd_tensor* t, int n, int crops_per_chunk) {
+  if (!c) return VTD_ERR_ARG;
+  Guard g(c);
+  if (c->trocr && trocr_of(c)->loaded) FAIL(VTD_ERR_STATE, "transformer recogniser already loaded (create a new context to reload)");
+  SD sd; int r = make_sd(c, t, n, &sd); if (r) return r;
+  r = build_trocr(c, sd, crops_per_chunk > 0 ? crops_per_chunk : 32); if (r) return r;
+  CK(cudaDeviceSynchronize());
+  return VTD_OK;
+}
+
+int vtd_trocr_info(vtd_ctx* c, int32_t* info8) {
+  if (!c || !info8) return VTD_ERR_ARG;
+  Guard g(c);
+  if (!c->trocr || !trocr_of(c)->loaded) FAIL(VTD_ERR_STATE, "vtd_load_trocr has not been called");
+  TrocrState& t = *trocr_of(c);
+  info8[0] = t.S; info8[1] = t.T; info8[2] = t.De; info8[3] = t.Dd; info8[4] = t.V; info8[5] = t.Lcap; info8[6] = t.cap; info8[7] = t.Ld;
+  return VTD_OK;
+}
+
+int vtd_trocr_forward(vtd_ctx* c, const float* pixel_values, int n, const int32_t* decoder_ids, int L, int max_length,
+                      float* enc_out, float* logits_out, int32_t* ids_out, int* len_out) {
+  if (!c || !pixel_values) return VTD_ERR_ARG;
+  Guard g(c);
+  if (!c->trocr || !trocr_of(c)->loaded) FAIL(VTD_ERR_STATE, "vtd_load_trocr has not been called");
+  TrocrState& t = *trocr_of(c);
+  if (n <= 0) return VTD_OK;
+  const size_t per = (size_t)3 * t.S * t.S;
+  if (!t.px_stage) CK(cudaMalloc(&t.px_stage, (size_t)t.cap * per * 4));
+  for (int first = 0; first < n; first += t.cap) {
+    const int nc = n - first < t.cap ? n - first : t.cap;
+    CK(cudaMemcpyAsync(t.px_stage, pixel_values + (size_t)first * per, (size_t)nc * per * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(nchw_to_patches(t.px_stage, t.patches, nc, t.S, t.P, c->stream, &c->lc));
+    int r = trocr_encode(c, nc); if (r) return r;
+    if (enc_out) {
+      std::vector<bf16> h((size_t)nc * t.T * t.De);
+      CK(cudaMemcpyAsync(h.data(), t.enc, h.size() * 2, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      float* o = enc_out + (size_t)first * t.T * t.De;
+      for (size_t i = 0; i < h.size(); ++i) o[i] = (float)h[i];
+    }
+    if (decoder_ids && logits_out) {                      // teacher forcing: the logits of every given position
+      if (L <= 0 || L > t.Lcap) FAIL(VTD_ERR_ARG, "L must be in 1..%d", t.Lcap);
+      std::vector<int> ids((size_t)nc * t.Lcap, t.pad_id);
+      for (int b = 0; b < nc; ++b) for (int i = 0; i < L; ++i) ids[(size_t)b * t.Lcap + i] = decoder_ids[(size_t)(first + b) * L + i];
+      CK(cudaMemcpyAsync(t.ids_dev, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      for (int tp = 0; tp < L; ++tp) {
+        r = trocr_decode_step(c, nc, tp); if (r) return r;
+        CK(cudaMemcpy2DAsync(logits_out + ((size_t)first * L + tp) * t.V, (size_t)L * t.V * 4, t.logits, (size_t)t.Vp * 4, (size_t)t.V * 4, nc,
+                             cudaMemcpyDeviceToHost, c->stream));
+      }
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    if (ids_out) {
+      r = trocr_generate(c, nc, max_length, ids_out + (size_t)first * max_length, len_out ? len_out + first : nullptr);
+      if (r) return r;
+    }
+  }
+  return VTD_OK;
+}
+
+int vtd_trocr_generate_crops(vtd_ctx* c, const uint8_t* const* crops, const int* h, const int* w, const int* pitch, int n_crops,
+                             int max_length, int32_t* ids_out, int* len_out) {
+  if (!c || !crops || !h || !w || !pitch || !ids_out) return VTD_ERR_ARG;
+  Guard g(c);
+  if (!c->trocr || !trocr_of(c)->loaded) FAIL(VTD_ERR_STATE, "vtd_load_trocr has not been called");
+  TrocrState& t = *trocr_of(c);
+  for (int first = 0; first < n_crops; first += t.cap) {
+    const int nc = n_crops - first < t.cap ? n_crops - first : t.cap;
+    // stage the crops, their Pillow coefficient tables (csrc/resize_tab.h, per crop and axis) and the pass-1 intermediate
+    size_t bytes = 0, tmp_bytes = 0;
+    int max_h = 1;
+    for (int i = 0; i < nc; ++i) {
+      const int hh = h[first + i], ww = w[first + i];
+      if (hh <= 0 || ww <= 0 || pitch[first + i] < 3 * ww || !crops[first + i]) FAIL(VTD_ERR_ARG, "crop %d is empty or has a bad pitch", first + i);
+      bytes += ((size_t)hh * ww * 3 + 15) & ~(size_t)15;
+      tmp_bytes += ((size_t)hh * t.S * 3 + 15) & ~(size_t)15;
+      if (hh > max_h) max_h = hh;
+    }
+    if (bytes > t.crop_cap) { if (t.crop_store) cudaFree(t.crop_store); t.crop_store = nullptr; t.crop_cap = 0; CK(cudaMalloc(&t.crop_store, bytes * 2)); t.crop_cap = bytes * 2; }
+    if (tmp_bytes > t.tmp_cap) { if (t.tmp) cudaFree(t.tmp); t.tmp = nullptr; t.tmp_cap = 0; CK(cudaMalloc(&t.tmp, tmp_bytes * 2)); t.tmp_cap = tmp_bytes * 2; }
+    std::vector<const uint8_t*> ptrs(nc);
+    std::vector<TrocrCropMeta> meta(nc);
+    std::vector<int> tab;
+    size_t off = 0; long long toff = 0;
+    for (int i = 0; i < nc; ++i) {
+      const int hh = h[first + i], ww = w[first + i];
+      CK(cudaMemcpy2DAsync(t.crop_store + off, (size_t)ww * 3, crops[first + i], pitch[first + i], (size_t)ww * 3, hh, cudaMemcpyHostToDevice, c->stream));
+      ptrs[i] = t.crop_store + off;
+      off += ((size_t)hh * ww * 3 + 15) & ~(size_t)15;
+      TrocrCropMeta m;
+      m.h = hh; m.w = ww; m.pitch = ww * 3; m.tmp_off = toff;
+      toff += (long long)(((size_t)hh * t.S * 3 + 15) & ~(size_t)15);
+      for (int axis = 0; axis < 2; ++axis) {
+        std::vector<int> lo, cnt, kk; int ks = 0, mc = 0;
+        compute_resize_tab(axis == 0 ? ww : hh, t.S, &lo, &cnt, &kk, &ks, &mc);
+        (axis == 0 ? m.offx : m.offy) = (int)tab.size();
+        (axis == 0 ? m.ksx : m.ksy) = ks;
+        tab.insert(tab.end(), lo.begin(), lo.end()); tab.insert(tab.end(), cnt.begin(), cnt.end()); tab.insert(tab.end(), kk.begin(), kk.end());
+      }
+      meta[i] = m;
+    }
+    if (tab.size() * 4 > t.tab_cap) { if (t.tab_dev) cudaFree(t.tab_dev); t.tab_dev = nullptr; t.tab_cap = 0; CK(cudaMalloc(&t.tab_dev, tab.size() * 8)); t.tab_cap = tab.size() * 8; }
+    CK(cudaMemcpyAsync(t.tab_dev, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(t.crop_ptrs, ptrs.data(), sizeof(void*) * nc, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(t.meta_dev, meta.data(), sizeof(TrocrCropMeta) * nc, cudaMemcpyHostToDevice, c->stream));
+    CK(trocr_resize_patches(t.crop_ptrs, t.meta_dev, t.tab_dev, t.tmp, t.patches, nc, t.S, t.P, max_h, c->stream, &c->lc));
+    CK(cudaStreamSynchronize(c->stream));                  // the host vectors above die with this iteration
+    int r = trocr_encode(c, nc); if (r) return r;
+    r = trocr_generate(c, nc, max_length, ids_out + (size_t)first * max_length, len_out ? len_out + first : nullptr);
+    if (r) return r;
+  }
+  return VTD_OK;
 }
 
 int vtd_run_batch(vtd_ctx* c, const uint8_t* const* frames, int n, int h, int w, int pitch, int pixfmt, int on_dev,

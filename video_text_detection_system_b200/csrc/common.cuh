@@ -84,8 +84,9 @@ struct ConvDesc {
   const void* res;     // residual, see res_mode (RES_SAME: [N,Ho,Wo,Cout]; RES_UP2: [N,Ho/2,Wo/2,Cout])
   void* out;           // OUT_NHWC: [N,Ho,Wo,Cout]; OUT_D2S: [N,2Ho,2Wo,Cout/4], channel co = (dy*2+dx)*(Cout/4)+c
   int N, H, W, Cin, Ho, Wo, Cout, KH, KW, stride, pad;
-  int relu, res_mode, out_mode;
+  int relu, res_mode, out_mode;   // relu: 0 none, 1 ReLU, 2 exact GELU (tcgen05 path only)
   int out_f32;         // 1: `out` is fp32 regardless of the activation type (logits, gate pre-activations)
+  int hint_lw = -1, hint_lh = -1;   // tcgen05 path only: force the tile shape 2^lw x 2^lh pixels (GEMMs over token maps: whole rows)
   int pool = 0;        // tcgen05 path only: max-pool fused into the epilogue, `out` is the POOLED map: 1 = 2x2 s2, 2 = (2,1) s(2,1)
 };
 
@@ -204,6 +205,26 @@ cudaError_t ctc_greedy(const float* x /*[B,T,ld], V <= ld*/, int B, int T, int V
                        LaunchCounter* lc);
 cudaError_t ctc_into_records(const float* logits, int n_crops, int first_crop, int T, int V, int ld, int canonical,
                              const int* offsets, int n, int kmax, void* records, cudaStream_t s, LaunchCounter* lc);
+
+// ---- transformer recogniser (TrOCR branch, text_recognizer.py:39-69): the non-GEMM kernels (trocr.cu) -----------------------
+cudaError_t layernorm_rows(const bf16* x, const float* gamma, const float* beta, bf16* y, long long rows, int C, float eps,
+                           cudaStream_t s, LaunchCounter* lc);
+cudaError_t attention_enc(const bf16* qkv /*[n][S][3D]*/, bf16* out /*[n][S][D]*/, int n, int S, int heads, float scale,
+                          cudaStream_t s, LaunchCounter* lc);
+cudaError_t attention_decode(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldkv, int Lcap, int L, int n, int heads,
+                             float scale, bf16* out /*[n][heads*64]*/, cudaStream_t s, LaunchCounter* lc);
+cudaError_t vit_assemble(const bf16* patches, const bf16* cls, const bf16* pos, bf16* h, int n, int P, int D, cudaStream_t s,
+                         LaunchCounter* lc);
+cudaError_t trocr_embed(const int* ids, int ids_ld, int t, const bf16* tok, const bf16* pos, bf16* x, int n, int D, float scale,
+                        cudaStream_t s, LaunchCounter* lc);
+cudaError_t kv_append(const bf16* qkv /*[n][3D]*/, bf16* cache /*[n][Lcap][2D]*/, int n, int t, int Lcap, int D, cudaStream_t s,
+                      LaunchCounter* lc);
+cudaError_t argmax_rows(const float* logits, int n, int V, int ld, int* ids, int ids_ld, int t, int eos, int pad, int* finished,
+                        int* n_finished, cudaStream_t s, LaunchCounter* lc);
+struct TrocrCropMeta { int h, w, pitch, ksx, ksy, offx, offy; long long tmp_off; };   // == CropMeta of trocr.cu
+cudaError_t trocr_resize_patches(const uint8_t* const* crops_dev, const void* meta_dev, const int* tab_dev, uint8_t* tmp, bf16* patches,
+                                 int n, int S, int P, int max_h, cudaStream_t s, LaunchCounter* lc);
+cudaError_t nchw_to_patches(const float* x, bf16* patches, int n, int S, int P, cudaStream_t s, LaunchCounter* lc);
 
 // ---- layout helpers ----------------------------------------------------------------------------------------
 template <typename T>

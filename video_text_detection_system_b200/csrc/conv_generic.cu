@@ -189,9 +189,12 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(ConvDesc d) {
         for (int j = 0; j < 4; ++j) if (co0 + j < d.Cout) v[j] += to_f(res[ridx + j]);
       }
     }
-    if (d.relu) {
+    if (d.relu == 1) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (d.relu == 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
     }
     if (d.out_mode == OUT_NHWC) {
       long long oidx = (((long long)n * d.Ho + oy) * d.Wo + ox) * d.Cout + co0;

@@ -226,9 +226,12 @@ __device__ __forceinline__ void epilogue_conv(const TcParams& p, uint32_t tmem_a
           }
         }
       }
-      if (p.relu) {
+      if (p.relu == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      } else if (p.relu == 2) {                       // exact GELU (transformer MLPs): x/2 (1 + erf(x / sqrt 2))
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
       }
       if (p.out_f32) {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.Cout + co);
@@ -294,9 +297,12 @@ __device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUte
         }
       }
     }
-    if (p.relu) {
+    if (p.relu == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    } else if (p.relu == 2) {                         // exact GELU (transformer MLPs)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
     }
     if (p.out_f32) {
 #pragma unroll
@@ -1801,6 +1807,12 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   }
   fill_common(pl, d.N, d.Ho, d.Wo, d.Cout, d.Cin, bn, d.pool);
   TcParams& p = pl->p;
+  if (d.hint_lw >= 0 && d.hint_lh >= 0 && d.hint_lw + d.hint_lh <= 7 && !d.pool) {
+    p.lw = d.hint_lw; p.lh = d.hint_lh;
+    const int hbw = 1 << p.lw, hbh = 1 << p.lh, hbn = 128 >> (p.lw + p.lh);
+    p.tiles_x = (d.Wo + hbw - 1) / hbw; p.tiles_y = (d.Ho + hbh - 1) / hbh; p.tiles_n = (d.N + hbn - 1) / hbn;
+    p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_blocks;
+  }
   p.KH = d.KH; p.KW = d.KW; p.stride = d.stride; p.pad = d.pad;
   p.relu = d.relu; p.res_mode = d.res_mode; p.out_f32 = d.out_f32;
   p.bias = d.bias; p.res = reinterpret_cast<const bf16*>(d.res); p.out = d.out;
