@@ -315,6 +315,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip e2e_api, e2e_nv12 and the sustained run")
     ap.add_argument("--sustained-frames", type=int, default=None,
                     help="frames of the sustained run (default: BASELINE configs[3]'s 3000 at 1080p, 600 at 4K)")
+    ap.add_argument("--trocr", action="store_true",
+                    help="also time the transformer recogniser (TrOCR branch, base configuration, random-init) on a chunk of "
+                         "crops; on by default with --config 5 (BASELINE configs[4]: 'CRNN+Transformer recognizer')")
     ap.add_argument("--profile-out", default=None, help="write the per-op device-time table (JSON) here")
     args = ap.parse_args()
     select_workload(args.config, args.crop_w)
@@ -561,6 +564,12 @@ def main():
         except Exception as ex:
             print("e2e_api unavailable: %r" % (ex,), file=sys.stderr)
 
+    if (args.trocr or args.config == 5) and world == 1 and not args.no_extras:
+        try:
+            extras["trocr"] = trocr_leg(args, _lib, synthetic, local_rank, recs0, counts, host_pool, B)
+        except Exception as ex:
+            print("trocr leg unavailable: %r" % (ex,), file=sys.stderr)
+
     pk = peaks()
     # roofline of the dominant kernel family: every tcgen05 conv launch of the timed region
     tc_flops = tc_ms = 0.0
@@ -650,6 +659,41 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def trocr_leg(args, _lib, synthetic, device, recs0, counts, host_pool, B):
+    """The reference's OTHER recogniser (TransformerRecognizer, text_recognizer.py:39-69; BASELINE configs[4] names
+    "CRNN+Transformer"): microsoft/trocr-base-printed's architecture with random-init weights, greedy generate(max_length=50),
+    on the crops the detector found in the first frames of the last batch (host BGR crops -> vtd_trocr_generate_crops: H2D,
+    device-side 384x384 processor resize, ViT encoder, 49 decoder steps, ids back).  Wall clock around the C-ABI call."""
+    model = synthetic.random_trocr_model("base", seed=0)
+    chunk = 64
+    eng = _lib.Engine(device=device, dtype=args.dtype if args.dtype != "fp32" else "fp16", det_h=32, det_w=32, max_batch=1, max_boxes=64,
+                      max_src_h=32, max_src_w=32)
+    eng.load_trocr(model.state_dict(), crops_per_chunk=chunk)
+    del model
+    recs = recs0[0].reshape(B, KMAX, 128).view(_lib.RECORD_DTYPE).reshape(B, KMAX)
+    frames = host_pool.numpy()
+    crops = []
+    for i in range(B):
+        for j in range(int(counts[i])):
+            x1, y1, x2, y2 = (int(v) for v in recs[i][j]["bbox"])
+            c = frames[i % frames.shape[0]][y1:y2, x1:x2]
+            if c.size:
+                crops.append(np.ascontiguousarray(c))
+    crops = crops[:2 * chunk]
+    if not crops:
+        raise RuntimeError("no crops to recognise")
+    eng.trocr_generate_crops(crops[:8], 50)                       # warm-up
+    t0 = time.perf_counter()
+    ids, lens = eng.trocr_generate_crops(crops, 50)
+    dt = time.perf_counter() - t0
+    eng.close()
+    gf_crop = 2 * (577 * (768 * 768 * 4 + 2 * 768 * 3072) * 12 + 12 * 2 * 577 * 577 * 768) / 1e9       # encoder, 2 x MAC
+    return {"value": len(crops) / dt, "unit": "crops/s", "crops": len(crops), "seconds": dt, "tokens_per_crop": float(lens.mean()),
+            "frames_per_s_at_50_crops": len(crops) / dt / BOXES, "encoder_gflop_per_crop": gf_crop,
+            "model": "ViT-B/16@384 encoder + 12-layer TrOCR decoder (microsoft/trocr-base-printed configuration, random-init), "
+                     "greedy generate(max_length=50), %d crops per chunk" % chunk}
 
 
 def api_leg(args, _lib, synthetic, det_sd, rec_sd, host_pool, bias, B, NW, device, bb):

@@ -70,3 +70,34 @@ def test_trocr_crops_through_the_processor(E, tp):
     print("trocr crops: agreement %.3f" % float((ids == want).mean()))
     assert (ids == want).mean() >= 0.9
     assert ids[:, 0].tolist() == [2] * len(crops)
+
+
+def test_pipeline_with_transformer_ocr(tp):
+    """VideoTextPipeline(use_transformer_ocr=True), the reference's default: fused detection of the batch, then ONE
+    batched pass of the transformer recogniser over all crops; the result schema is the reference's
+    (pipeliine.py:127-133), 'recognition_confidence' its constant 0.95 (text_recognizer.py:64)."""
+    from oracle import port
+    from video_text_detection_system_b200 import VideoTextPipeline, synthetic
+    model = tp.build("tiny", seed=2)
+    P = VideoTextPipeline(use_transformer_ocr=True, backbone="resnet18", pretrained=False, det_size=(256, 1280),
+                          trocr_state_dict=model.state_dict())
+    det = port.build_dbnet("resnet18", seed=0)
+    P.detector.model.load_state_dict(det.state_dict())
+    frames = list(synthetic.synthetic_frames(2, 288, 1440, seed=11))
+    bias = torch.from_numpy(synthetic.planted_logit_bias(2, 256, 1280, seed=6, boxes=10)).cuda()
+    P.logit_bias_dev = bias.data_ptr()
+    got = P.detect_and_recognize(frames)
+    S = tp.image_size(model)
+    assert sum(len(g) for g in got) >= 10
+    for f, regions in zip(frames, got):
+        crops = [f[r["bbox"][1]:r["bbox"][3], r["bbox"][0]:r["bbox"][2]] for r in regions]
+        want = tp.generate(model, tp.processor_pixel_values(crops, S), 50)
+        for r, w in zip(regions, want):
+            assert set(r) == {"bbox", "text", "detection_confidence", "recognition_confidence", "polygon"}
+            assert r["recognition_confidence"] == 0.95
+            ids = [int(v) for v in w if v not in (0, 1, 2)]
+            assert r["text"] == " ".join(map(str, ids))
+    single = P.process_single_frame(frames[0])
+    assert [d["text"] for d in single["detections"]] == [r["text"] for r in got[0]]
+    # recognize(): the reference's never-raise convention
+    assert P.recognizer.recognize(np.zeros((0, 0, 3), np.uint8)) == {"text": "", "confidence": 0.0}

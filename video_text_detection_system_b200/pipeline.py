@@ -30,7 +30,7 @@ class VideoTextPipeline:
                  **engine_kwargs):
         det_kw = {k: engine_kwargs[k] for k in ("backbone", "pretrained", "det_size", "dtype", "max_boxes",
                                                 "unclip_ratio") if k in engine_kwargs}
-        rec_kw = {k: engine_kwargs[k] for k in ("crop_w", "dtype") if k in engine_kwargs}
+        rec_kw = {k: engine_kwargs[k] for k in ("crop_w", "dtype", "trocr_state_dict", "trocr_decode", "trocr_dir") if k in engine_kwargs}
         self.detector = TextDetector(detector_path, **det_kw)
         self.recognizer = TextRecognizer(recognizer_path, use_transformer=use_transformer_ocr, **rec_kw)
         self.video_processor = VideoProcessor()
@@ -58,14 +58,13 @@ class VideoTextPipeline:
         """True when a caller replaced detect/recognize/forward (the reference's tests do): fall back to
         the reference's per-frame control flow so the replacements take effect."""
         return ("detect" in vars(self.detector) or "recognize" in vars(self.recognizer)
-                or self.detector._forward_is_patched() or self.recognizer._forward_is_patched()
-                or self.recognizer.use_transformer)      # TrOCR branch: detect on the fused path, recognise per crop list
+                or self.detector._forward_is_patched() or self.recognizer._forward_is_patched())
 
     def _engine(self, src_h: int, src_w: int, n: int, slot: int = 0):
         cap = max(int(self.batch_size), n, 1)
         with self.detector._lock:
             eng = self.detector._engine_for(src_h, src_w, max_batch=cap, crop_w=self.recognizer.crop_w, slot=slot)
-            if not eng.rec_loaded:
+            if not eng.rec_loaded and not self.recognizer.use_transformer:
                 self.recognizer.model._check_supported()
                 eng.load_recognizer(self.recognizer.model.state_dict())
             lock = self._slot_locks.setdefault(slot, __import__("threading").Lock())
@@ -77,6 +76,8 @@ class VideoTextPipeline:
             return []
         h, w = frames[0].shape[:2]
         eng, lock = self._engine(h, w, len(frames), slot)
+        if self.recognizer.use_transformer:
+            return self._detect_then_trocr(frames, eng, lock)
         with lock:
             rec, cnt = eng.run_batch(frames, thr=self.confidence_threshold, recognize=True,
                                      logit_bias_dev=self.logit_bias_dev)
@@ -88,6 +89,29 @@ class VideoTextPipeline:
             return [records_to_regions(rec[i], int(cnt[i])) for i in range(len(frames))]
         with gc_paused():
             return [records_to_regions(rec[i], int(cnt[i])) for i in range(len(frames))]
+
+    def _detect_then_trocr(self, frames: List[np.ndarray], eng, lock) -> List[List[Dict[str, Any]]]:
+        """use_transformer_ocr=True (the reference's default): detection of the whole batch on the fused device path, then
+        ONE batched pass of the transformer recogniser over every crop of the batch (pipeliine.py:116-125 crops the
+        original BGR frame and calls recognize() per crop)."""
+        with lock:
+            rec, cnt = eng.run_batch(frames, thr=self.confidence_threshold, recognize=False, logit_bias_dev=self.logit_bias_dev)
+        crops, where = [], []
+        for i, f in enumerate(frames):
+            for j in range(int(cnt[i])):
+                x1, y1, x2, y2 = (int(v) for v in rec[i][j]["bbox"])
+                crop = f[y1:y2, x1:x2]
+                if crop.size == 0:                       # :122-123
+                    continue
+                crops.append(crop)
+                where.append((i, j))
+        texts = self.recognizer.model.recognize_batch(crops) if crops else []
+        out: List[List[Dict[str, Any]]] = [[] for _ in frames]
+        for (i, j), t in zip(where, texts):
+            r = rec[i][j]
+            out[i].append({"bbox": [int(v) for v in r["bbox"]], "text": t["text"], "detection_confidence": float(r["det_conf"]),
+                           "recognition_confidence": t["confidence"], "polygon": r["polygon"].reshape(4, 2).tolist()})
+        return out
 
     # ---- reference surface ----------------------------------------------------------------------------
     async def process_video(self, video_path: str, output_dir: str, progress_callback=None) -> Dict[str, Any]:

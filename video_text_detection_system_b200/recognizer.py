@@ -23,7 +23,7 @@ logger = logging.getLogger(__name__)
 
 class TextRecognizer:
     def __init__(self, model_path: str = None, use_transformer: bool = True, *, crop_w: int = 128,
-                 dtype: Optional[str] = None):
+                 dtype: Optional[str] = None, trocr_state_dict=None, trocr_decode=None, trocr_dir: Optional[str] = None):
         self.use_transformer = use_transformer
         self.device = "cuda"
         self.crop_w = int(crop_w)
@@ -32,7 +32,8 @@ class TextRecognizer:
             # text_recognizer.py:76-77: the TrOCR branch.  As in the reference, construction fails when the weights are
             # not to be had (from_pretrained raises offline); no silent substitution of the CRNN.
             from .transformer_recognizer import TransformerRecognizer
-            self.model = TransformerRecognizer(dtype=dtype)
+            self.model = TransformerRecognizer(trocr_dir or "microsoft/trocr-base-printed", dtype=dtype,
+                                               state_dict=trocr_state_dict, decode=trocr_decode)
             return
         self.vocab = self._build_vocab()
         self.model = CRNN(len(self.vocab))
