@@ -70,7 +70,10 @@ enum { VTD_FLAG_UNFUSED_HEAD = 1,
 /* Test aid: every device buffer of the context is allocated between two canary pages; vtd_check_guards() reports how
  * many canary bytes the kernels have overwritten (out-of-bounds WRITES next to a buffer; compute-sanitizer is not
  * available on every pool).  Costs 8 KB per buffer, nothing at run time. */
-       VTD_FLAG_GUARD_ALLOCS = 2 };
+       VTD_FLAG_GUARD_ALLOCS = 2,
+/* Speed tier only: run the DBNet stem and its 3x3 s2 max-pool as two kernels (the full-resolution stem map goes through
+ * HBM) instead of the fused kernel.  Same results bit for bit. */
+       VTD_FLAG_UNFUSED_STEM = 4 };
 
 /* One entry of a PyTorch state dict, fp32, C-contiguous, host memory. */
 typedef struct vtd_tensor {

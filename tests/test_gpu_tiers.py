@@ -159,6 +159,34 @@ def test_one_pass_head_equals_two_kernel_head_bit_for_bit(E, port, h, w, n):
     assert np.array_equal(m, (p > 0.3).astype(np.uint8))
 
 
+@pytest.mark.parametrize("h,w,n", [(736, 1312, 3), (352, 1024, 1), (64, 256, 2), (160, 224, 2)])
+def test_fused_stem_pool_equals_two_kernels_bit_for_bit(E, port, h, w, n):
+    """conv1 7x7 s2 + BN + ReLU + MaxPool2d(3, 2, 1) in ONE kernel (the full-resolution stem map never reaches HBM)
+    against the two-kernel path of the same library (VTD_FLAG_UNFUSED_STEM): max commutes with the 16-bit rounding, so
+    every later tensor must be IDENTICAL -- full and partial batches, odd column-tile counts (328 = 5.2 x 63 pooled
+    columns), bands of pooled rows, the left / right / top / bottom borders.  (224-wide inputs are below the fused
+    kernel's minimum width: both engines then run the same two kernels.)"""
+    net = port.build_dbnet("resnet18", seed=7)
+    x = np.random.default_rng(h * w).standard_normal((n, 3, h, w)).astype(np.float32)
+    outs = []
+    for fuse in (True, False):
+        eng = E.Engine(backbone=18, dtype=T16, det_h=h, det_w=w, max_batch=n, fuse_stem=fuse)
+        eng.load_detector(net.state_dict())
+        p, t = eng.dbnet_forward(x)
+        res = [p, t, eng.debug_tensor("c2", n)]
+        if n > 1:
+            p1, t1 = eng.dbnet_forward(x[:1])
+            res += [p1, t1]
+        outs.append(res)
+        eng.close()
+    for u, v in zip(outs[0], outs[1]):
+        assert np.array_equal(u, v)
+    with torch.no_grad():
+        ref = port.dbnet_forward(net, torch.from_numpy(x), return_feats=True)
+    assert np.abs(outs[0][2] - ref["c2"].numpy()).max() <= 0.02 * np.abs(ref["c2"].numpy()).max()
+    assert np.abs(outs[0][0] - ref["probability"].numpy()).max() <= 1e-2
+
+
 # ------------------------------------------------------------------------------------- end to end, every tier
 @pytest.mark.parametrize("dtype", ["fp32", "fp16", "bf16"])
 def test_run_batch_every_tier_vs_oracle(E, port, dtype):

@@ -23,6 +23,7 @@ STAGE_NAMES = ("preprocess", "head_tail", "boxes", "crop", "lstm0", "lstm1", "ct
 VTD_IDS_STRIDE = 64
 VTD_FLAG_UNFUSED_HEAD = 1
 VTD_FLAG_GUARD_ALLOCS = 2
+VTD_FLAG_UNFUSED_STEM = 4
 
 CHARS = "0123456789abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~ "
 
@@ -164,7 +165,7 @@ class Engine:
 
     def __init__(self, device: int = 0, backbone: int = 18, dtype: str = "fp32", det_h: int = 640, det_w: int = 640,
                  crop_w: int = 128, max_batch: int = 1, max_boxes: int = 256, max_src_h: int = 2160,
-                 max_src_w: int = 3840, canonical_ctc: bool = False, unclip_ratio: float = 1.0, fuse_head: bool = True, guard_allocs: bool = False):
+                 max_src_w: int = 3840, canonical_ctc: bool = False, unclip_ratio: float = 1.0, fuse_head: bool = True, guard_allocs: bool = False, fuse_stem: bool = True):
         d = str(dtype).lower()
         # "fp16" / "bf16" name the 16-bit storage type of the speed tier and with it the library; "fp32" (the CUDA-core
         # parity tier) and "16bit" (the speed tier) take the process default (VTD_STORAGE, shipped = half)
@@ -187,6 +188,8 @@ class Engine:
         cfg.canonical_ctc = 1 if canonical_ctc else 0
         cfg.unclip_ratio = float(unclip_ratio)
         cfg.flags = 0 if fuse_head else VTD_FLAG_UNFUSED_HEAD      # parity harness: keep the "head" feature map (same results)
+        if not fuse_stem:
+            cfg.flags |= VTD_FLAG_UNFUSED_STEM                     # parity harness: stem and max-pool as two kernels (same results)
         if guard_allocs:
             cfg.flags |= VTD_FLAG_GUARD_ALLOCS                     # test aid: canary pages around every device buffer
         self.cfg = cfg

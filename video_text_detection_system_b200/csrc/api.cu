@@ -34,6 +34,7 @@ struct Op {
   double prof_ms = 0.0; long long prof_n = 0; bool prof_pending = false;
   ConvDesc d{};
   TcPlan* plan = nullptr;
+  StemPoolPlan* sp = nullptr;   // the op is the fused DBNet stem + max-pool (stem_pool_tcgen05)
   bool fused_head = false;      // plan is the one-pass DB head (dbhead_fused_tcgen05): 3x3 convolutions + both tails
   // pool
   const void* pin = nullptr; void* pout = nullptr;
@@ -77,6 +78,7 @@ struct vtd_ctx {
   bool det_loaded = false, rec_loaded = false;
   std::vector<Op> det_prog, rec_prog;
   std::map<std::string, DebugEntry> dbg;
+  bool use_stem_pool = false;           // DBNet stem and its max-pool run as one kernel (input buffer has a 6-px left border)
   bool use_win = false, use_tchead = false, use_tclstm = false;   // tcgen05 stems / head tail / LSTM (bf16 tier)
   OutLayout pre_lay{}, crops_lay{};
   TcPlan* head_plan = nullptr;
@@ -302,6 +304,7 @@ cudaError_t run_op(vtd_ctx* c, const Op& op, int n) {
     return maxpool_nhwc<float>((const float*)op.pin, (float*)op.pout, n, op.H, op.W, op.C, op.kh, op.kw, op.sh, op.sw,
                                op.ph, op.pw, c->stream, &c->lc);
   }
+  if (op.sp) return stem_pool_tcgen05(op.sp, n, c->stream, &c->lc);
   if (op.fused_head) return dbhead_fused_tcgen05(op.plan, n, c->cur_thr, c->cur_bias, c->stream, &c->lc);
   if (op.plan) return conv_tcgen05(op.plan, n, c->stream, &c->lc);
   ConvDesc d = op.d;
@@ -393,21 +396,31 @@ int build_detector(vtd_ctx* c, const SD& sd) {
             ww[(((size_t)o * 7 + rr) * 8 + ss + 1) * 4 + ch] = hc.w[(((size_t)o * 7 + rr) * 7 + ss) * 4 + ch];
     void* wdev = nullptr; float* bdev = nullptr; void* o = nullptr;
     if ((r = upload_act_type(c, ww, &wdev)) || (r = upload_f32(c, hc.b, &bdev)) ||
-        (r = dev_alloc(c, &o, (size_t)B * (dh / 2) * (dw / 2) * 64 * c->esz)))
+        (!c->use_stem_pool && (r = dev_alloc(c, &o, (size_t)B * (dh / 2) * (dw / 2) * 64 * c->esz))))
       return r;
     Op op;
     op.kind = Op::CONV;
     op.d.H = dh; op.d.W = dw; op.d.Cin = 4; op.d.Ho = dh / 2; op.d.Wo = dw / 2; op.d.Cout = 64; op.d.KH = op.d.KW = 7;
     op.d.stride = 2; op.d.pad = 3; op.d.N = B;
     std::string e;
-    op.plan = tc_plan_create_win(c->pre, B, dh + 6, dw + 8, 4, 2, 7, dh / 2, dw / 2, wdev, bdev, o, 1, &e);
-    if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 stem plan: %s", e.c_str());
-    P.push_back(op);
-    a.p = o; a.H = dh / 2; a.W = dw / 2; a.C = 64;
+    if (c->use_stem_pool) {
+      // conv1 + BN + ReLU + MaxPool2d(3, 2, 1) in one kernel: `o` (allocated above for the stem map) is not used
+      void* po = nullptr;
+      if ((r = dev_alloc(c, &po, (size_t)B * (dh / 4) * (dw / 4) * 64 * c->esz))) return r;
+      op.sp = stem_pool_plan_create(c->pre, B, dh, dw, wdev, bdev, po, &e);
+      if (!op.sp) FAIL(VTD_ERR_CUDA, "fused stem plan: %s", e.c_str());
+      P.push_back(op);
+      a.p = po; a.H = dh / 4; a.W = dw / 4; a.C = 64;
+    } else {
+      op.plan = tc_plan_create_win(c->pre, B, dh + 6, dw + 8, 4, 2, 7, dh / 2, dw / 2, wdev, bdev, o, 1, &e);
+      if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 stem plan: %s", e.c_str());
+      P.push_back(op);
+      a.p = o; a.H = dh / 2; a.W = dw / 2; a.C = 64;
+    }
   } else {
     if ((r = add_conv(c, &P, hc, B, x, 2, 3, true, nullptr, RES_NONE, false, &a))) return r;
   }
-  if ((r = add_pool(c, &P, B, a, 3, 3, 2, 2, 1, 1, &a))) return r;
+  if (!c->use_stem_pool && (r = add_pool(c, &P, B, a, 3, 3, 2, 2, 1, 1, &a))) return r;
   const bool r50 = c->cfg.backbone == 50;
   const int nblocks18[4] = {2, 2, 2, 2}, nblocks50[4] = {3, 4, 6, 3};
   Act feats[4];
@@ -909,6 +922,7 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   c->esz = c->bf16_mode ? 2 : 4;
   c->T = cfg->crop_w / 4 - 1;
   c->use_win = c->bf16_mode && !dev_env("VTD_NO_WIN");
+  c->use_stem_pool = c->use_win && cfg->det_w / 2 >= 128 && !(cfg->flags & VTD_FLAG_UNFUSED_STEM);
   c->use_tchead = c->bf16_mode && !dev_env("VTD_NO_TCHEAD");
   c->use_tclstm = c->bf16_mode && !dev_env("VTD_NO_TCLSTM");
   c->use_plstm = c->use_tclstm && !dev_env("VTD_NO_PLSTM");
@@ -925,7 +939,7 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
   c->frame_bytes_cap = (((size_t)cfg->max_src_h * cfg->max_src_w * 3) + 255) & ~(size_t)255;
   if ((r = dalloc(c, &c->frames_store, c->frame_bytes_cap * B)) || (r = dalloc(c, &c->store_ptrs_dev, sizeof(void*) * B)) ||
       (r = dalloc(c, &c->ext_ptrs_dev, sizeof(void*) * B)) ||
-      (r = dev_alloc(c, &c->pre, (size_t)B * (c->use_win ? (size_t)(dh + 6) * (dw + 8) : px) * 4 * c->esz + 4096 /* the stem's row copies overhang */)) || (r = dalloc(c, &c->prob, (size_t)B * px * 4)) ||
+      (r = dev_alloc(c, &c->pre, (size_t)B * (c->use_win ? (size_t)(dh + 6) * (dw + (c->use_stem_pool ? 10 : 8)) : px) * 4 * c->esz + 4096 /* the stem's row copies overhang */)) || (r = dalloc(c, &c->prob, (size_t)B * px * 4)) ||
       (r = dalloc(c, &c->thresh, (size_t)B * px * 4)) || (r = dalloc(c, &c->mask, (size_t)B * px)) ||
       // records and counts are ONE block (counts directly after the records): a rank's results travel in one collective
       (r = dalloc(c, &c->records, sizeof(vtd_record) * (size_t)B * cfg->max_boxes + sizeof(int) * B)) ||
@@ -958,9 +972,9 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
     c->err = "normalisation table kernel failed"; return fail(VTD_ERR_CUDA);
   }
   if (c->use_win) {   // zero-bordered stem inputs: 4 px left/right + 3 rows top/bottom (7x7 s2), 1 px + 1 row (3x3)
-    c->pre_lay = padded_layout(dh, dw, 4, 3, 3, 4, 4);
+    c->pre_lay = padded_layout(dh, dw, 4, 3, 3, c->use_stem_pool ? 6 : 4, 4);
     c->crops_lay = padded_layout(32, cfg->crop_w, 8, 1, 1, 1, 3);
-    cudaMemset(c->pre, 0, (size_t)B * (dh + 6) * (dw + 8) * 4 * c->esz);
+    cudaMemset(c->pre, 0, (size_t)B * (dh + 6) * (dw + (c->use_stem_pool ? 10 : 8)) * 4 * c->esz);
     cudaMemset(c->crops, 0, (size_t)c->rc * 34 * (cfg->crop_w + 4) * 8 * c->esz);
   } else {
     c->pre_lay = dense_layout(dh, dw, 4);
@@ -979,7 +993,7 @@ void vtd_destroy(vtd_ctx* c) {
   struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev == c->cfg.device ? -1 : prev_dev};
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (Op& op : c->det_prog) if (op.plan) tc_plan_destroy(op.plan);
+  for (Op& op : c->det_prog) { if (op.plan) tc_plan_destroy(op.plan); if (op.sp) stem_pool_plan_destroy(op.sp); }
   for (Op& op : c->rec_prog) if (op.plan) tc_plan_destroy(op.plan);
   for (int l = 0; l < 2; ++l) if (c->xproj_op[l].plan) tc_plan_destroy(c->xproj_op[l].plan);
   if (c->fc_op.plan) tc_plan_destroy(c->fc_op.plan);
@@ -1476,7 +1490,7 @@ int vtd_op_info(vtd_ctx* c, int which, int idx, int64_t* info, double* ms) {
   if (o.prof_pending) { cudaEventSynchronize(o.ev1); prof_harvest(o); }
   for (int i = 0; i < 16; ++i) info[i] = 0;
   if (o.kind == Op::CONV) {
-    info[0] = 0; info[1] = o.plan ? 1 : 0; info[2] = o.d.H; info[3] = o.d.W; info[4] = o.d.Cin; info[5] = o.d.Ho;
+    info[0] = 0; info[1] = (o.plan || o.sp) ? 1 : 0; info[2] = o.d.H; info[3] = o.d.W; info[4] = o.d.Cin; info[5] = o.d.Ho;
     info[6] = o.d.Wo; info[7] = o.d.Cout; info[8] = o.d.KH; info[9] = o.d.KW; info[10] = o.d.stride;
   } else {
     info[0] = 1; info[2] = o.H; info[3] = o.W; info[4] = o.C; info[8] = o.kh; info[9] = o.kw; info[10] = o.sh;

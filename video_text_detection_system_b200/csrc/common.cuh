@@ -117,6 +117,12 @@ LstmPlan* lstm_plan_create(const void* whh /*[2*1024][256] bf16, rows (dir, unit
 void lstm_plan_destroy(LstmPlan*);
 cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*[B][T][2][1024] bf16*/, void* seq_out, int B, int T, cudaStream_t s,
                                  LaunchCounter* lc);
+// DBNet stem (7x7 s2 + BN + ReLU) fused with the 3x3 s2 max-pool: the full-resolution stem map never reaches HBM
+struct StemPoolPlan;
+StemPoolPlan* stem_pool_plan_create(const void* in_padded, int N, int dh, int dw, const void* window_weights, const float* bias,
+                                    void* pooled_out, std::string* err);
+void stem_pool_plan_destroy(StemPoolPlan*);
+cudaError_t stem_pool_tcgen05(const StemPoolPlan* pl, int n, cudaStream_t s, LaunchCounter* lc);
 cudaError_t conv_tcgen05(const TcPlan* p, int n_actual, cudaStream_t s, LaunchCounter* lc);
 bool tc_supported(const ConvDesc& d);
 

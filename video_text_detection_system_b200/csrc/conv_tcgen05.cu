@@ -1665,6 +1665,215 @@ dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const
   }
 }
 
+// ---- DBNet stem + max-pool in one kernel ---------------------------------------------------------------------------------------
+// conv1 7x7 s2 (+ folded BN + ReLU) and nn.MaxPool2d(3, 2, 1) (torchvision ResNet children[0..3], text_detector.py:17-19) without
+// the full-resolution stem map ever reaching HBM: the separate kernels wrote 494 MB and re-read them per 16 frames at
+// 736x1312; this one reads the padded input (125 MB) and writes the pooled map (124 MB).
+// A work item is (image, column tile, band of pooled rows).  Stem rows are computed one after the other exactly as the
+// direct-window stem does (MODE_WIN / win2 above: the 7 padded input rows under a row tile of 128 outputs are bulk-copied
+// once, the MMA reads the overlapping 64-byte windows in place through a no-swizzle descriptor; 14 MMAs 128x64x16 per row
+// tile), but the epilogue keeps the last three ReLU'd rows in a shared-memory ring and, after every odd stem row 2y+1,
+// emits pooled row y = max over stem rows 2y-1..2y+1 and stem columns 2x-1..2x+1.  A column tile of 128 stem columns
+// starts at stem column 126 t - 1 and owns 63 pooled columns, so every pooling window lies inside its tile (2 of 128
+// columns are computed twice); out-of-range rows / columns contribute zeros, which is neutral after ReLU.
+// Roles: warp 0 producer (bulk copies), warp 1 MMA issuer, warps 2..9 epilogue + pooling.
+constexpr int SP_EPI_WARPS = 8;
+constexpr int SP_THREADS = 32 * (2 + SP_EPI_WARPS);
+constexpr int SP_ROWBUF = 128 * 128;                 // one stem row tile: 128 px x 64 ch x 2 B
+constexpr int SP_POOLED = 63;                        // pooled columns per column tile
+
+struct StemPoolParams {
+  const uint8_t* in;          // padded input [N][Hin][Win][4] 16-bit: 3 rows above, 6 px left of the image
+  long long in_rp, in_ip;     // row / image pitch in bytes
+  const float* bias;
+  bf16* out;                  // pooled map [N][Hp][Wp][64]
+  int N, Ho, Wo, Hp, Wp;      // stem map Ho x Wo, pooled map Hp x Wp
+  int tiles_x, bands, rows_per_band, total_items, stages;
+};
+
+__global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_constant__ CUtensorMap wmap, const StemPoolParams p) {
+  constexpr int B_ROW_BYTES = 64 * 64;                 // weights of one filter row: 64 out channels x 32 K (64-byte rows, SWIZZLE_64B)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t ring = (raw + 1023u) & ~1023u;
+  uint8_t* ring_ptr = smem_raw + (ring - raw);
+  const int stages = p.stages;
+  const uint32_t w0 = ring + stages * WIN2_SLOT;       // resident weights, 7 x 4 KB
+  const uint32_t rows0 = w0 + 7 * B_ROW_BYTES;         // three row buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (rows0 - ring) + 3 * SP_ROWBUF);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * 16, tfull0 = empty0 + 8 * 16, tempty0 = tfull0 + 8 * 4, wfull = tempty0 + 8 * 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, SP_EPI_WARPS); }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> image, column tile, band; the stem rows it computes: first = max(2 ya - 1, 0) .. last = 2 yb - 1
+  auto decode = [&](int item, int& n, int& t, int& ya, int& yb) {
+    const int band = item % p.bands; item /= p.bands;
+    t = item % p.tiles_x; n = item / p.tiles_x;
+    ya = band * p.rows_per_band; yb = min(ya + p.rows_per_band, p.Hp);
+  };
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if ((int)blockIdx.x < p.total_items && elect_one()) {
+      mbar_expect_tx(wfull, 7u * B_ROW_BYTES);
+      for (int j = 0; j < 7; ++j) tma_load_2d(w0 + j * B_ROW_BYTES, &wmap, wfull, j * 32, 0);
+    }
+    __syncwarp();
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int n, t, ya, yb; decode(item, n, t, ya, yb);
+      const int x0 = SP_POOLED * 2 * t - 1;                                       // first stem column of the tile
+      const uint8_t* base = p.in + (size_t)n * p.in_ip + (size_t)(2 * x0 + 2) * 8;  // its first window byte in a padded row
+      for (int r = max(2 * ya - 1, 0); r <= 2 * yb - 1; ++r) {
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t sa = ring + stage * WIN2_SLOT, fb = full0 + 8 * stage;
+          mbar_expect_tx(fb, 7u * WIN2_SLAB);
+          const uint8_t* src = base + (size_t)(2 * r) * p.in_rp;
+#pragma unroll
+          for (int j = 0; j < 7; ++j)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sa + j * WIN2_SLAB), "l"(src + (size_t)j * p.in_rp), "r"((uint32_t)WIN2_SLAB), "r"(fb) : "memory");
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc(64);
+    int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+    if ((int)blockIdx.x < p.total_items) mbar_wait(wfull, 0);
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int n, t, ya, yb; decode(item, n, t, ya, yb);
+      for (int r = max(2 * ya - 1, 0); r <= 2 * yb - 1; ++r) {
+        mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+        mbar_wait(full0 + 8 * stage, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t sa = ring + stage * WIN2_SLOT;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * 64);
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const uint64_t ad = umma_desc_nosw(sa + j * WIN2_SLAB, 16, 128);
+            const uint64_t bd = umma_desc<64>(w0 + j * B_ROW_BYTES);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) umma_f16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (j | k) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * stage);
+          umma_commit(tfull0 + 8 * as);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+        if (++as == 4) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue + pooling (8 warps, 256 threads) =====================
+    const int q = warp & 3, half = (warp - 2) >> 2;        // TMEM lane quarter; which 32 of the 64 channels
+    const int m = q * 32 + lane;                           // stem column inside the tile
+    const int et = threadIdx.x - 64;                       // 0..255
+    int as = 0; uint32_t aphase = 0;
+    float bias[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias[j] = __ldg(p.bias + half * 32 + j);
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int n, t, ya, yb; decode(item, n, t, ya, yb);
+      const int x0 = SP_POOLED * 2 * t - 1;
+      const int col = x0 + m;
+      const bool col_ok = col >= 0 && col < p.Wo;
+      const int r_first = max(2 * ya - 1, 0);
+      for (int r = r_first; r <= 2 * yb - 1; ++r) {
+        mbar_wait(tfull0 + 8 * as, aphase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64 + half * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+        if (++as == 4) { as = 0; aphase ^= 1; }
+        uint4 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = col_ok ? fmaxf(__uint_as_float(v[8 * j + 2 * e]) + bias[8 * j + 2 * e], 0.f) : 0.f;
+            const float b = col_ok ? fmaxf(__uint_as_float(v[8 * j + 2 * e + 1]) + bias[8 * j + 2 * e + 1], 0.f) : 0.f;
+            bf16x2 h = pack2(a, b);
+            w[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          o[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the pooling pass that read this ring slot (row r - 3) has finished
+        const uint32_t rowb = rows0 + (uint32_t)(r % 3) * SP_ROWBUF + (uint32_t)m * 128u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t c = (uint32_t)(half * 4 + j);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((c ^ (uint32_t)(m & 7)) << 4)), "r"(o[j].x), "r"(o[j].y),
+                       "r"(o[j].z), "r"(o[j].w) : "memory");
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");      // the row is complete
+        if ((r & 1) && r > 2 * ya) {                        // (the band's warm-up row 2 ya - 1 is odd too: it belongs to the band above)
+          // pooled row y = (r - 1) / 2 from stem rows r-2 (absent above the image), r-1, r
+          const int y = (r - 1) >> 1;
+          const bool has0 = r - 2 >= r_first;
+          const uint32_t b0 = rows0 + (uint32_t)((r + 1) % 3) * SP_ROWBUF;     // (r - 2) % 3
+          const uint32_t b1 = rows0 + (uint32_t)((r + 2) % 3) * SP_ROWBUF;     // (r - 1) % 3
+          const uint32_t b2 = rows0 + (uint32_t)(r % 3) * SP_ROWBUF;
+          for (int idx = et; idx < SP_POOLED * 8; idx += 256) {
+            const int xl = idx >> 3, c = idx & 7;
+            const int xg = SP_POOLED * t + xl;
+            if (xg >= p.Wp) continue;
+            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+              if (rr == 0 && !has0) continue;
+              const uint32_t rb = rr == 0 ? b0 : (rr == 1 ? b1 : b2);
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint32_t px = (uint32_t)(2 * xl + dx);
+                uint4 tv;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(tv.x), "=r"(tv.y), "=r"(tv.z), "=r"(tv.w)
+                             : "r"(rb + px * 128u + (((uint32_t)c ^ (px & 7u)) << 4)) : "memory");
+                bf16x2 a, b;
+#define VTD_HMAX2(dst, src) a = *reinterpret_cast<bf16x2*>(&dst); b = *reinterpret_cast<bf16x2*>(&src); a = __hmax2(a, b); dst = *reinterpret_cast<uint32_t*>(&a);
+                VTD_HMAX2(acc.x, tv.x) VTD_HMAX2(acc.y, tv.y) VTD_HMAX2(acc.z, tv.z) VTD_HMAX2(acc.w, tv.w)
+#undef VTD_HMAX2
+              }
+            }
+            *reinterpret_cast<uint4*>(p.out + (((size_t)n * p.Hp + y) * p.Wp + xg) * 64 + c * 8) = acc;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // the item's last pooling pass is done before the next item writes rows
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 
 // tile shape: BN x BH x BW = 128, all powers of two, least padding; ties prefer wider rows
@@ -1752,6 +1961,8 @@ int sm_count() {                        // of the CURRENT device (cached per ord
 }
 
 }  // namespace tc
+
+constexpr int SMEM_TOTAL = 227 * 1024;      // dynamic shared memory a CTA may use
 
 struct TcPlan {
   TcMaps maps;
@@ -2057,9 +2268,60 @@ cudaError_t dbhead_fused_tcgen05(TcPlan* pl, int n, float thr, const float* logi
   return cudaGetLastError();
 }
 
+// Fused stem + max-pool plan (stem_pool_kernel).  `in`: zero-bordered 16-bit input [N][dh + 6][dw + 10][4] (3 rows above /
+// below, 6 px left, 4 px right of the image); w: window weights [64][7][8 taps][4 ch]; out: pooled map [N][dh/4][dw/4][64].
+struct StemPoolPlan { CUtensorMap wmap; StemPoolParams p; int smem; };
+
+StemPoolPlan* stem_pool_plan_create(const void* in, int N, int dh, int dw, const void* w, const float* bias, void* out, std::string* err) {
+  auto fail = [&](const std::string& m) -> StemPoolPlan* { if (err) *err = m; return nullptr; };
+  if (dh % 4 || dw % 4 || dw / 2 < 128) return fail("map too small for the fused stem");
+  if (dev_env("VTD_NO_STEM_POOL")) return fail("disabled");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available from the driver");
+  StemPoolPlan* pl = new StemPoolPlan();
+  memset(pl, 0, sizeof(*pl));
+  StemPoolParams& p = pl->p;
+  p.in = reinterpret_cast<const uint8_t*>(in);
+  p.in_rp = (long long)(dw + 10) * 8; p.in_ip = p.in_rp * (dh + 6);
+  p.bias = bias; p.out = reinterpret_cast<bf16*>(out);
+  p.N = N; p.Ho = dh / 2; p.Wo = dw / 2; p.Hp = dh / 4; p.Wp = dw / 4;
+  p.tiles_x = (p.Wp + SP_POOLED - 1) / SP_POOLED;
+  // bands of pooled rows: enough items for ~4 per SM at the capacity batch, each band at least 8 rows
+  int bands = (4 * sm_count() + N * p.tiles_x - 1) / (N * p.tiles_x);
+  if (bands < 1) bands = 1;
+  if (bands > p.Hp / 8) bands = p.Hp / 8 > 0 ? p.Hp / 8 : 1;
+  p.rows_per_band = (p.Hp + bands - 1) / bands;
+  p.bands = (p.Hp + p.rows_per_band - 1) / p.rows_per_band;
+  p.total_items = N * p.tiles_x * p.bands;
+  CUresult r = encode_weights(enc, &pl->wmap, w, 7 * 32, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(stem weights) failed: " + std::to_string((int)r)); }
+  const int fixed = 7 * 64 * 64 + 3 * SP_ROWBUF + 512 + 1024;
+  int st = (SMEM_TOTAL - fixed) / WIN2_SLOT;
+  p.stages = st > 8 ? 8 : st;
+  pl->smem = p.stages * WIN2_SLOT + fixed;
+  return pl;
+}
+
+void stem_pool_plan_destroy(StemPoolPlan* p) { delete p; }
+
+cudaError_t stem_pool_tcgen05(const StemPoolPlan* pl, int n, cudaStream_t s, LaunchCounter* lc) {
+  if (n <= 0) return cudaSuccess;
+  StemPoolParams p = pl->p;
+  p.N = n < pl->p.N ? n : pl->p.N;
+  p.total_items = p.N * p.tiles_x * p.bands;
+  static PerDeviceFlag attr_done;
+  cudaError_t e = once_per_device(attr_done, [] {
+    return cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  if (e != cudaSuccess) return e;
+  const int grid = p.total_items < sm_count() ? p.total_items : sm_count();
+  stem_pool_kernel<<<grid, SP_THREADS, pl->smem, s>>>(pl->wmap, p);
+  if (lc) lc->n++;
+  return cudaGetLastError();
+}
+
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
-constexpr int SMEM_TOTAL = 227 * 1024;      // dynamic shared memory a CTA may use
 
 // ring depth / resident weights for a plan (called once per plan, after mode, block_n and p are filled)
 template <int BN, int MODE>
