@@ -187,6 +187,25 @@ def test_fused_stem_pool_equals_two_kernels_bit_for_bit(E, port, h, w, n):
     assert np.abs(outs[0][0] - ref["probability"].numpy()).max() <= 1e-2
 
 
+@pytest.mark.parametrize("cw,n", [(128, 70), (100, 9), (64, 3)])
+def test_fused_crnn_first_layer_equals_two_step_path_bit_for_bit(E, port, cw, n):
+    """The CRNN's Conv2d(3,64,3,1,1) + BN + ReLU + MaxPool2d(2,2) through the direct-window + pooling-ring kernel of the
+    DBNet stem against the windowed-TMA path (VTD_FLAG_UNFUSED_STEM): identical logits, for crop widths 128 (the
+    reference's), 100 (BASELINE's wording: a partial column tile) and 64."""
+    net = port.build_crnn(seed=4)
+    x = np.random.default_rng(cw).random((n, 3, 32, cw)).astype(np.float32)
+    outs = []
+    for fuse in (True, False):
+        eng = E.Engine(dtype=T16, det_h=32, det_w=32, crop_w=cw, max_batch=1, max_boxes=128, max_src_h=32, max_src_w=32, fuse_stem=fuse)
+        eng.load_recognizer(net.state_dict())
+        outs.append(eng.crnn_forward(x))
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])
+    with torch.no_grad():
+        ref = net(torch.from_numpy(x)).numpy()
+    assert np.abs(outs[0] - ref).max() <= 1e-3
+
+
 # ------------------------------------------------------------------------------------- end to end, every tier
 @pytest.mark.parametrize("dtype", ["fp32", "fp16", "bf16"])
 def test_run_batch_every_tier_vs_oracle(E, port, dtype):

@@ -575,8 +575,12 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
       op.d.stride = 1; op.d.pad = 1; op.d.N = B;
       std::string e;
       op.d.pool = fuse;
-      op.plan = tc_plan_create_win(c->crops, B, 34, cw + 4, 8, 1, 3, 32, cw, wdev, bdev, o, 1, &e, fuse);
-      if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 CRNN stem plan: %s", e.c_str());
+      if (fuse == 1 && !(c->cfg.flags & VTD_FLAG_UNFUSED_STEM))      // direct windows + pooling ring: the DBNet stem's kernel
+        op.sp = stem_pool_plan_create_crnn(c->crops, B, cw, wdev, bdev, o, &e);
+      if (!op.sp) {
+        op.plan = tc_plan_create_win(c->crops, B, 34, cw + 4, 8, 1, 3, 32, cw, wdev, bdev, o, 1, &e, fuse);
+        if (!op.plan) FAIL(VTD_ERR_CUDA, "tcgen05 CRNN stem plan: %s", e.c_str());
+      }
       P.push_back(op);
       a.p = o; a.H = fuse ? 16 : 32; a.W = fuse == 1 ? cw / 2 : cw; a.C = 64;
       if (fuse) continue;
@@ -944,7 +948,7 @@ int vtd_create(vtd_ctx** out, const vtd_config* cfg) {
       // records and counts are ONE block (counts directly after the records): a rank's results travel in one collective
       (r = dalloc(c, &c->records, sizeof(vtd_record) * (size_t)B * cfg->max_boxes + sizeof(int) * B)) ||
       (r = dalloc(c, &c->offsets, sizeof(int) * (B + 1))) ||
-      (r = dev_alloc(c, &c->crops, (size_t)c->rc * (c->use_win ? (size_t)34 * (cfg->crop_w + 4) * 8 : (size_t)32 * cfg->crop_w * 4) * c->esz)) ||
+      (r = dev_alloc(c, &c->crops, (size_t)c->rc * (c->use_win ? (size_t)34 * (cfg->crop_w + 4) * 8 : (size_t)32 * cfg->crop_w * 4) * c->esz + 4096 /* row copies overhang */)) ||
       (r = dalloc(c, &c->ids_dev, (size_t)c->rc * VTD_IDS_STRIDE)) || (r = dalloc(c, &c->len_dev, (size_t)c->rc * 4)) ||
       (r = dalloc(c, &c->conf_dev, (size_t)c->rc * 4)) || (r = dalloc(c, &c->list_ptrs, sizeof(void*) * c->rc)) ||
       (r = dalloc(c, &c->list_meta, sizeof(int) * 3 * c->rc)))
@@ -994,7 +998,7 @@ void vtd_destroy(vtd_ctx* c) {
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (Op& op : c->det_prog) { if (op.plan) tc_plan_destroy(op.plan); if (op.sp) stem_pool_plan_destroy(op.sp); }
-  for (Op& op : c->rec_prog) if (op.plan) tc_plan_destroy(op.plan);
+  for (Op& op : c->rec_prog) { if (op.plan) tc_plan_destroy(op.plan); if (op.sp) stem_pool_plan_destroy(op.sp); }
   for (int l = 0; l < 2; ++l) if (c->xproj_op[l].plan) tc_plan_destroy(c->xproj_op[l].plan);
   if (c->fc_op.plan) tc_plan_destroy(c->fc_op.plan);
   if (c->head_plan) tc_plan_destroy(c->head_plan);

@@ -121,6 +121,8 @@ cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*[B][T][
 struct StemPoolPlan;
 StemPoolPlan* stem_pool_plan_create(const void* in_padded, int N, int dh, int dw, const void* window_weights, const float* bias,
                                     void* pooled_out, std::string* err);
+StemPoolPlan* stem_pool_plan_create_crnn(const void* crops_padded, int N, int crop_w, const void* window_weights, const float* bias,
+                                         void* pooled_out, std::string* err);
 void stem_pool_plan_destroy(StemPoolPlan*);
 cudaError_t stem_pool_tcgen05(const StemPoolPlan* pl, int n, cudaStream_t s, LaunchCounter* lc);
 cudaError_t conv_tcgen05(const TcPlan* p, int n_actual, cudaStream_t s, LaunchCounter* lc);

@@ -1680,7 +1680,9 @@ dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const
 constexpr int SP_EPI_WARPS = 8;
 constexpr int SP_THREADS = 32 * (2 + SP_EPI_WARPS);
 constexpr int SP_ROWBUF = 128 * 128;                 // one stem row tile: 128 px x 64 ch x 2 B
-constexpr int SP_POOLED = 63;                        // pooled columns per column tile
+// The same kernel also runs the CRNN's first layer (text_recognizer.py:17: Conv2d(3, 64, 3, 1, 1) + BN + ReLU + MaxPool2d(2, 2)),
+// template parameter CRNN: 3 filter rows instead of 7, conv stride 1 (8 channels per padded pixel, so consecutive outputs are
+// again 16 bytes apart), 2x2 s2 pooling without overlap (column tiles of 128 conv columns = 64 pooled ones).
 
 struct StemPoolParams {
   const uint8_t* in;          // padded input [N][Hin][Win][4] 16-bit: 3 rows above, 6 px left of the image
@@ -1691,15 +1693,20 @@ struct StemPoolParams {
   int tiles_x, bands, rows_per_band, total_items, stages;
 };
 
+template <bool CRNN>
 __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_constant__ CUtensorMap wmap, const StemPoolParams p) {
   constexpr int B_ROW_BYTES = 64 * 64;                 // weights of one filter row: 64 out channels x 32 K (64-byte rows, SWIZZLE_64B)
+  constexpr int NR = CRNN ? 3 : 7;                     // filter rows = bulk-copied input rows per conv row tile
+  constexpr int SY = CRNN ? 1 : 2;                     // input rows per conv row (conv stride)
+  constexpr int SP_POOLED = CRNN ? 64 : 63;            // pooled columns per column tile
+  constexpr int SLOT = CRNN ? 7 * 1024 : WIN2_SLOT;    // ring slot: NR slabs of WIN2_SLAB bytes
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t ring = (raw + 1023u) & ~1023u;
   uint8_t* ring_ptr = smem_raw + (ring - raw);
   const int stages = p.stages;
-  const uint32_t w0 = ring + stages * WIN2_SLOT;       // resident weights, 7 x 4 KB
-  const uint32_t rows0 = w0 + 7 * B_ROW_BYTES;         // three row buffers
+  const uint32_t w0 = ring + stages * SLOT;            // resident weights, NR x 4 KB
+  const uint32_t rows0 = w0 + NR * B_ROW_BYTES;        // three row buffers
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (rows0 - ring) + 3 * SP_ROWBUF);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * 16, tfull0 = empty0 + 8 * 16, tempty0 = tfull0 + 8 * 4, wfull = tempty0 + 8 * 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
@@ -1730,23 +1737,23 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
   if (warp == 0) {
     // ===================== producer =====================
     if ((int)blockIdx.x < p.total_items && elect_one()) {
-      mbar_expect_tx(wfull, 7u * B_ROW_BYTES);
-      for (int j = 0; j < 7; ++j) tma_load_2d(w0 + j * B_ROW_BYTES, &wmap, wfull, j * 32, 0);
+      mbar_expect_tx(wfull, (uint32_t)NR * B_ROW_BYTES);
+      for (int j = 0; j < NR; ++j) tma_load_2d(w0 + j * B_ROW_BYTES, &wmap, wfull, j * 32, 0);
     }
     __syncwarp();
     int stage = 0; uint32_t phase = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int n, t, ya, yb; decode(item, n, t, ya, yb);
-      const int x0 = SP_POOLED * 2 * t - 1;                                       // first stem column of the tile
-      const uint8_t* base = p.in + (size_t)n * p.in_ip + (size_t)(2 * x0 + 2) * 8;  // its first window byte in a padded row
-      for (int r = max(2 * ya - 1, 0); r <= 2 * yb - 1; ++r) {
+      const int x0 = CRNN ? 128 * t : SP_POOLED * 2 * t - 1;                      // first conv column of the tile
+      const uint8_t* base = p.in + (size_t)n * p.in_ip + (CRNN ? (size_t)x0 * 16 : (size_t)(2 * x0 + 2) * 8);  // its first window byte in a padded row
+      for (int r = CRNN ? 2 * ya : max(2 * ya - 1, 0); r <= 2 * yb - 1; ++r) {
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         if (elect_one()) {
-          const uint32_t sa = ring + stage * WIN2_SLOT, fb = full0 + 8 * stage;
-          mbar_expect_tx(fb, 7u * WIN2_SLAB);
-          const uint8_t* src = base + (size_t)(2 * r) * p.in_rp;
+          const uint32_t sa = ring + stage * SLOT, fb = full0 + 8 * stage;
+          mbar_expect_tx(fb, (uint32_t)NR * WIN2_SLAB);
+          const uint8_t* src = base + (size_t)(SY * r) * p.in_rp;
 #pragma unroll
-          for (int j = 0; j < 7; ++j)
+          for (int j = 0; j < NR; ++j)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(sa + j * WIN2_SLAB), "l"(src + (size_t)j * p.in_rp), "r"((uint32_t)WIN2_SLAB), "r"(fb) : "memory");
         }
@@ -1761,15 +1768,15 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
     if ((int)blockIdx.x < p.total_items) mbar_wait(wfull, 0);
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int n, t, ya, yb; decode(item, n, t, ya, yb);
-      for (int r = max(2 * ya - 1, 0); r <= 2 * yb - 1; ++r) {
+      for (int r = CRNN ? 2 * ya : max(2 * ya - 1, 0); r <= 2 * yb - 1; ++r) {
         mbar_wait(tempty0 + 8 * as, aphase ^ 1);
         mbar_wait(full0 + 8 * stage, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
-          const uint32_t sa = ring + stage * WIN2_SLOT;
+          const uint32_t sa = ring + stage * SLOT;
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * 64);
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
+          for (int j = 0; j < NR; ++j) {
             const uint64_t ad = umma_desc_nosw(sa + j * WIN2_SLAB, 16, 128);
             const uint64_t bd = umma_desc<64>(w0 + j * B_ROW_BYTES);
 #pragma unroll
@@ -1794,10 +1801,10 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
     for (int j = 0; j < 32; ++j) bias[j] = __ldg(p.bias + half * 32 + j);
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int n, t, ya, yb; decode(item, n, t, ya, yb);
-      const int x0 = SP_POOLED * 2 * t - 1;
+      const int x0 = CRNN ? 128 * t : SP_POOLED * 2 * t - 1;
       const int col = x0 + m;
       const bool col_ok = col >= 0 && col < p.Wo;
-      const int r_first = max(2 * ya - 1, 0);
+      const int r_first = CRNN ? 2 * ya : max(2 * ya - 1, 0);
       for (int r = r_first; r <= 2 * yb - 1; ++r) {
         mbar_wait(tfull0 + 8 * as, aphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1833,7 +1840,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
         if ((r & 1) && r > 2 * ya) {                        // (the band's warm-up row 2 ya - 1 is odd too: it belongs to the band above)
           // pooled row y = (r - 1) / 2 from stem rows r-2 (absent above the image), r-1, r
           const int y = (r - 1) >> 1;
-          const bool has0 = r - 2 >= r_first;
+          const bool has0 = !CRNN && r - 2 >= r_first;          // 2x2 pooling: rows r-1 and r only
           const uint32_t b0 = rows0 + (uint32_t)((r + 1) % 3) * SP_ROWBUF;     // (r - 2) % 3
           const uint32_t b1 = rows0 + (uint32_t)((r + 2) % 3) * SP_ROWBUF;     // (r - 1) % 3
           const uint32_t b2 = rows0 + (uint32_t)(r % 3) * SP_ROWBUF;
@@ -1847,7 +1854,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
               if (rr == 0 && !has0) continue;
               const uint32_t rb = rr == 0 ? b0 : (rr == 1 ? b1 : b2);
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
+              for (int dx = 0; dx < (CRNN ? 2 : 3); ++dx) {
                 const uint32_t px = (uint32_t)(2 * xl + dx);
                 uint4 tv;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(tv.x), "=r"(tv.y), "=r"(tv.z), "=r"(tv.w)
@@ -2270,7 +2277,7 @@ cudaError_t dbhead_fused_tcgen05(TcPlan* pl, int n, float thr, const float* logi
 
 // Fused stem + max-pool plan (stem_pool_kernel).  `in`: zero-bordered 16-bit input [N][dh + 6][dw + 10][4] (3 rows above /
 // below, 6 px left, 4 px right of the image); w: window weights [64][7][8 taps][4 ch]; out: pooled map [N][dh/4][dw/4][64].
-struct StemPoolPlan { CUtensorMap wmap; StemPoolParams p; int smem; };
+struct StemPoolPlan { CUtensorMap wmap; StemPoolParams p; int smem; bool crnn; };
 
 StemPoolPlan* stem_pool_plan_create(const void* in, int N, int dh, int dw, const void* w, const float* bias, void* out, std::string* err) {
   auto fail = [&](const std::string& m) -> StemPoolPlan* { if (err) *err = m; return nullptr; };
@@ -2285,7 +2292,7 @@ StemPoolPlan* stem_pool_plan_create(const void* in, int N, int dh, int dw, const
   p.in_rp = (long long)(dw + 10) * 8; p.in_ip = p.in_rp * (dh + 6);
   p.bias = bias; p.out = reinterpret_cast<bf16*>(out);
   p.N = N; p.Ho = dh / 2; p.Wo = dw / 2; p.Hp = dh / 4; p.Wp = dw / 4;
-  p.tiles_x = (p.Wp + SP_POOLED - 1) / SP_POOLED;
+  p.tiles_x = (p.Wp + 63 - 1) / 63;                       // 63 pooled columns per column tile (stem_pool_kernel<false>)
   // bands of pooled rows: enough items for ~4 per SM at the capacity batch, each band at least 8 rows
   int bands = (4 * sm_count() + N * p.tiles_x - 1) / (N * p.tiles_x);
   if (bands < 1) bands = 1;
@@ -2299,6 +2306,35 @@ StemPoolPlan* stem_pool_plan_create(const void* in, int N, int dh, int dw, const
   int st = (SMEM_TOTAL - fixed) / WIN2_SLOT;
   p.stages = st > 8 ? 8 : st;
   pl->smem = p.stages * WIN2_SLOT + fixed;
+  pl->crnn = false;
+  return pl;
+}
+
+// The CRNN's first layer through the same kernel.  `in`: zero-bordered crops [N][34][cw + 4][8] (1 row above / below, 1 px
+// left, 3 right); w: window weights [64][3][4 taps][8 ch]; out: pooled map [N][16][cw / 2][64].
+StemPoolPlan* stem_pool_plan_create_crnn(const void* in, int N, int cw, const void* w, const float* bias, void* out, std::string* err) {
+  auto fail = [&](const std::string& m) -> StemPoolPlan* { if (err) *err = m; return nullptr; };
+  if (cw % 2 || cw < 16) return fail("crop width not supported by the fused first layer");
+  if (dev_env("VTD_NO_STEM_POOL")) return fail("disabled");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled not available from the driver");
+  StemPoolPlan* pl = new StemPoolPlan();
+  memset(pl, 0, sizeof(*pl));
+  StemPoolParams& p = pl->p;
+  p.in = reinterpret_cast<const uint8_t*>(in);
+  p.in_rp = (long long)(cw + 4) * 16; p.in_ip = p.in_rp * 34;
+  p.bias = bias; p.out = reinterpret_cast<bf16*>(out);
+  p.N = N; p.Ho = 32; p.Wo = cw; p.Hp = 16; p.Wp = cw / 2;
+  p.tiles_x = (cw + 127) / 128;
+  p.bands = 1; p.rows_per_band = p.Hp;
+  p.total_items = N * p.tiles_x;
+  CUresult r = encode_weights(enc, &pl->wmap, w, 3 * 32, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(CRNN stem weights) failed: " + std::to_string((int)r)); }
+  const int fixed = 3 * 64 * 64 + 3 * SP_ROWBUF + 512 + 1024;
+  int st = (SMEM_TOTAL - fixed) / (7 * 1024);
+  p.stages = st > 12 ? 12 : st;
+  pl->smem = p.stages * 7 * 1024 + fixed;
+  pl->crnn = true;
   return pl;
 }
 
@@ -2309,13 +2345,16 @@ cudaError_t stem_pool_tcgen05(const StemPoolPlan* pl, int n, cudaStream_t s, Lau
   StemPoolParams p = pl->p;
   p.N = n < pl->p.N ? n : pl->p.N;
   p.total_items = p.N * p.tiles_x * p.bands;
-  static PerDeviceFlag attr_done;
-  cudaError_t e = once_per_device(attr_done, [] {
-    return cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static PerDeviceFlag attr_done[2];
+  cudaError_t e = pl->crnn ? once_per_device(attr_done[1], [] {
+    return cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }) : once_per_device(attr_done[0], [] {
+    return cudaFuncSetAttribute(stem_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (e != cudaSuccess) return e;
   const int grid = p.total_items < sm_count() ? p.total_items : sm_count();
-  stem_pool_kernel<<<grid, SP_THREADS, pl->smem, s>>>(pl->wmap, p);
+  if (pl->crnn) stem_pool_kernel<true><<<grid, SP_THREADS, pl->smem, s>>>(pl->wmap, p);
+  else stem_pool_kernel<false><<<grid, SP_THREADS, pl->smem, s>>>(pl->wmap, p);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
