@@ -1672,8 +1672,9 @@ dbhead_fused_kernel(const __grid_constant__ TcMaps maps, const TcParams p, const
 // A work item is (image, column tile, band of pooled rows).  Stem rows are computed one after the other exactly as the
 // direct-window stem does (MODE_WIN / win2 above: the 7 padded input rows under a row tile of 128 outputs are bulk-copied
 // once, the MMA reads the overlapping 64-byte windows in place through a no-swizzle descriptor; 14 MMAs 128x64x16 per row
-// tile), but the epilogue keeps the last three ReLU'd rows in a shared-memory ring and, after every odd stem row 2y+1,
-// emits pooled row y = max over stem rows 2y-1..2y+1 and stem columns 2x-1..2x+1.  A column tile of 128 stem columns
+// tile), but the epilogue keeps the last two ReLU'd rows of its column in REGISTERS and, after every odd stem row 2y+1,
+// emits pooled row y = max over stem rows 2y-1..2y+1 (registers) and stem columns 2x-1..2x+1 (row maxima staged once in
+// shared memory).  A column tile of 128 stem columns
 // starts at stem column 126 t - 1 and owns 63 pooled columns, so every pooling window lies inside its tile (2 of 128
 // columns are computed twice); out-of-range rows / columns contribute zeros, which is neutral after ReLU.
 // Roles: warp 0 producer (bulk copies), warp 1 MMA issuer, warps 2..9 epilogue + pooling.
@@ -1706,8 +1707,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
   uint8_t* ring_ptr = smem_raw + (ring - raw);
   const int stages = p.stages;
   const uint32_t w0 = ring + stages * SLOT;            // resident weights, NR x 4 KB
-  const uint32_t rows0 = w0 + NR * B_ROW_BYTES;        // three row buffers
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (rows0 - ring) + 3 * SP_ROWBUF);
+  const uint32_t rows0 = w0 + NR * B_ROW_BYTES;        // two buffers for the row maxima (DBNet's horizontal pooling)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (rows0 - ring) + 2 * SP_ROWBUF);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * 16, tfull0 = empty0 + 8 * 16, tempty0 = tfull0 + 8 * 4, wfull = tempty0 + 8 * 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1792,10 +1793,16 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
     }
   } else {
     // ===================== epilogue + pooling (8 warps, 256 threads) =====================
+    // A thread owns one conv column of the tile (TMEM lane) and 32 of the 64 channels in EVERY row, so the vertical
+    // half of the pooling never leaves its registers: it keeps the previous two ReLU'd rows (packed 16-bit) and, after
+    // every odd conv row, takes the maximum over the window's rows.  Only the horizontal half needs other threads'
+    // columns: DBNet (3-wide windows that straddle warps) stages the row maxima in shared memory (two slots, one
+    // CTA-wide barrier per POOLED row); the CRNN's 2-wide windows are lane pairs of one warp (one shuffle).
     const int q = warp & 3, half = (warp - 2) >> 2;        // TMEM lane quarter; which 32 of the 64 channels
-    const int m = q * 32 + lane;                           // stem column inside the tile
+    const int m = q * 32 + lane;                           // conv column inside the tile
     const int et = threadIdx.x - 64;                       // 0..255
     int as = 0; uint32_t aphase = 0;
+    int slot = 0;
     float bias[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias[j] = __ldg(p.bias + half * 32 + j);
@@ -1805,71 +1812,91 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
       const int col = x0 + m;
       const bool col_ok = col >= 0 && col < p.Wo;
       const int r_first = CRNN ? 2 * ya : max(2 * ya - 1, 0);
-      for (int r = r_first; r <= 2 * yb - 1; ++r) {
+      uint32_t prev1[16], prev2[16];                        // rows r-1, r-2 of my column (zeros: neutral after ReLU)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { prev1[j] = 0u; prev2[j] = 0u; }
+      // the accumulator of row r+1 is requested (tcgen05.ld) as soon as row r's has been turned into `cur`: its TMEM latency
+      // hides behind the pooling work below
+      uint32_t v[32];
+      auto request = [&]() {
         mbar_wait(tfull0 + 8 * as, aphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 64 + half * 32), v);
+      };
+      request();
+      for (int r = r_first; r <= 2 * yb - 1; ++r) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * as);
         if (++as == 4) { as = 0; aphase ^= 1; }
-        uint4 o[4];
+        uint32_t cur[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t w[4];
+        for (int j = 0; j < 16; ++j) {
+          const float a = col_ok ? fmaxf(__uint_as_float(v[2 * j]) + bias[2 * j], 0.f) : 0.f;
+          const float b = col_ok ? fmaxf(__uint_as_float(v[2 * j + 1]) + bias[2 * j + 1], 0.f) : 0.f;
+          bf16x2 h = pack2(a, b);
+          cur[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (r < 2 * yb - 1) request();
+        if ((r & 1) && r > 2 * ya - (CRNN ? 1 : 0)) {        // (DBNet: the band's warm-up row 2 ya - 1 is odd too and belongs to the band above)
+          const int y = (r - 1) >> 1;                          // pooled row
+          uint32_t vm[16];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = col_ok ? fmaxf(__uint_as_float(v[8 * j + 2 * e]) + bias[8 * j + 2 * e], 0.f) : 0.f;
-            const float b = col_ok ? fmaxf(__uint_as_float(v[8 * j + 2 * e + 1]) + bias[8 * j + 2 * e + 1], 0.f) : 0.f;
-            bf16x2 h = pack2(a, b);
-            w[e] = *reinterpret_cast<uint32_t*>(&h);
+          for (int j = 0; j < 16; ++j) {
+            bf16x2 a = __hmax2(*reinterpret_cast<bf16x2*>(&cur[j]), *reinterpret_cast<bf16x2*>(&prev1[j]));
+            if (!CRNN) a = __hmax2(a, *reinterpret_cast<bf16x2*>(&prev2[j]));
+            vm[j] = *reinterpret_cast<uint32_t*>(&a);
           }
-          o[j] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // the pooling pass that read this ring slot (row r - 3) has finished
-        const uint32_t rowb = rows0 + (uint32_t)(r % 3) * SP_ROWBUF + (uint32_t)m * 128u;
+          if (CRNN) {
+            // 2x2: columns 2x, 2x+1 are lanes 2i, 2i+1 of this warp; the even lane stores channels 0..15 of the pair's
+            // maximum, the odd lane channels 16..31
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t c = (uint32_t)(half * 4 + j);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + ((c ^ (uint32_t)(m & 7)) << 4)), "r"(o[j].x), "r"(o[j].y),
-                       "r"(o[j].z), "r"(o[j].w) : "memory");
-        }
-        asm volatile("bar.sync 2, 256;" ::: "memory");      // the row is complete
-        if ((r & 1) && r > 2 * ya) {                        // (the band's warm-up row 2 ya - 1 is odd too: it belongs to the band above)
-          // pooled row y = (r - 1) / 2 from stem rows r-2 (absent above the image), r-1, r
-          const int y = (r - 1) >> 1;
-          const bool has0 = !CRNN && r - 2 >= r_first;          // 2x2 pooling: rows r-1 and r only
-          const uint32_t b0 = rows0 + (uint32_t)((r + 1) % 3) * SP_ROWBUF;     // (r - 2) % 3
-          const uint32_t b1 = rows0 + (uint32_t)((r + 2) % 3) * SP_ROWBUF;     // (r - 1) % 3
-          const uint32_t b2 = rows0 + (uint32_t)(r % 3) * SP_ROWBUF;
-          for (int idx = et; idx < SP_POOLED * 8; idx += 256) {
-            const int xl = idx >> 3, c = idx & 7;
-            const int xg = SP_POOLED * t + xl;
-            if (xg >= p.Wp) continue;
-            uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t o = __shfl_xor_sync(0xffffffffu, vm[j], 1);
+              bf16x2 a = __hmax2(*reinterpret_cast<bf16x2*>(&vm[j]), *reinterpret_cast<const bf16x2*>(&o));
+              vm[j] = *reinterpret_cast<uint32_t*>(&a);
+            }
+            const int xg = (x0 + m) >> 1;
+            if (col_ok && xg < p.Wp) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out + (((size_t)n * p.Hp + y) * p.Wp + xg) * 64 + half * 32 + (lane & 1) * 16);
+              if (lane & 1) { dst[0] = make_uint4(vm[8], vm[9], vm[10], vm[11]); dst[1] = make_uint4(vm[12], vm[13], vm[14], vm[15]); }
+              else { dst[0] = make_uint4(vm[0], vm[1], vm[2], vm[3]); dst[1] = make_uint4(vm[4], vm[5], vm[6], vm[7]); }
+            }
+          } else {
+            const uint32_t rowb = rows0 + (uint32_t)slot * SP_ROWBUF;
 #pragma unroll
-            for (int rr = 0; rr < 3; ++rr) {
-              if (rr == 0 && !has0) continue;
-              const uint32_t rb = rr == 0 ? b0 : (rr == 1 ? b1 : b2);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t c = (uint32_t)(half * 4 + j);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowb + (uint32_t)m * 128u + ((c ^ (uint32_t)(m & 7)) << 4)), "r"(vm[4 * j]),
+                           "r"(vm[4 * j + 1]), "r"(vm[4 * j + 2]), "r"(vm[4 * j + 3]) : "memory");
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the row maxima of all 128 columns are in place (and every thread
+                                                               // has left the pooling pass of the row before last: two slots)
+            for (int idx = et; idx < SP_POOLED * 8; idx += 256) {
+              const int xl = idx >> 3, c = idx & 7;
+              const int xg = SP_POOLED * t + xl;
+              if (xg >= p.Wp) continue;
+              uint4 acc = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-              for (int dx = 0; dx < (CRNN ? 2 : 3); ++dx) {
+              for (int dx = 0; dx < 3; ++dx) {
                 const uint32_t px = (uint32_t)(2 * xl + dx);
                 uint4 tv;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(tv.x), "=r"(tv.y), "=r"(tv.z), "=r"(tv.w)
-                             : "r"(rb + px * 128u + (((uint32_t)c ^ (px & 7u)) << 4)) : "memory");
+                             : "r"(rowb + px * 128u + (((uint32_t)c ^ (px & 7u)) << 4)) : "memory");
                 bf16x2 a, b;
 #define VTD_HMAX2(dst, src) a = *reinterpret_cast<bf16x2*>(&dst); b = *reinterpret_cast<bf16x2*>(&src); a = __hmax2(a, b); dst = *reinterpret_cast<uint32_t*>(&a);
                 VTD_HMAX2(acc.x, tv.x) VTD_HMAX2(acc.y, tv.y) VTD_HMAX2(acc.z, tv.z) VTD_HMAX2(acc.w, tv.w)
 #undef VTD_HMAX2
               }
+              *reinterpret_cast<uint4*>(p.out + (((size_t)n * p.Hp + y) * p.Wp + xg) * 64 + c * 8) = acc;
             }
-            *reinterpret_cast<uint4*>(p.out + (((size_t)n * p.Hp + y) * p.Wp + xg) * 64 + c * 8) = acc;
+            slot ^= 1;
           }
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { prev2[j] = prev1[j]; prev1[j] = cur[j]; }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");        // the item's last pooling pass is done before the next item writes rows
     }
   }
 
@@ -2302,7 +2329,7 @@ StemPoolPlan* stem_pool_plan_create(const void* in, int N, int dh, int dw, const
   p.total_items = N * p.tiles_x * p.bands;
   CUresult r = encode_weights(enc, &pl->wmap, w, 7 * 32, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(stem weights) failed: " + std::to_string((int)r)); }
-  const int fixed = 7 * 64 * 64 + 3 * SP_ROWBUF + 512 + 1024;
+  const int fixed = 7 * 64 * 64 + 2 * SP_ROWBUF + 512 + 1024;
   int st = (SMEM_TOTAL - fixed) / WIN2_SLOT;
   p.stages = st > 8 ? 8 : st;
   pl->smem = p.stages * WIN2_SLOT + fixed;
@@ -2330,7 +2357,7 @@ StemPoolPlan* stem_pool_plan_create_crnn(const void* in, int N, int cw, const vo
   p.total_items = N * p.tiles_x;
   CUresult r = encode_weights(enc, &pl->wmap, w, 3 * 32, 64, 32, 64, CU_TENSOR_MAP_SWIZZLE_64B);
   if (r != CUDA_SUCCESS) { delete pl; return fail("cuTensorMapEncodeTiled(CRNN stem weights) failed: " + std::to_string((int)r)); }
-  const int fixed = 3 * 64 * 64 + 3 * SP_ROWBUF + 512 + 1024;
+  const int fixed = 3 * 64 * 64 + 2 * SP_ROWBUF + 512 + 1024;
   int st = (SMEM_TOTAL - fixed) / (7 * 1024);
   p.stages = st > 12 ? 12 : st;
   pl->smem = p.stages * 7 * 1024 + fixed;
