@@ -197,6 +197,23 @@ int  vtd_read_records(vtd_ctx* ctx, int n, vtd_record* records_host, int* counts
  * max_batch*(max_boxes*128 + 4) bytes: one collective gathers them (parallel.gather_packed). */
 int  vtd_get_records(vtd_ctx* ctx, vtd_record** records_dev, int** counts_dev);
 
+/* ---- result sink, annotated frames: ProcessingService._draw_detections drop-in (app/services/processing_service.py:188-218).
+ * Draws, per item and in array order within a frame, the green 2-px bbox outline, the filled label plate above it and the
+ * black label text (cv2.rectangle / cv2.getTextSize / cv2.putText, FONT_HERSHEY_SIMPLEX 0.5, thickness 1) into HxWx3 BGR
+ * frames, IN PLACE: device frames are drawn where they are, host frames are copied up, drawn and copied back.  The label is
+ * the caller's bytes ("%s (%.2f)" % (text, detection_confidence) in the reference, :198); bytes outside 32..126 draw '?'
+ * as OpenCV does.  Items may be in any frame order; order among the items of one frame is the draw order.
+ * frame index outside [0,n), label_len outside [0,VTD_OVERLAY_LABEL_MAX] or |coordinate| > 2^24: VTD_ERR_ARG. */
+enum { VTD_OVERLAY_LABEL_MAX = 232 };
+typedef struct vtd_overlay_item {
+  int32_t frame;          /* index into frames[] */
+  int32_t bbox[4];        /* x1,y1,x2,y2 as in the detection dict */
+  int32_t label_len;
+  uint8_t label[VTD_OVERLAY_LABEL_MAX];
+} vtd_overlay_item;       /* 256 bytes */
+int  vtd_draw_detections(vtd_ctx* ctx, uint8_t* const* frames, int n, int h, int w, int pitch, int frames_on_device,
+                         const vtd_overlay_item* items, int n_items);
+
 /* ---- parity harness: copy a named intermediate to the host as fp32 NCHW.
  * names: "input","c2","c3","c4","c5","p2_in","p2","head","crops","cnn","rnn0","rnn1","logits". */
 int  vtd_debug_tensor(vtd_ctx* ctx, const char* name, int n, float* host_out, int64_t capacity, int64_t* shape4);

@@ -56,6 +56,10 @@ RECORD_DTYPE = np.dtype([("frame", "<i4"), ("bbox", "<i4", (4,)), ("polygon", "<
                          ("pad", "u1", (24,))])
 assert C.sizeof(VtdRecord) == 128 and RECORD_DTYPE.itemsize == 128
 
+OVERLAY_LABEL_MAX = 232
+OVERLAY_DTYPE = np.dtype([("frame", "<i4"), ("bbox", "<i4", (4,)), ("label_len", "<i4"), ("label", "u1", (OVERLAY_LABEL_MAX,))])
+assert OVERLAY_DTYPE.itemsize == 256
+
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -70,7 +74,7 @@ def exported_symbols() -> List[str]:
             "vtd_dbnet_forward", "vtd_extract_boxes", "vtd_postprocess_map", "vtd_recognize_boxes",
             "vtd_recognize_crops", "vtd_crnn_forward", "vtd_ctc_decode", "vtd_load_trocr", "vtd_trocr_info",
             "vtd_trocr_generate_crops", "vtd_trocr_forward", "vtd_run_batch", "vtd_read_records",
-            "vtd_get_records", "vtd_debug_tensor", "vtd_set_profiling", "vtd_op_count", "vtd_op_info"]
+            "vtd_get_records", "vtd_draw_detections", "vtd_debug_tensor", "vtd_set_profiling", "vtd_op_count", "vtd_op_info"]
 
 
 _libs: Dict[str, object] = {}
@@ -105,6 +109,7 @@ def load_library(variant: Optional[str] = None):
         lib.vtd_time_T.argtypes = [vp]
         lib.vtd_abi_version.argtypes = []
         lib.vtd_check_guards.argtypes = [vp, C.POINTER(C.c_int64)]
+        lib.vtd_draw_detections.argtypes = [vp, _u8pp, i32, i32, i32, i32, i32, vp, i32]
         lib.vtd_load_detector.argtypes = [vp, C.POINTER(VtdTensor), i32]
         lib.vtd_load_recognizer.argtypes = [vp, C.POINTER(VtdTensor), i32]
         lib.vtd_preprocess.argtypes = [vp, _u8pp, i32, i32, i32, i32, i32, i32]
@@ -406,6 +411,26 @@ class Engine:
         self._check(self.lib.vtd_trocr_info(self._h, info))
         self.trocr = dict(zip(("image", "tokens", "enc_width", "dec_width", "vocab", "max_positions", "crops_per_chunk", "dec_layers"),
                               [int(v) for v in info]))
+
+    def draw_detections(self, frames, items: np.ndarray, on_device: bool = False, h: int = 0, w: int = 0, pitch: int = 0) -> None:
+        """vtd_draw_detections: draws `items` (OVERLAY_DTYPE records) into the frames IN PLACE.  frames: a list of HxWx3 uint8
+        arrays of one size (host), or -- on_device -- a list of device addresses with h, w, pitch given."""
+        items = np.ascontiguousarray(items, dtype=OVERLAY_DTYPE)
+        n = len(frames)
+        ptrs = (C.c_void_p * max(n, 1))()
+        if on_device:
+            for i, a in enumerate(frames):
+                ptrs[i] = int(a)
+        else:
+            h, w = frames[0].shape[:2]
+            pitch = frames[0].strides[0]
+            for i, f in enumerate(frames):
+                if (not isinstance(f, np.ndarray) or f.dtype != np.uint8 or f.ndim != 3 or f.shape != (h, w, 3) or f.strides[2] != 1
+                        or f.strides[1] != 3 or f.strides[0] != pitch or not f.flags.writeable):
+                    raise ValueError("frame %d: expected writeable HxWx3 uint8 frames of one size and pitch" % i)
+                ptrs[i] = f.ctypes.data
+        self._check(self.lib.vtd_draw_detections(self._h, C.cast(ptrs, _u8pp), n, int(h), int(w), int(pitch), 1 if on_device else 0,
+                                                 items.ctypes.data, len(items)))
 
     def trocr_generate_crops(self, crops: Sequence[np.ndarray], max_length: int = 50) -> Tuple[np.ndarray, np.ndarray]:
         """BGR uint8 crops -> (ids [n, max_length] int32 padded as generate() pads, lengths [n])."""

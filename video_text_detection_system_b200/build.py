@@ -17,8 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libvtd_b200.so")
 SOURCES = ["api.cu", "preprocess.cu", "conv_generic.cu", "conv_tcgen05.cu", "db_head.cu", "boxes.cu", "crop.cu",
-           "lstm.cu", "lstm_tcgen05.cu", "ctc.cu", "misc.cu", "trocr.cu"]
-HEADERS = ["common.cuh", "box_geom.cuh", "tc_common.cuh", "resize_tab.h", "trocr_host.inc", os.path.join("..", "..", "include", "vtd.h")]
+           "lstm.cu", "lstm_tcgen05.cu", "ctc.cu", "misc.cu", "trocr.cu", "overlay.cu"]
+HEADERS = ["common.cuh", "box_geom.cuh", "tc_common.cuh", "resize_tab.h", "trocr_host.inc", "overlay_atlas.h", os.path.join("..", "..", "include", "vtd.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

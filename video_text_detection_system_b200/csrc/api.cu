@@ -104,6 +104,7 @@ struct vtd_ctx {
   const uint8_t** frame_ptrs_dev = nullptr;    // whichever of the two the current batch uses
   const uint8_t** frame_ptrs_pinned = nullptr;
   cudaEvent_t ptrs_event = nullptr;
+  OverlayItem* ov_items = nullptr; int* ov_end = nullptr; bool ov_tables = false;   // annotated-frame overlay (lazy)
   int cur_h = 0, cur_w = 0, cur_pitch = 0, cur_n = 0, cur_pix = 0;
   ResizeTab tx, ty; int tab_h = -1, tab_w = -1;
   float* norm_lut = nullptr;            // [3][256] u8 -> normalised fp32
@@ -1431,6 +1432,74 @@ int vtd_run_batch(vtd_ctx* c, const uint8_t* const* frames, int n, int h, int w,
   if ((r = extract_locked(c, n, h, w))) return r;
   if (recognize && (r = recognize_locked(c, n))) return r;
   if (rh || ch) return read_records_locked(c, n, rh, ch);
+  return VTD_OK;
+}
+
+// ProcessingService._draw_detections (processing_service.py:188-218) on the device: csrc/overlay.cu
+int vtd_draw_detections(vtd_ctx* c, uint8_t* const* frames, int n, int h, int w, int pitch, int on_dev,
+                        const vtd_overlay_item* items, int n_items) {
+  static_assert(sizeof(vtd_overlay_item) == sizeof(OverlayItem) && sizeof(OverlayItem) == 256, "overlay item layout");
+  static_assert(offsetof(vtd_overlay_item, label) == offsetof(OverlayItem, label), "overlay item layout");
+  static_assert((int)VTD_OVERLAY_LABEL_MAX == OV_LABEL_MAX, "overlay label capacity");
+  if (!c || !frames || (n_items > 0 && !items)) return VTD_ERR_ARG;
+  Guard g(c);
+  constexpr int PER_FRAME = 256;               // the kernel's list of later, overlapping detections (overlay.cu)
+  if (n <= 0 || n > c->cfg.max_batch) FAIL(VTD_ERR_CAPACITY, "n=%d outside 1..max_batch=%d", n, c->cfg.max_batch);
+  if (h <= 0 || w <= 0 || pitch < w * 3) FAIL(VTD_ERR_ARG, "frame %dx%d with pitch %d", h, w, pitch);
+  for (int i = 0; i < n; ++i) if (!frames[i]) FAIL(VTD_ERR_ARG, "frame %d is a null pointer", i);
+  if (n_items < 0) FAIL(VTD_ERR_ARG, "n_items=%d", n_items);
+  if (n_items == 0) return VTD_OK;
+  std::vector<int> per(n, 0);
+  for (int i = 0; i < n_items; ++i) {
+    const vtd_overlay_item& it = items[i];
+    if (it.frame < 0 || it.frame >= n) FAIL(VTD_ERR_ARG, "item %d names frame %d of %d", i, it.frame, n);
+    if (it.label_len < 0 || it.label_len > VTD_OVERLAY_LABEL_MAX) FAIL(VTD_ERR_ARG, "item %d: label of %d bytes", i, it.label_len);
+    for (int k = 0; k < 4; ++k)
+      if (it.bbox[k] > (1 << 24) || it.bbox[k] < -(1 << 24)) FAIL(VTD_ERR_ARG, "item %d: coordinate %d", i, it.bbox[k]);
+    if (++per[it.frame] > PER_FRAME) FAIL(VTD_ERR_CAPACITY, "more than %d items on frame %d", PER_FRAME, it.frame);
+  }
+  // group by frame, keeping the draw order inside each frame
+  std::vector<int> start(n + 1, 0);
+  for (int f = 0; f < n; ++f) start[f + 1] = start[f] + per[f];
+  std::vector<OverlayItem> sorted(n_items);
+  std::vector<int> fend(n_items), fill(start.begin(), start.end() - 1);
+  for (int i = 0; i < n_items; ++i) {
+    const int at = fill[items[i].frame]++;
+    memcpy(&sorted[at], &items[i], sizeof(OverlayItem));
+    fend[at] = start[items[i].frame + 1];
+  }
+  int r;
+  if (!c->ov_items) {
+    const size_t cap = (size_t)c->cfg.max_batch * PER_FRAME;
+    if ((r = dalloc(c, &c->ov_items, cap * sizeof(OverlayItem))) || (r = dalloc(c, &c->ov_end, cap * sizeof(int)))) return r;
+  }
+  if (!c->ov_tables) { CK(overlay_upload_tables(c->stream)); c->ov_tables = true; }
+  const size_t rowb = (size_t)w * 3;
+  uint8_t* const* ptrs_dev;
+  int dev_pitch = pitch;
+  if (!on_dev) {
+    const size_t fb = rowb * h;
+    if (fb > c->frame_bytes_cap) FAIL(VTD_ERR_CAPACITY, "frame of %zu bytes exceeds the staging slot", fb);
+    dev_pitch = (int)rowb;
+    for (int i = 0; i < n; ++i)
+      CK(cudaMemcpy2DAsync(c->frames_store + (size_t)i * c->frame_bytes_cap, rowb, frames[i], pitch, rowb, h, cudaMemcpyHostToDevice,
+                           c->stream));
+    ptrs_dev = const_cast<uint8_t* const*>(reinterpret_cast<const uint8_t* const*>(c->store_ptrs_dev));
+  } else {
+    CK(cudaEventSynchronize(c->ptrs_event));
+    for (int i = 0; i < n; ++i) c->frame_ptrs_pinned[i] = frames[i];
+    CK(cudaMemcpyAsync(c->ext_ptrs_dev, c->frame_ptrs_pinned, sizeof(void*) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ptrs_event, c->stream));
+    ptrs_dev = const_cast<uint8_t* const*>(reinterpret_cast<const uint8_t* const*>(c->ext_ptrs_dev));
+  }
+  CK(cudaMemcpyAsync(c->ov_items, sorted.data(), sizeof(OverlayItem) * n_items, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->ov_end, fend.data(), sizeof(int) * n_items, cudaMemcpyHostToDevice, c->stream));
+  CK(draw_overlay(ptrs_dev, h, w, dev_pitch, c->ov_items, c->ov_end, n_items, c->stream, &c->lc));
+  if (!on_dev)
+    for (int i = 0; i < n; ++i)
+      CK(cudaMemcpy2DAsync(frames[i], pitch, c->frames_store + (size_t)i * c->frame_bytes_cap, rowb, rowb, h, cudaMemcpyDeviceToHost,
+                           c->stream));
+  CK(cudaStreamSynchronize(c->stream));          // host frames are complete; `sorted`/`fend` die here
   return VTD_OK;
 }
 

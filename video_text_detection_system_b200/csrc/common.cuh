@@ -234,6 +234,14 @@ cudaError_t trocr_resize_patches(const uint8_t* const* crops_dev, const void* me
                                  int n, int S, int P, int max_h, cudaStream_t s, LaunchCounter* lc);
 cudaError_t nchw_to_patches(const float* x, bf16* patches, int n, int S, int P, cudaStream_t s, LaunchCounter* lc);
 
+// ---- annotated-frame overlay (overlay.cu) ----------------------------------------------------------------------
+constexpr int OV_LABEL_MAX = 232;
+struct OverlayItem { int32_t frame; int32_t bbox[4]; int32_t label_len; uint8_t label[OV_LABEL_MAX]; };   // == vtd_overlay_item
+cudaError_t overlay_upload_tables(cudaStream_t s);
+// items grouped by frame; frame_end[i] = one past the last item of item i's frame
+cudaError_t draw_overlay(uint8_t* const* frames, int h, int w, int pitch, const OverlayItem* items, const int* frame_end,
+                         int n_items, cudaStream_t s, LaunchCounter* lc);
+
 // ---- layout helpers ----------------------------------------------------------------------------------------
 template <typename T>
 cudaError_t nchw_f32_to_nhwc(const float* in, T* out, int N, int C, int H, int W, OutLayout lay, cudaStream_t s,

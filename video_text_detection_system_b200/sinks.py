@@ -9,7 +9,9 @@ At the rates the device path delivers (16 frames x ~50 detections every ~5 ms) a
 bottleneck, so the text formats are written as strings in one pass per frame, and the database rows are plain dicts in
 the bulk-insert shape.  Outputs are character-for-character those of the reference's functions for the same result
 dictionary (tests/test_sinks.py checks them against goldens minted from the reference's own code, and against
-xml.etree / csv on hostile strings).  Nothing here touches the device; the overlay drawn on the GPU is not built yet.
+xml.etree / csv on hostile strings).  The annotated frame exists twice: `draw_detections` (OpenCV on the host, the reference's
+own calls) and `OverlayRenderer` / `draw_detections_batch` (csrc/overlay.cu through vtd_draw_detections: a batch of frames
+drawn in HBM, pixel-identical to the host version for labels inside the frame).
 """
 from __future__ import annotations
 
@@ -144,6 +146,81 @@ def draw_detections(frame: np.ndarray, detections: List[Dict[str, Any]]) -> np.n
         cv2.rectangle(frame, (x1, y1 - th - 10), (x1 + tw, y1), green, -1)
         cv2.putText(frame, label, (x1, y1 - 5), font, 0.5, black, 1)
     return frame
+
+
+# ---------------------------------------------------------------------------------------------- overlay (device)
+def overlay_items(detections_per_frame: List[List[Dict[str, Any]]]) -> np.ndarray:
+    """The draw list of vtd_draw_detections for a batch: one record per detection with a 4-element bbox, label
+    "%s (%.2f)" % (text, detection_confidence) as processing_service.py:198 formats it, UTF-8 bytes (OpenCV draws '?' for
+    every byte outside 32..126)."""
+    from ._lib import OVERLAY_DTYPE, OVERLAY_LABEL_MAX
+    rows = []
+    for f, dets in enumerate(detections_per_frame):
+        for d in dets:
+            box = d.get("bbox", [])
+            if len(box) != 4:
+                continue
+            label = ("%s (%.2f)" % (d.get("text", ""), d.get("detection_confidence", 0.0))).encode("utf-8")
+            if len(label) > OVERLAY_LABEL_MAX:
+                raise ValueError("label of %d bytes exceeds the overlay's %d" % (len(label), OVERLAY_LABEL_MAX))
+            rows.append((f, [int(v) for v in box], label))
+    items = np.zeros(len(rows), OVERLAY_DTYPE)
+    for i, (f, box, label) in enumerate(rows):
+        items[i]["frame"] = f
+        items[i]["bbox"] = box
+        items[i]["label_len"] = len(label)
+        items[i]["label"][:len(label)] = np.frombuffer(label, np.uint8)
+    return items
+
+
+class OverlayRenderer:
+    """Draws the detections of a batch of equally sized BGR frames on the device, in place (vtd_draw_detections).  Owns a
+    small context sized for the frames it is given; pass `engine=` to draw with an existing one (its max_batch / max_src
+    must cover the frames)."""
+
+    def __init__(self, engine=None, device: int = 0, max_batch: int = 16):
+        self._engine = engine
+        self._own = None
+        self._device = int(device)
+        self._max_batch = int(max_batch)
+
+    def _eng(self, n: int, h: int, w: int):
+        if self._engine is not None:
+            return self._engine
+        key = (max(n, self._max_batch), h, w)
+        if self._own is None or self._own[0][0] < key[0] or self._own[0][1:] != key[1:]:
+            from ._lib import Engine
+            self._own = (key, Engine(device=self._device, dtype="fp16", det_h=32, det_w=32, max_batch=key[0], max_boxes=64,
+                                     max_src_h=h, max_src_w=w))
+        return self._own[1]
+
+    def draw(self, frames: List[np.ndarray], detections_per_frame: List[List[Dict[str, Any]]]) -> List[np.ndarray]:
+        if len(frames) != len(detections_per_frame):
+            raise ValueError("one detection list per frame")
+        if not frames:
+            return frames
+        items = overlay_items(detections_per_frame)
+        h, w = frames[0].shape[:2]
+        eng = self._eng(len(frames), h, w)
+        step = eng.cfg.max_batch
+        for first in range(0, len(frames), step):
+            part = frames[first:first + step]
+            sel = items[(items["frame"] >= first) & (items["frame"] < first + len(part))].copy()
+            sel["frame"] -= first
+            if len(sel):
+                eng.draw_detections(part, sel)
+        return frames
+
+
+_renderer = None
+
+
+def draw_detections_batch(frames: List[np.ndarray], detections_per_frame: List[List[Dict[str, Any]]]) -> List[np.ndarray]:
+    """Device counterpart of [draw_detections(f, d) for f, d in zip(frames, detections_per_frame)]; draws in place."""
+    global _renderer
+    if _renderer is None:
+        _renderer = OverlayRenderer()
+    return _renderer.draw(frames, detections_per_frame)
 
 
 class ResultSinks:
