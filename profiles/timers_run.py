@@ -1,4 +1,4 @@
-"""Dev tool: with a -DVTD_TIMERS build (VTD_NVCC_EXTRA=-DVTD_TIMERS python -m ...build --force) print, for every tcgen05
+"""Dev tool: with the developer build (python video_text_detection_system_b200/build.py --dev; run with VTD_STORAGE=dev) print, for every tcgen05
 conv launch of one bench-shaped batch, where each role warp spent its cycles."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,7 +6,7 @@ import numpy as np, torch
 from oracle import port
 from video_text_detection_system_b200 import _lib
 B = 16
-eng = _lib.Engine(device=0, backbone=18, dtype="bf16", det_h=736, det_w=1312, crop_w=128, max_batch=B, max_boxes=64,
+eng = _lib.Engine(device=0, backbone=18, dtype="16bit", det_h=736, det_w=1312, crop_w=128, max_batch=B, max_boxes=64,
                   max_src_h=1080, max_src_w=1920)
 eng.load_detector(port.build_dbnet("resnet18", seed=0).state_dict())
 eng.load_recognizer(port.build_crnn(seed=0).state_dict())

@@ -46,6 +46,10 @@ def variant_paths(variant: str = ""):
         return OBJ, LIB, []
     if variant == "bf16":
         return OBJ + "_bf16", os.path.join(HERE, "libvtd_b200_bf16.so"), ["-DVTD_BF16_STORAGE"]
+    if variant == "dev":      # developer build: tuning switches and per-role cycle counters compiled in (never shipped, never benched)
+        return OBJ + "_dev", os.path.join(HERE, "libvtd_b200_dev.so"), ["-DVTD_DEV", "-DVTD_TIMERS"]
+    if variant == "prev":     # A/B aid: a release build of an older checkout copied here as libvtd_b200_prev.so (VTD_STORAGE=prev)
+        return OBJ + "_prev", os.path.join(HERE, "libvtd_b200_prev.so"), []
     raise ValueError("unknown build variant %r" % variant)
 
 
@@ -84,4 +88,4 @@ def build_library(force: bool = False, verbose: bool = False, variant: str = "")
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True, variant="bf16" if "--bf16" in sys.argv else ""))
+    print(build_library(force="--force" in sys.argv, verbose=True, variant="bf16" if "--bf16" in sys.argv else "dev" if "--dev" in sys.argv else ""))

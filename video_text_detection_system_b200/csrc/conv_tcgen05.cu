@@ -330,15 +330,19 @@ __device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUte
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (((uint32_t)j ^ sw) << 4)), "r"(o[j].x), "r"(o[j].y),
                  "r"(o[j].z), "r"(o[j].w) : "memory");
   if (p.pool) {
-    // fused max-pool (nn.MaxPool2d after conv+BN+ReLU, text_recognizer.py:17-23): the warp's box is 16 x 2 pixels, so every
-    // pooling window lies inside it.  Each lane reduces a slice of one pooled pixel from the staged rows with packed
-    // bf16 max (max commutes with the bf16 rounding already applied) and only the pooled box goes to HBM.
+    // fused max-pool (nn.MaxPool2d after conv+BN+ReLU, text_recognizer.py:17-23): the warp's box is 16 x 2 pixels (8 x 4 in
+    // the halo tiles), so every pooling window lies inside it.  Each lane reduces a slice of one pooled pixel from the
+    // staged rows with packed bf16 max (max commutes with the bf16 rounding already applied) and only the pooled box goes
+    // to HBM.  Staged row of box pixel (x, y) = y * bw + x; pooled pixel pp = py * (pooled box width) + px.
     __syncwarp();
     const bool p22 = p.pool == 1;
+    const int bw = 1 << p.lw;                                   // box width: 16 or 8
     const int pp = p22 ? lane >> 2 : lane >> 1;                 // pooled pixel of the box: 8 (2x2) or 16 ((2,1))
     const int c_first = p22 ? (lane & 3) * 2 : (lane & 1) * 4;  // first 16-byte chunk of this lane's slice
     const int nch = p22 ? 2 : 4;
-    const int r00 = p22 ? 2 * pp : pp;                          // top-left source row (pixel) of the window
+    const int pbw = p22 ? bw >> 1 : bw;
+    const int ppx = pp & (pbw - 1), ppy = pp / pbw;
+    const int r00 = 2 * ppy * bw + (p22 ? 2 * ppx : ppx);       // top-left source row (pixel) of the window
     const uint32_t prow = pstg + (uint32_t)pp * 128u;
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
@@ -347,8 +351,8 @@ __device__ __forceinline__ void epilogue_group_tma(const TcParams& p, const CUte
       uint4 m4;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        if (!p22 && (w & 1)) continue;                          // (2,1): rows r and r + 16 only
-        const uint32_t r = (uint32_t)(r00 + (w & 1) + (w >> 1) * 16);
+        if (!p22 && (w & 1)) continue;                          // (2,1): the pixel and the one below it only
+        const uint32_t r = (uint32_t)(r00 + (w & 1) + (w >> 1) * bw);
         uint4 t;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
                      : "r"(stg + r * 128u + ((c ^ (r & 7u)) << 4)) : "memory");
@@ -988,7 +992,8 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const uint32_t bslot = (uint32_t)taps * BSLAB;
   const uint32_t bring = ring + a_st * HALO_SLOT;
   const uint32_t stg0 = bring + b_st * bslot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (stg0 - ring) + NUM_EPI_WARPS * 4096);
+  const uint32_t pstg0 = stg0 + NUM_EPI_WARPS * 4096;    // pooled boxes (p.pool only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_ptr + (pstg0 - ring) + (p.pool ? NUM_EPI_WARPS * 2048 : 0));
   const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * 4, bfull0 = aempty0 + 8 * 4, bempty0 = bfull0 + 8 * 8;
   const uint32_t tfull0 = bempty0 + 8 * 8, tempty0 = tfull0 + 8 * 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
@@ -1025,6 +1030,14 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     int as_ = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+    // p.bres (one 64-channel chunk, the ring holds all nine taps of this CTA's weight half): loaded once, never released --
+    // streamed per tile the weights of a 64 -> 128 layer alone would ask more of L2 than it delivers
+    if (p.bres && cluster_id < npairs && elect_one())
+      for (int tg = 0; tg < tgroups; ++tg) {
+        if (rank == 0) mbar_expect_tx(bfull0 + 8 * tg, 2u * bslot);
+        tma_load_4d_2sm(bring + tg * bslot, &maps.b4, bfull0 + 8 * tg, 0, (int)rank * HALF_N, 0, tg * taps);
+      }
+    __syncwarp();
     for (int pair = cluster_id; pair < npairs; pair += nclusters) {
       int t = my_tile(pair);
       const int tx = t % p.tiles_x; t /= p.tiles_x;
@@ -1038,6 +1051,7 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         }
         __syncwarp();
         if (++as_ == a_st) { as_ = 0; aph ^= 1; }
+        if (p.bres) continue;
         for (int tg = 0; tg < tgroups; ++tg) {
           mbar_wait(bempty0 + 8 * bs, bph ^ 1);
           if (elect_one()) {
@@ -1063,7 +1077,7 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
           const uint32_t sa = ring + as_ * HALO_SLOT;
           int fr = 0, fs = 0;
           for (int tg = 0; tg < tgroups; ++tg) {
-            mbar_wait(bfull0 + 8 * bs, bph);
+            if (!p.bres || pair == cluster_id) mbar_wait(bfull0 + 8 * bs, bph);       // resident weights: landed once
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
               const uint64_t ad0 = umma_desc_sw128(sa + (uint32_t)(fr * HALO_PW + fs) * 128u, HALO_PW * 128u);
@@ -1073,7 +1087,7 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 for (int k = 0; k < 4; ++k)
                   umma_f16_2sm(d_tmem, ad0 + (uint64_t)(tt * 8 + k * 2), bd0 + (uint64_t)(tt * (BSLAB >> 4) + k * 2), idesc,
                                (kc | tg | tt | k) ? 1u : 0u);
-              umma_commit_2sm(bempty0 + 8 * bs);
+              if (!p.bres) umma_commit_2sm(bempty0 + 8 * bs);
               if (tg == tgroups - 1) {
                 umma_commit_2sm(aempty0 + 8 * as_);
                 if (kc == kchunks - 1) umma_commit_2sm(tfull0 + 8 * acc);
@@ -1124,13 +1138,13 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             for (int j = 0; j < 8; ++j) rv[j] = make_uint4(0u, 0u, 0u, 0u);
           }
         }
-        epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, 0u, tmem_acc, q, lane, g, use_res, rv, 0, tx * 8 + (m0 & 7),
-                                    ty * 16 + ((m0 >> 3) & 15), t);
+        epilogue_group_tma<BLOCK_N>(p, &maps.o, stg, pstg0 + (uint32_t)(warp - 2) * 2048u, tmem_acc, q, lane, g, use_res, rv, 0,
+                                    tx * 8 + (m0 & 7), ty * 16 + ((m0 >> 3) & 15), t);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0)
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader + 8 * acc) : "memory");
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader + 8 * acc) : "memory");
       if (++acc == ACC) { acc = 0; accph ^= 1; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1311,7 +1325,7 @@ conv_tc2g_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0)
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader + 8 * acc) : "memory");
+        asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(tempty_leader + 8 * acc) : "memory");
       if (++acc == ACC) { acc = 0; accph ^= 1; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -2066,7 +2080,10 @@ TcPlan* tc_plan_create(const ConvDesc& d, std::string* err) {
   p.halo = (d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && d.Cin == 64 && d.Cout == 64 && !d.pool && d.Ho >= 8 &&
             d.Wo >= 8 && !dev_env("VTD_NO_HALO") && !dev_env("VTD_NO_BRES")) ? 1 : 0;
   // any other 3x3 s1 p1 layer whose maps tile into 8 x 16 pixels with little waste: halo mode with streamed weights (2)
-  if (!p.halo && d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && !d.pool && !dev_env("VTD_NO_HALO")) {
+  // (a pooled layer only as a CTA pair, N = 128, whole pooling windows per 8 x 16 tile: the CRNN's 64 -> 128 layer)
+  if (!p.halo && d.KH == 3 && d.KW == 3 && d.stride == 1 && d.pad == 1 && !dev_env("VTD_NO_HALO") &&
+      (!d.pool || (bn == 128 && d.Cout == 128 && !d.out_f32 && d.N * ((d.Wo + 7) / 8) * ((d.Ho + 15) / 16) >= 2 &&
+                   !dev_env("VTD_NO_POOL_HALO") && !dev_env("VTD_CTA2")))) {
     const long long covered = (long long)((d.Wo + 7) / 8 * 8) * ((d.Ho + 15) / 16 * 16);
     int mask = 3;                                         // bit 0: N = 128 layers, bit 1: N = 256 layers
     if (const char* e = dev_env("VTD_HALO2")) mask = atoi(e);
@@ -2416,10 +2433,17 @@ static void plan_smem(TcPlan* pl) {
       const int bslot2 = p.b_taps * (BN / 2) * 128;
       const int fixed2 = 1024 + 512;
       p.stages = 2; p.epi_tma = 1;
-      int bst = (SMEM_TOTAL - fixed2 - p.stages * HALO_SLOT - NUM_EPI_WARPS * 4096) / bslot2;
+      const int stg2 = NUM_EPI_WARPS * 4096 + (p.pool ? NUM_EPI_WARPS * 2048 : 0);
+      int bst = (SMEM_TOTAL - fixed2 - p.stages * HALO_SLOT - stg2) / bslot2;
       p.b_stages = bst > 8 ? 8 : bst;
+      // one 64-channel chunk and room for all nine taps: the weights stay (conv_tc2_kernel, p.bres), the patch ring deepens
+      if (p.Cin == 64 && p.b_taps == 3 && bst >= 3 && !dev_env("VTD_NO_BRES")) {
+        p.bres = 1; p.b_stages = 3;
+        int ast = (SMEM_TOTAL - fixed2 - 3 * bslot2 - stg2) / HALO_SLOT;
+        p.stages = ast > 4 ? 4 : ast;
+      }
       p.dbg = 0;
-      pl->smem = p.stages * HALO_SLOT + p.b_stages * bslot2 + NUM_EPI_WARPS * 4096 + fixed2;
+      pl->smem = p.stages * HALO_SLOT + p.b_stages * bslot2 + stg2 + fixed2;
       return;
     }
     const int stg = NUM_EPI_WARPS * 4096;
