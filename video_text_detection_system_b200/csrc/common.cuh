@@ -229,6 +229,10 @@ cudaError_t kv_append(const bf16* qkv /*[n][3D]*/, bf16* cache /*[n][Lcap][2D]*/
                       LaunchCounter* lc);
 cudaError_t argmax_rows(const float* logits, int n, int V, int ld, int* ids, int ids_ld, int t, int eos, int pad, int* finished,
                         int* n_finished, cudaStream_t s, LaunchCounter* lc);
+// Linears of the decode loop (M <= 128 rows): every SM streams a slice of the weights (trocr.cu)
+bool skinny_gemm_supported(int M, int N, int K);
+cudaError_t skinny_gemm(const bf16* X, int ldx, const bf16* W, const float* bias, const bf16* res, int ldres, void* out, int ldo,
+                        int out_f32, int M, int N, int K, int act, cudaStream_t s, LaunchCounter* lc);
 struct TrocrCropMeta { int h, w, pitch, ksx, ksy, offx, offy; long long tmp_off; };   // == CropMeta of trocr.cu
 cudaError_t trocr_resize_patches(const uint8_t* const* crops_dev, const void* meta_dev, const int* tab_dev, uint8_t* tmp, bf16* patches,
                                  int n, int S, int P, int max_h, cudaStream_t s, LaunchCounter* lc);

@@ -62,6 +62,136 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
   }
 }
 
+// LayerNorm of a handful of rows (the decode loop: one row per crop): one CTA per row, the row held in registers, so the
+// two reductions cost two block-wide shuffles instead of three strided passes of one warp.
+__global__ void __launch_bounds__(256) layernorm_row_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ y, int C, float eps) {
+  __shared__ float red[2][8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+  const size_t row = blockIdx.x;
+  const bool on = t * 8 < C;
+  float v[8];
+  float s = 0.f;
+  if (on) {
+    const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + t * 8);
+    const bf16x2* h = reinterpret_cast<const bf16x2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = unpack2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; s += f.x + f.y; }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0) red[0][warp] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < nw; ++w) s += red[0][w];
+  const float mean = s / (float)C;
+  float q = 0.f;
+  if (on) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float a = v[e] - mean; q += a * a; }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+  if (lane == 0) red[1][warp] = q;
+  __syncthreads();
+  q = 0.f;
+  for (int w = 0; w < nw; ++w) q += red[1][w];
+  const float rstd = rsqrtf(q / (float)C + eps);
+  if (on) {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + t * 8), g1 = *reinterpret_cast<const float4*>(gamma + t * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + t * 8), b1 = *reinterpret_cast<const float4*>(beta + t * 8 + 4);
+    uint4 o;
+    o.x = pack16((v[0] - mean) * rstd * g0.x + b0.x, (v[1] - mean) * rstd * g0.y + b0.y);
+    o.y = pack16((v[2] - mean) * rstd * g0.z + b0.z, (v[3] - mean) * rstd * g0.w + b0.w);
+    o.z = pack16((v[4] - mean) * rstd * g1.x + b1.x, (v[5] - mean) * rstd * g1.y + b1.y);
+    o.w = pack16((v[6] - mean) * rstd * g1.z + b1.z, (v[7] - mean) * rstd * g1.w + b1.w);
+    *reinterpret_cast<uint4*>(y + row * C + t * 8) = o;
+  }
+}
+
+// ---- skinny GEMM: the Linears of the DECODE loop ------------------------------------------------------------------------
+// Y[m][n] = act(sum_k X[m][k] W[n][k] + bias[n]) (+ res[m][n]) for m < M <= 128 rows (one row per crop).  On the 128-row tcgen05
+// tiles such a GEMM is N/256 CTAs streaming 0.5-2 MB of weights each (19 us per launch measured); here the N columns are spread
+// over every SM -- a CTA owns 8*WN columns, its 8 warps are WN column tiles x (8/WN) slices of K -- and the weights cross HBM
+// once at full width.  mma.sync m16n8k16 with a permuted K order: within a 32-wide K block thread t of a quad loads the 8
+// consecutive elements 8t..8t+7 of its A rows and of its B column as ONE 16-byte load each and feeds elements 0..3 to the first
+// MMA, 4..7 to the second; A and B use the same permutation, so the sum over K is unchanged.  Partial sums of the K slices meet
+// in shared memory, where bias, residual and activation are applied.
+template <int MT>
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const bf16* __restrict__ X, int ldx, const bf16* __restrict__ W,
+                                                          const float* __restrict__ bias, const bf16* __restrict__ res, int ldres,
+                                                          void* __restrict__ out, int ldo, int out_f32, int M, int N, int K, int act,
+                                                          int WN) {
+  __shared__ float red[MT * 16 * 64];                    // [K slice][row][column of the CTA]
+  extern __shared__ __align__(16) uint8_t wsm[];         // the CTA's 8*WN weight rows, pitch 2K + 64 bytes (conflict-free 16-byte reads)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int WK = 8 / WN, wn = warp % WN, wk = warp / WN;
+  const int cols = 8 * WN;
+  const int ks = K / WK, k0 = wk * ks;
+  // the whole weight slice is requested at once (cp.async): 16-130 KB in flight per SM is what keeps HBM busy when every CTA
+  // has only microseconds of work
+  const int pitch = 2 * K + 64, chunks = K / 8;
+  for (int i = threadIdx.x; i < cols * chunks; i += 256) {
+    const int r = i / chunks, ch = i % chunks;
+    const int col = blockIdx.x * cols + r;
+    const bf16* src = W + (size_t)(col < N ? col : N - 1) * K + ch * 8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(wsm + (size_t)r * pitch + ch * 16)), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  float acc[MT][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  const uint8_t* wrow = wsm + (size_t)(wn * 8 + g) * pitch + (size_t)(k0 + t * 8) * 2;
+  const bf16* xrow[MT][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int r0 = i * 16 + g, r1 = r0 + 8;
+    xrow[i][0] = X + (size_t)(r0 < M ? r0 : M - 1) * ldx + k0 + t * 8;
+    xrow[i][1] = X + (size_t)(r1 < M ? r1 : M - 1) * ldx + k0 + t * 8;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+#pragma unroll 2
+  for (int kb = 0; kb < ks; kb += 32) {
+    const uint4 wv = *reinterpret_cast<const uint4*>(wrow + (size_t)kb * 2);
+    uint4 xa[MT], xb[MT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      xa[i] = *reinterpret_cast<const uint4*>(xrow[i][0] + kb);
+      xb[i] = *reinterpret_cast<const uint4*>(xrow[i][1] + kb);
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const uint32_t a1[4] = {xa[i].x, xb[i].x, xa[i].y, xb[i].y};
+      const uint32_t a2[4] = {xa[i].z, xb[i].z, xa[i].w, xb[i].w};
+      mma16816(acc[i], a1, wv.x, wv.y);
+      mma16816(acc[i], a2, wv.z, wv.w);
+    }
+  }
+  // C fragment: (row g, cols 2t, 2t+1), (row g + 8, cols 2t, 2t+1)
+  float* mine = red + (size_t)wk * (MT * 16) * cols;
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    const int r0 = i * 16 + g, c = wn * 8 + 2 * t;
+    mine[r0 * cols + c] = acc[i][0]; mine[r0 * cols + c + 1] = acc[i][1];
+    mine[(r0 + 8) * cols + c] = acc[i][2]; mine[(r0 + 8) * cols + c + 1] = acc[i][3];
+  }
+  __syncthreads();
+  const int nb = blockIdx.x * cols;
+  for (int o = threadIdx.x; o < MT * 16 * cols; o += 256) {
+    const int m = o / cols, c = o % cols, col = nb + c;
+    if (m >= M || col >= N) continue;
+    float v = 0.f;
+    for (int w = 0; w < WK; ++w) v += red[(size_t)w * (MT * 16) * cols + o];
+    if (bias) v += bias[col];
+    if (res) v += to_f(res[(size_t)m * ldres + col]);
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 2) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
+    if (out_f32) reinterpret_cast<float*>(out)[(size_t)m * ldo + col] = v;
+    else reinterpret_cast<bf16*>(out)[(size_t)m * ldo + col] = f32_to_16(v);
+  }
+}
+
 // ---- encoder attention -------------------------------------------------------------------------------------------------
 // grid (ceil(S/64), heads, n); 4 warps, 16 query rows each; head dimension 64.
 constexpr int AT_LD = 72;          // shared-memory row pitch in elements (64 + 8: conflict-free ldmatrix)
@@ -179,40 +309,44 @@ __global__ void __launch_bounds__(128) attention_enc_kernel(const bf16* __restri
 // ---- decode attention: one query per (crop, head) against L cached keys/values -------------------------------------------
 // q: [n][ldq] (head hd at hd*64); k, v: [n][Lcap][ldkv] (head hd at hd*64 from each base pointer); out: [n][heads*64]
 constexpr int AD_MAXL = 640;
+// Eight lanes share a key / value row: each reads 16 bytes (8 of the 64 head dimensions), so a warp instruction covers four
+// whole 128-byte rows, 16 rows per CTA pass, all loads of a pass independent (the rows of one head are 2*D*2 bytes apart in the
+// [token][K | V] buffers; one thread per row with eight dependent 16-byte loads ran at 2 TB/s).
 __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k,
                                                                const bf16* __restrict__ v, int ldkv, int Lcap, int L, float scale,
                                                                bf16* __restrict__ out, int D) {
   __shared__ float sc[AD_MAXL];
   __shared__ float red[4];
-  __shared__ float part[2][64];
+  __shared__ float part[16][64];
   const int hd = blockIdx.x, n = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  float qv[64];
+  const int sub = t & 7, grp = t >> 3;                  // 8 dimensions sub*8.., row group 0..15
+  float qv[8];
   {
-    const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)n * ldq + hd * 64);
+    const uint4 u = *reinterpret_cast<const uint4*>(q + (size_t)n * ldq + hd * 64 + sub * 8);
+    const bf16x2* h = reinterpret_cast<const bf16x2*>(&u);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint4 u = qp[i];
-      const bf16x2* h = reinterpret_cast<const bf16x2*>(&u);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = unpack2(h[e]); qv[i * 8 + 2 * e] = f.x; qv[i * 8 + 2 * e + 1] = f.y; }
-    }
+    for (int e = 0; e < 4; ++e) { const float2 f = unpack2(h[e]); qv[2 * e] = f.x * scale; qv[2 * e + 1] = f.y * scale; }
   }
-  const bf16* kb = k + (size_t)n * Lcap * ldkv + hd * 64;
-  const bf16* vb = v + (size_t)n * Lcap * ldkv + hd * 64;
+  const bf16* kb = k + (size_t)n * Lcap * ldkv + hd * 64 + sub * 8;
+  const bf16* vb = v + (size_t)n * Lcap * ldkv + hd * 64 + sub * 8;
   float mx = -INFINITY;
-  for (int j = t; j < L; j += 128) {
-    const uint4* kp = reinterpret_cast<const uint4*>(kb + (size_t)j * ldkv);
+#pragma unroll 4
+  for (int j0 = 0; j0 < L; j0 += 16) {                  // uniform trip count: the shuffles below need the whole warp
+    const int j = j0 + grp;
     float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint4 u = kp[i];
+    if (j < L) {
+      const uint4 u = *reinterpret_cast<const uint4*>(kb + (size_t)j * ldkv);
       const bf16x2* h = reinterpret_cast<const bf16x2*>(&u);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = unpack2(h[e]); acc += qv[i * 8 + 2 * e] * f.x + qv[i * 8 + 2 * e + 1] * f.y; }
+      for (int e = 0; e < 4; ++e) { const float2 f = unpack2(h[e]); acc += qv[2 * e] * f.x + qv[2 * e + 1] * f.y; }
     }
-    acc *= scale;
-    sc[j] = acc;
-    mx = fmaxf(mx, acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (j < L) {
+      if (sub == 0) sc[j] = acc;
+      mx = fmaxf(mx, acc);
+    }
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
@@ -227,13 +361,25 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __res
   if (lane == 0) red[warp] = sum;
   __syncthreads();
   sum = red[0] + red[1] + red[2] + red[3];
-  // out[d] = sum_j p[j] v[j][d]: thread (half, d) walks every second key
-  const int d = t & 63, half = t >> 6;
-  float acc = 0.f;
-  for (int j = half; j < L; j += 2) acc += sc[j] * to_f(vb[(size_t)j * ldkv + d]);
-  part[half][d] = acc;
+  // out[d] = sum_j p[j] v[j][d]: row group grp walks every sixteenth key, 8 dimensions per lane
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int j = grp; j < L; j += 16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(vb + (size_t)j * ldkv);
+    const bf16x2* h = reinterpret_cast<const bf16x2*>(&u);
+    const float pj = sc[j];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = unpack2(h[e]); acc[2 * e] += pj * f.x; acc[2 * e + 1] += pj * f.y; }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[grp][sub * 8 + e] = acc[e];
   __syncthreads();
-  if (t < 64) out[(size_t)n * D + hd * 64 + t] = f32_to_16((part[0][t] + part[1][t]) / sum);
+  if (t < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) o += part[r][t];
+    out[(size_t)n * D + hd * 64 + t] = f32_to_16(o / sum);
+  }
 }
 
 // ---- small elementwise kernels ---------------------------------------------------------------------------------------------
@@ -378,7 +524,39 @@ cudaError_t layernorm_rows(const bf16* x, const float* gamma, const float* beta,
                            cudaStream_t s, LaunchCounter* lc) {
   if (rows <= 0) return cudaSuccess;
   if (C & 1) return cudaErrorInvalidValue;
-  layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, gamma, beta, y, rows, C, eps);
+  if (rows <= 512 && C % 8 == 0 && C <= 2048) {           // decode loop: a CTA per row
+    const int threads = ((C / 8 + 31) / 32) * 32;
+    layernorm_row_kernel<<<(unsigned)rows, threads, 0, s>>>(x, gamma, beta, y, C, eps);
+  } else {
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, gamma, beta, y, rows, C, eps);
+  }
+  if (lc) lc->n++;
+  return cudaGetLastError();
+}
+
+bool skinny_gemm_supported(int M, int N, int K) { return M >= 1 && M <= 128 && K % 256 == 0 && N >= 8; }
+
+cudaError_t skinny_gemm(const bf16* X, int ldx, const bf16* W, const float* bias, const bf16* res, int ldres, void* out, int ldo,
+                        int out_f32, int M, int N, int K, int act, cudaStream_t s, LaunchCounter* lc) {
+  if (M <= 0) return cudaSuccess;
+  if (!skinny_gemm_supported(M, N, K)) return cudaErrorInvalidValue;
+  int WN = 1;
+  while (WN < 8 && (N + 8 * WN - 1) / (8 * WN) > 320) WN *= 2;     // enough CTAs for every SM, K slices of at least 256 / WN
+  while (WN > 1 && (size_t)8 * WN * (2 * K + 64) > 160 * 1024) WN /= 2;
+  const size_t smem = (size_t)8 * WN * (2 * K + 64);
+  if (smem > 160 * 1024) return cudaErrorInvalidValue;
+  static PerDeviceFlag attr_done;
+  cudaError_t ae = once_per_device(attr_done, [] {
+    cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(skinny_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(skinny_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    return e;
+  });
+  if (ae != cudaSuccess) return ae;
+  const unsigned grid = (unsigned)((N + 8 * WN - 1) / (8 * WN));
+  if (M <= 32) skinny_gemm_kernel<2><<<grid, 256, smem, s>>>(X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
+  else if (M <= 64) skinny_gemm_kernel<4><<<grid, 256, smem, s>>>(X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
+  else skinny_gemm_kernel<8><<<grid, 256, smem, s>>>(X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
