@@ -220,15 +220,18 @@ cudaError_t layernorm_rows(const bf16* x, const float* gamma, const float* beta,
 cudaError_t attention_enc(const bf16* qkv /*[n][S][3D]*/, bf16* out /*[n][S][D]*/, int n, int S, int heads, float scale,
                           cudaStream_t s, LaunchCounter* lc);
 cudaError_t attention_decode(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldkv, int Lcap, int L, int n, int heads,
-                             float scale, bf16* out /*[n][heads*64]*/, cudaStream_t s, LaunchCounter* lc);
+                             float scale, bf16* out /*[n][heads*64]*/, cudaStream_t s, LaunchCounter* lc, const int* tdev = nullptr);
+// tdev (optional, every decode-loop kernel below): the decode position lives in device memory, so that one captured CUDA
+// graph of a decode step can be replayed for every position; argmax_rows advances it
 cudaError_t vit_assemble(const bf16* patches, const bf16* cls, const bf16* pos, bf16* h, int n, int P, int D, cudaStream_t s,
                          LaunchCounter* lc);
 cudaError_t trocr_embed(const int* ids, int ids_ld, int t, const bf16* tok, const bf16* pos, bf16* x, int n, int D, float scale,
-                        cudaStream_t s, LaunchCounter* lc);
+                        cudaStream_t s, LaunchCounter* lc, const int* tdev = nullptr);
 cudaError_t kv_append(const bf16* qkv /*[n][3D]*/, bf16* cache /*[n][Lcap][2D]*/, int n, int t, int Lcap, int D, cudaStream_t s,
-                      LaunchCounter* lc);
+                      LaunchCounter* lc, const int* tdev = nullptr);
 cudaError_t argmax_rows(const float* logits, int n, int V, int ld, int* ids, int ids_ld, int t, int eos, int pad, int* finished,
-                        int* n_finished, cudaStream_t s, LaunchCounter* lc);
+                        int* n_finished, cudaStream_t s, LaunchCounter* lc, int* tdev = nullptr);
+cudaError_t advance_position(int* tdev, cudaStream_t s, LaunchCounter* lc);      // *tdev += 1, after a step's argmax
 // Linears of the decode loop (M <= 128 rows): every SM streams a slice of the weights (trocr.cu)
 bool skinny_gemm_supported(int M, int N, int K);
 cudaError_t skinny_gemm(const bf16* X, int ldx, const bf16* W, const float* bias, const bf16* res, int ldres, void* out, int ldo,

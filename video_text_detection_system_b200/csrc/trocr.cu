@@ -314,8 +314,9 @@ constexpr int AD_MAXL = 640;
 // [token][K | V] buffers; one thread per row with eight dependent 16-byte loads ran at 2 TB/s).
 __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k,
                                                                const bf16* __restrict__ v, int ldkv, int Lcap, int L, float scale,
-                                                               bf16* __restrict__ out, int D) {
+                                                               bf16* __restrict__ out, int D, const int* __restrict__ tdev) {
   __shared__ float sc[AD_MAXL];
+  if (tdev) L = *tdev + 1;                               // decode position on the device (graph replay): keys 0..t
   __shared__ float red[4];
   __shared__ float part[16][64];
   const int hd = blockIdx.x, n = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -398,8 +399,9 @@ __global__ void vit_assemble_kernel(const bf16* __restrict__ patches, const bf16
 }
 
 __global__ void trocr_embed_kernel(const int* __restrict__ ids, int ids_ld, int t, const bf16* __restrict__ tok, const bf16* __restrict__ pos,
-                                   bf16* __restrict__ x, int n, int D, float scale) {
+                                   bf16* __restrict__ x, int n, int D, float scale, const int* __restrict__ tdev) {
   const int b = blockIdx.x;
+  if (tdev) t = *tdev;
   const int id = ids[(size_t)b * ids_ld + t];
   const bf16x2* te = reinterpret_cast<const bf16x2*>(tok + (size_t)id * D);
   const bf16x2* pe = reinterpret_cast<const bf16x2*>(pos + (size_t)(t + 2) * D);        // TrOCRLearnedPositionalEmbedding: offset 2
@@ -410,19 +412,24 @@ __global__ void trocr_embed_kernel(const int* __restrict__ ids, int ids_ld, int 
   }
 }
 
-__global__ void kv_append_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ cache, int n, int t, int Lcap, int D) {
+__global__ void kv_append_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ cache, int n, int t, int Lcap, int D,
+                                 const int* __restrict__ tdev) {
   // qkv [n][3D] (q | k | v) -> cache [n][Lcap][2D] (k | v) at position t
   const int b = blockIdx.x;
+  if (tdev) t = *tdev;
   const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)b * 3 * D + D);
   uint4* dst = reinterpret_cast<uint4*>(cache + ((size_t)b * Lcap + t) * 2 * D);
   for (int i = threadIdx.x; i < 2 * D / 8; i += blockDim.x) dst[i] = src[i];
 }
 
+__global__ void advance_position_kernel(int* t) { *t += 1; }
+
 // greedy choice over [n][ld] fp32 logits (V valid classes); writes ids[b][t + 1]; finished sequences emit pad
 __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, int V, int ld, int* __restrict__ ids,
                                                            int ids_ld, int t, int eos, int pad, int* __restrict__ finished,
-                                                           int* __restrict__ n_finished) {
+                                                           int* __restrict__ n_finished, int* __restrict__ tdev) {
   __shared__ float bv[32];
+  if (tdev) t = *tdev;
   __shared__ int bi[32];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* row = logits + (size_t)b * ld;
@@ -569,10 +576,10 @@ cudaError_t attention_enc(const bf16* qkv, bf16* out, int n, int S, int heads, f
 }
 
 cudaError_t attention_decode(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldkv, int Lcap, int L, int n, int heads, float scale,
-                             bf16* out, cudaStream_t s, LaunchCounter* lc) {
+                             bf16* out, cudaStream_t s, LaunchCounter* lc, const int* tdev) {
   if (n <= 0) return cudaSuccess;
   if (L <= 0 || L > AD_MAXL) return cudaErrorInvalidValue;
-  attention_decode_kernel<<<dim3(heads, n), 128, 0, s>>>(q, ldq, k, v, ldkv, Lcap, L, scale, out, heads * 64);
+  attention_decode_kernel<<<dim3(heads, n), 128, 0, s>>>(q, ldq, k, v, ldkv, Lcap, L, scale, out, heads * 64, tdev);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
@@ -586,24 +593,30 @@ cudaError_t vit_assemble(const bf16* patches, const bf16* cls, const bf16* pos, 
 }
 
 cudaError_t trocr_embed(const int* ids, int ids_ld, int t, const bf16* tok, const bf16* pos, bf16* x, int n, int D, float scale,
-                        cudaStream_t s, LaunchCounter* lc) {
+                        cudaStream_t s, LaunchCounter* lc, const int* tdev) {
   if (n <= 0) return cudaSuccess;
-  trocr_embed_kernel<<<n, 256, 0, s>>>(ids, ids_ld, t, tok, pos, x, n, D, scale);
+  trocr_embed_kernel<<<n, 256, 0, s>>>(ids, ids_ld, t, tok, pos, x, n, D, scale, tdev);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
 
-cudaError_t kv_append(const bf16* qkv, bf16* cache, int n, int t, int Lcap, int D, cudaStream_t s, LaunchCounter* lc) {
+cudaError_t kv_append(const bf16* qkv, bf16* cache, int n, int t, int Lcap, int D, cudaStream_t s, LaunchCounter* lc, const int* tdev) {
   if (n <= 0) return cudaSuccess;
-  kv_append_kernel<<<n, 256, 0, s>>>(qkv, cache, n, t, Lcap, D);
+  kv_append_kernel<<<n, 256, 0, s>>>(qkv, cache, n, t, Lcap, D, tdev);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
 
 cudaError_t argmax_rows(const float* logits, int n, int V, int ld, int* ids, int ids_ld, int t, int eos, int pad, int* finished,
-                        int* n_finished, cudaStream_t s, LaunchCounter* lc) {
+                        int* n_finished, cudaStream_t s, LaunchCounter* lc, int* tdev) {
   if (n <= 0) return cudaSuccess;
-  argmax_rows_kernel<<<n, 1024, 0, s>>>(logits, V, ld, ids, ids_ld, t, eos, pad, finished, n_finished);
+  argmax_rows_kernel<<<n, 1024, 0, s>>>(logits, V, ld, ids, ids_ld, t, eos, pad, finished, n_finished, tdev);
+  if (lc) lc->n++;
+  return cudaGetLastError();
+}
+
+cudaError_t advance_position(int* tdev, cudaStream_t s, LaunchCounter* lc) {
+  advance_position_kernel<<<1, 1, 0, s>>>(tdev);
   if (lc) lc->n++;
   return cudaGetLastError();
 }
