@@ -35,6 +35,24 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
 }
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch for the decode loop's chain of small kernels: every kernel lets its successor start at once
+// (pdl_go) and waits for its predecessor's results only where it first needs them (pdl_wait) -- block scheduling, the prologue
+// and, in the skinny GEMM, the whole weight prefetch overlap the predecessor's tail.  A kernel launched without the attribute
+// (or after a non-kernel stream operation) finds both instructions to be no-ops.
+__device__ __forceinline__ void pdl_go() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- LayerNorm: one warp per row ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ y, long long rows, int C,
@@ -67,6 +85,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 __global__ void __launch_bounds__(256) layernorm_row_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, bf16* __restrict__ y, int C, float eps) {
   __shared__ float red[2][8];
+  pdl_go();
+  pdl_wait();
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
   const size_t row = blockIdx.x;
   const bool on = t * 8 < C;
@@ -131,6 +151,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const bf16* __restrict
   // the whole weight slice is requested at once (cp.async): 16-130 KB in flight per SM is what keeps HBM busy when every CTA
   // has only microseconds of work
   const int pitch = 2 * K + 64, chunks = K / 8;
+  pdl_go();
   for (int i = threadIdx.x; i < cols * chunks; i += 256) {
     const int r = i / chunks, ch = i % chunks;
     const int col = blockIdx.x * cols + r;
@@ -138,6 +159,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const bf16* __restrict
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(wsm + (size_t)r * pitch + ch * 16)), "l"(src) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  pdl_wait();                                            // the weights do not depend on the previous kernel; X, res and out do
   float acc[MT][4];
 #pragma unroll
   for (int i = 0; i < MT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
@@ -316,6 +338,8 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __res
                                                                const bf16* __restrict__ v, int ldkv, int Lcap, int L, float scale,
                                                                bf16* __restrict__ out, int D, const int* __restrict__ tdev) {
   __shared__ float sc[AD_MAXL];
+  pdl_go();
+  pdl_wait();
   if (tdev) L = *tdev + 1;                               // decode position on the device (graph replay): keys 0..t
   __shared__ float red[4];
   __shared__ float part[16][64];
@@ -400,6 +424,8 @@ __global__ void vit_assemble_kernel(const bf16* __restrict__ patches, const bf16
 
 __global__ void trocr_embed_kernel(const int* __restrict__ ids, int ids_ld, int t, const bf16* __restrict__ tok, const bf16* __restrict__ pos,
                                    bf16* __restrict__ x, int n, int D, float scale, const int* __restrict__ tdev) {
+  pdl_go();
+  pdl_wait();
   const int b = blockIdx.x;
   if (tdev) t = *tdev;
   const int id = ids[(size_t)b * ids_ld + t];
@@ -415,6 +441,8 @@ __global__ void trocr_embed_kernel(const int* __restrict__ ids, int ids_ld, int 
 __global__ void kv_append_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ cache, int n, int t, int Lcap, int D,
                                  const int* __restrict__ tdev) {
   // qkv [n][3D] (q | k | v) -> cache [n][Lcap][2D] (k | v) at position t
+  pdl_go();
+  pdl_wait();
   const int b = blockIdx.x;
   if (tdev) t = *tdev;
   const uint4* src = reinterpret_cast<const uint4*>(qkv + (size_t)b * 3 * D + D);
@@ -422,13 +450,15 @@ __global__ void kv_append_kernel(const bf16* __restrict__ qkv, bf16* __restrict_
   for (int i = threadIdx.x; i < 2 * D / 8; i += blockDim.x) dst[i] = src[i];
 }
 
-__global__ void advance_position_kernel(int* t) { *t += 1; }
+__global__ void advance_position_kernel(int* t) { pdl_go(); pdl_wait(); *t += 1; }
 
 // greedy choice over [n][ld] fp32 logits (V valid classes); writes ids[b][t + 1]; finished sequences emit pad
 __global__ void __launch_bounds__(1024) argmax_rows_kernel(const float* __restrict__ logits, int V, int ld, int* __restrict__ ids,
                                                            int ids_ld, int t, int eos, int pad, int* __restrict__ finished,
                                                            int* __restrict__ n_finished, int* __restrict__ tdev) {
   __shared__ float bv[32];
+  pdl_go();
+  pdl_wait();
   if (tdev) t = *tdev;
   __shared__ int bi[32];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -533,7 +563,8 @@ cudaError_t layernorm_rows(const bf16* x, const float* gamma, const float* beta,
   if (C & 1) return cudaErrorInvalidValue;
   if (rows <= 512 && C % 8 == 0 && C <= 2048) {           // decode loop: a CTA per row
     const int threads = ((C / 8 + 31) / 32) * 32;
-    layernorm_row_kernel<<<(unsigned)rows, threads, 0, s>>>(x, gamma, beta, y, C, eps);
+    cudaError_t e = launch_pdl(layernorm_row_kernel, dim3((unsigned)rows), dim3(threads), 0, s, x, gamma, beta, y, C, eps);
+    if (e != cudaSuccess) return e;
   } else {
     layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, gamma, beta, y, rows, C, eps);
   }
@@ -561,11 +592,12 @@ cudaError_t skinny_gemm(const bf16* X, int ldx, const bf16* W, const float* bias
   });
   if (ae != cudaSuccess) return ae;
   const unsigned grid = (unsigned)((N + 8 * WN - 1) / (8 * WN));
-  if (M <= 32) skinny_gemm_kernel<2><<<grid, 256, smem, s>>>(X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
-  else if (M <= 64) skinny_gemm_kernel<4><<<grid, 256, smem, s>>>(X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
-  else skinny_gemm_kernel<8><<<grid, 256, smem, s>>>(X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
+  cudaError_t le;
+  if (M <= 32) le = launch_pdl(skinny_gemm_kernel<2>, dim3(grid), dim3(256), smem, s, X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
+  else if (M <= 64) le = launch_pdl(skinny_gemm_kernel<4>, dim3(grid), dim3(256), smem, s, X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
+  else le = launch_pdl(skinny_gemm_kernel<8>, dim3(grid), dim3(256), smem, s, X, ldx, W, bias, res, ldres, out, ldo, out_f32, M, N, K, act, WN);
   if (lc) lc->n++;
-  return cudaGetLastError();
+  return le;
 }
 
 cudaError_t attention_enc(const bf16* qkv, bf16* out, int n, int S, int heads, float scale, cudaStream_t s, LaunchCounter* lc) {
@@ -579,9 +611,9 @@ cudaError_t attention_decode(const bf16* q, int ldq, const bf16* k, const bf16* 
                              bf16* out, cudaStream_t s, LaunchCounter* lc, const int* tdev) {
   if (n <= 0) return cudaSuccess;
   if (L <= 0 || L > AD_MAXL) return cudaErrorInvalidValue;
-  attention_decode_kernel<<<dim3(heads, n), 128, 0, s>>>(q, ldq, k, v, ldkv, Lcap, L, scale, out, heads * 64, tdev);
+  cudaError_t e = launch_pdl(attention_decode_kernel, dim3(heads, n), dim3(128), 0, s, q, ldq, k, v, ldkv, Lcap, L, scale, out, heads * 64, tdev);
   if (lc) lc->n++;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t vit_assemble(const bf16* patches, const bf16* cls, const bf16* pos, bf16* h, int n, int P, int D, cudaStream_t s,
@@ -595,30 +627,30 @@ cudaError_t vit_assemble(const bf16* patches, const bf16* cls, const bf16* pos, 
 cudaError_t trocr_embed(const int* ids, int ids_ld, int t, const bf16* tok, const bf16* pos, bf16* x, int n, int D, float scale,
                         cudaStream_t s, LaunchCounter* lc, const int* tdev) {
   if (n <= 0) return cudaSuccess;
-  trocr_embed_kernel<<<n, 256, 0, s>>>(ids, ids_ld, t, tok, pos, x, n, D, scale, tdev);
+  cudaError_t e = launch_pdl(trocr_embed_kernel, dim3(n), dim3(256), 0, s, ids, ids_ld, t, tok, pos, x, n, D, scale, tdev);
   if (lc) lc->n++;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t kv_append(const bf16* qkv, bf16* cache, int n, int t, int Lcap, int D, cudaStream_t s, LaunchCounter* lc, const int* tdev) {
   if (n <= 0) return cudaSuccess;
-  kv_append_kernel<<<n, 256, 0, s>>>(qkv, cache, n, t, Lcap, D, tdev);
+  cudaError_t e = launch_pdl(kv_append_kernel, dim3(n), dim3(256), 0, s, qkv, cache, n, t, Lcap, D, tdev);
   if (lc) lc->n++;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t argmax_rows(const float* logits, int n, int V, int ld, int* ids, int ids_ld, int t, int eos, int pad, int* finished,
                         int* n_finished, cudaStream_t s, LaunchCounter* lc, int* tdev) {
   if (n <= 0) return cudaSuccess;
-  argmax_rows_kernel<<<n, 1024, 0, s>>>(logits, V, ld, ids, ids_ld, t, eos, pad, finished, n_finished, tdev);
+  cudaError_t e = launch_pdl(argmax_rows_kernel, dim3(n), dim3(1024), 0, s, logits, V, ld, ids, ids_ld, t, eos, pad, finished, n_finished, tdev);
   if (lc) lc->n++;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t advance_position(int* tdev, cudaStream_t s, LaunchCounter* lc) {
-  advance_position_kernel<<<1, 1, 0, s>>>(tdev);
+  cudaError_t e = launch_pdl(advance_position_kernel, dim3(1), dim3(1), 0, s, tdev);
   if (lc) lc->n++;
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t trocr_resize_patches(const uint8_t* const* crops_dev, const void* meta_dev, const int* tab_dev, uint8_t* tmp, bf16* patches,
