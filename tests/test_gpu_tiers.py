@@ -353,6 +353,37 @@ def test_no_kernel_writes_outside_its_buffers(E, port, bb, dtype, h, w, sh, sw, 
     eng.close()
 
 
+def test_trocr_and_overlay_kernels_write_inside_their_buffers(E):
+    """The same canary evidence for the transformer recogniser (skinny GEMMs, decode attention, KV cache, the captured
+    decode-step graph, partial chunks) and for the overlay (items, glyph blits clipped at the frame border)."""
+    from video_text_detection_system_b200 import synthetic
+    from video_text_detection_system_b200.sinks import overlay_items
+    model = synthetic.random_trocr_model("small", seed=0)
+    eng = E.Engine(dtype="fp16", det_h=32, det_w=32, max_batch=3, max_boxes=64, max_src_h=120, max_src_w=200, guard_allocs=True)
+    eng.load_trocr(model.state_dict(), crops_per_chunk=4)
+    rng = np.random.default_rng(0)
+    crops = [rng.integers(0, 256, (int(rng.integers(8, 40)), int(rng.integers(16, 120)), 3), dtype=np.uint8) for _ in range(7)]
+    ids, lens = eng.trocr_generate_crops(crops, 20)            # 4 + 3 crops: two chunk sizes, two graphs
+    assert ids.shape == (7, 20) and eng.check_guards() == 0
+    ids2, _ = eng.trocr_generate_crops(crops[:1], 6)
+    assert np.array_equal(ids2[0, :6][ids2[0, :6] != ids2[0, -1]], ids[0, :6][ids2[0, :6] != ids2[0, -1]]) and eng.check_guards() == 0
+    # 70 crops in one chunk: the 128-row variant of the skinny GEMM; row results do not depend on the variant
+    big = E.Engine(dtype="fp16", det_h=32, det_w=32, max_batch=1, max_boxes=64, max_src_h=32, max_src_w=32, guard_allocs=True)
+    big.load_trocr(model.state_dict(), crops_per_chunk=96)
+    many = [crops[i % 7] for i in range(70)]
+    ids70, _ = big.trocr_generate_crops(many, 20)
+    assert big.check_guards() == 0
+    for i in range(70):
+        assert np.array_equal(ids70[i], ids[i % 7]), i
+    big.close()
+    frames = [rng.integers(0, 256, (120, 200, 3), dtype=np.uint8) for _ in range(3)]
+    dets = [[{"bbox": [int(rng.integers(-30, 190)), int(rng.integers(-10, 130)), int(rng.integers(0, 230)), int(rng.integers(0, 150))],
+              "text": "border %d" % i, "detection_confidence": 0.5} for i in range(40)] for _ in range(3)]
+    eng.draw_detections(frames, overlay_items(dets))
+    assert eng.check_guards() == 0
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------- two devices, one process
 def test_contexts_on_two_devices_in_one_process(E, port):
     """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a second context on another GPU must get its own

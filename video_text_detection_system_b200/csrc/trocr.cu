@@ -572,7 +572,7 @@ cudaError_t layernorm_rows(const bf16* x, const float* gamma, const float* beta,
   return cudaGetLastError();
 }
 
-bool skinny_gemm_supported(int M, int N, int K) { return M >= 1 && M <= 128 && K % 256 == 0 && N >= 8; }
+bool skinny_gemm_supported(int M, int N, int K) { return M >= 1 && M <= 128 && K >= 32 && K % 32 == 0 && N >= 8; }
 
 cudaError_t skinny_gemm(const bf16* X, int ldx, const bf16* W, const float* bias, const bf16* res, int ldres, void* out, int ldo,
                         int out_f32, int M, int N, int K, int act, cudaStream_t s, LaunchCounter* lc) {
@@ -580,6 +580,7 @@ cudaError_t skinny_gemm(const bf16* X, int ldx, const bf16* W, const float* bias
   if (!skinny_gemm_supported(M, N, K)) return cudaErrorInvalidValue;
   int WN = 1;
   while (WN < 8 && (N + 8 * WN - 1) / (8 * WN) > 320) WN *= 2;     // enough CTAs for every SM, K slices of at least 256 / WN
+  while (WN < 8 && K % (32 * (8 / WN)) != 0) WN *= 2;              // a K slice is whole 32-wide blocks
   while (WN > 1 && (size_t)8 * WN * (2 * K + 64) > 160 * 1024) WN /= 2;
   const size_t smem = (size_t)8 * WN * (2 * K + 64);
   if (smem > 160 * 1024) return cudaErrorInvalidValue;
