@@ -865,7 +865,7 @@ void trocr_free(vtd_ctx* c) {
   kill(t->patch_op); kill(t->lm);
   for (auto& e : t->el) { kill(e.qkv); kill(e.proj); kill(e.fc1); kill(e.fc2); }
   for (auto& d : t->dl) { kill(d.qkv); kill(d.so); kill(d.cq); kill(d.co); kill(d.fc1); kill(d.fc2); kill(d.ckv); }
-  if (t->step_exec) cudaGraphExecDestroy(t->step_exec);
+  for (auto& kv : t->step_graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
   if (t->pinned) cudaFreeHost(t->pinned);
   if (t->crop_store) cudaFree(t->crop_store);
   if (t->tmp) cudaFree(t->tmp);

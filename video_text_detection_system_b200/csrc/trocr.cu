@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __res
   const bf16* kb = k + (size_t)n * Lcap * ldkv + hd * 64 + sub * 8;
   const bf16* vb = v + (size_t)n * Lcap * ldkv + hd * 64 + sub * 8;
   float mx = -INFINITY;
-#pragma unroll 4
+#pragma unroll 8
   for (int j0 = 0; j0 < L; j0 += 16) {                  // uniform trip count: the shuffles below need the whole warp
     const int j = j0 + grp;
     float acc = 0.f;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __res
   sum = red[0] + red[1] + red[2] + red[3];
   // out[d] = sum_j p[j] v[j][d]: row group grp walks every sixteenth key, 8 dimensions per lane
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
   for (int j = grp; j < L; j += 16) {
     const uint4 u = *reinterpret_cast<const uint4*>(vb + (size_t)j * ldkv);
     const bf16x2* h = reinterpret_cast<const bf16x2*>(&u);
