@@ -5,6 +5,7 @@
 // of conv / pool launches with every pointer, shape and tensor map bound when the weights are loaded, so
 // a batch is a fixed sequence of launches with no allocation, no shape logic and no host<->device sync
 // except the one that returns the per-frame box counts before the recogniser is sized.
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 #include "resize_tab.h"
 #include "../../include/vtd.h"
@@ -328,9 +329,19 @@ void stage_harvest(StageProf& sp) {
   if (sp.pending && cudaEventElapsedTime(&ms, sp.ev0, sp.ev1) == cudaSuccess) { sp.ms += ms; sp.n++; }
   sp.pending = false;
 }
+// NVTX ranges (header-only NVTX v3; no-ops unless a tool is attached): one per API call and per stage of the path, so a
+// timeline shows preprocess / detector / boxes / crop / crnn / lstm / ctc per batch and context
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+static const char* const kStageNames[] = {"vtd.preprocess", "vtd.head_tail", "vtd.boxes", "vtd.crop", "vtd.lstm0", "vtd.lstm1", "vtd.ctc"};
+
 struct StageTimer {                      // brackets a stage with CUDA events on the launching stream when profiling is on
-  vtd_ctx* c; StageProf* sp;
-  StageTimer(vtd_ctx* ctx, int id) : c(ctx), sp(ctx->profiling ? &ctx->stage_prof[id] : nullptr) {
+  vtd_ctx* c; StageProf* sp; NvtxRange range;
+  StageTimer(vtd_ctx* ctx, int id) : c(ctx), sp(ctx->profiling ? &ctx->stage_prof[id] : nullptr), range(kStageNames[id]) {
     if (!sp) return;
     if (!sp->ev0) { cudaEventCreate(&sp->ev0); cudaEventCreate(&sp->ev1); }
     if (sp->pending) { cudaEventSynchronize(sp->ev1); stage_harvest(*sp); }
@@ -673,6 +684,7 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
 
 // crops [0,nc) already in c->crops -> logits in c->logits
 int run_crnn(vtd_ctx* c, int nc) {
+  NvtxRange range("vtd.crnn");
   int r = run_prog(c, c->rec_prog, nc); if (r) return r;
   for (int l = 0; l < 2; ++l) {
     // the second layer's xproj reuses its own buffer (allocated by add_conv)
@@ -698,6 +710,7 @@ int run_crnn(vtd_ctx* c, int nc) {
 
 int detect_maps_locked(vtd_ctx* c, int n, float thr, const float* logit_bias) {
   c->cur_thr = thr; c->cur_bias = logit_bias;
+  NvtxRange range("vtd.detector");
   int r = run_prog(c, c->det_prog, n); if (r) return r;
   if (c->head_fused) return VTD_OK;       // the last op of the program was the whole head
   const int dh = c->cfg.det_h, dw = c->cfg.det_w;
@@ -1433,6 +1446,7 @@ int vtd_run_batch(vtd_ctx* c, const uint8_t* const* frames, int n, int h, int w,
                   float thr, const float* logit_bias, int recognize, vtd_record* rh, int* ch) {
   if (!c || !frames) return VTD_ERR_ARG;
   Guard g(c);
+  NvtxRange range("vtd_run_batch");
   if (!c->det_loaded) FAIL(VTD_ERR_STATE, "vtd_load_detector has not been called");
   if (recognize && !c->rec_loaded) FAIL(VTD_ERR_STATE, "vtd_load_recognizer has not been called");
   int r = preprocess_locked(c, frames, n, h, w, pitch, pixfmt, on_dev); if (r) return r;
