@@ -59,8 +59,79 @@ def tables():
     return widths, int(th), int(base), cells
 
 
+SIDES = ("top", "bottom", "left", "right")
+
+
+def _bits(mask, x0, y0):
+    """CELL_H rows of CELL_W bits of a boolean image, cell origin (x0, y0); pixels outside the image read 0."""
+    h, w = mask.shape
+    out = np.zeros(CELL_H, np.uint16)
+    weights = (1 << np.arange(CELL_W)).astype(np.uint32)
+    for r in range(CELL_H):
+        y = y0 + r
+        if 0 <= y < h:
+            xs = np.arange(x0, x0 + CELL_W)
+            ok = (xs >= 0) & (xs < w)
+            row = np.zeros(CELL_W, bool)
+            row[ok] = mask[y, xs[ok]]
+            out[r] = int((row * weights).sum())
+    return out
+
+
+def clip_patches(widths, cells):
+    """Where a glyph stroke crosses the frame border OpenCV clips the segment (clipLine, 16.16 fixed point) before it rasterises
+    it, so the pixels that remain can differ from the unclipped glyph's.  For every glyph, phase, border and number k of cell
+    rows / columns beyond that border (1..16) the clipped glyph is rendered by OpenCV and kept when it differs from the cropped
+    cell: key = (((c - 32) * 2 + phase) * 4 + side) * 17 + k.  The result does not depend on where along the border the glyph
+    sits nor on the frame size (checked here on a second frame size)."""
+    import cv2
+    font = cv2.FONT_HERSHEY_SIMPLEX
+    odd = next(c for c in range(FIRST, LAST + 1) if widths[c - FIRST] % 2)
+    prefix = chr(odd) + " "
+    shift2 = widths[odd - FIRST] + widths[0]
+
+    def clipped(c, ph, h, w, penx, oy):
+        im = np.full((h, w), 255, np.uint8)
+        if ph == 0:
+            cv2.putText(im, chr(c), (penx, oy), font, 0.5, 0, 1)
+            return _bits(im == 0, penx, oy + ROW0)
+        ox = penx - shift2 // 2
+        cv2.putText(im, prefix + chr(c), (ox, oy), font, 0.5, 0, 1)
+        pre = np.full((h, w), 255, np.uint8)
+        cv2.putText(pre, prefix, (ox, oy), font, 0.5, 0, 1)
+        return _bits((im == 0) & ~(pre == 0), penx, oy + ROW0)
+
+    def cropped(c, ph, h, w, penx, oy):
+        out = np.zeros(CELL_H, np.uint16)
+        for r in range(CELL_H):
+            y = oy + ROW0 + r
+            if 0 <= y < h:
+                keep = 0
+                for b in range(CELL_W):
+                    if 0 <= penx + b < w and (int(cells[c - FIRST, ph, r]) >> b) & 1:
+                        keep |= 1 << b
+                out[r] = keep
+        return out
+
+    keys, rows = [], []
+    for c in range(FIRST, LAST + 1):
+        for ph in range(2):
+            for side in range(4):
+                for k in range(1, CELL_W + 1 if side >= 2 else CELL_H):
+                    got = []
+                    for (h, w, along) in ((80, 120, 40), (57, 203, 23)):
+                        px, oy = ((along, -ROW0 - k), (along, h - 1 - (CELL_H - 1 + ROW0) + k), (-k, along), (w - CELL_W + k, along))[side]
+                        got.append((clipped(c, ph, h, w, px, oy), cropped(c, ph, h, w, px, oy)))
+                    assert np.array_equal(got[0][0], got[1][0]), (chr(c), ph, SIDES[side], k)
+                    if not np.array_equal(got[0][0], got[0][1]):
+                        keys.append((((c - FIRST) * 2 + ph) * 4 + side) * 17 + k)
+                        rows.append(got[0][0])
+    return keys, rows
+
+
 def header_text() -> str:
     widths, th, base, cells = tables()
+    pkeys, prows = clip_patches(widths, cells)
     out = ["// GENERATED by gen_overlay_atlas.py from OpenCV's own rendering of FONT_HERSHEY_SIMPLEX at scale 0.5, thickness 1 -- do not edit.",
            "// cells[c - 32][phase][row]: bit b = pixel (floor(pen) + b, baseline - 12 + row); phase = pen at x.0 / x.5.",
            "#pragma once", "#include <cstdint>", "namespace vtd {",
@@ -72,6 +143,14 @@ def header_text() -> str:
         rows = ["{%s}" % ", ".join("0x%04x" % v for v in cells[i, ph]) for ph in range(2)]
         ch = chr(FIRST + i)
         out.append("  {%s,\n   %s},  // %s" % (rows[0], rows[1], "backslash" if ch == "\\" else repr(ch)))
+    out += ["};",
+            "// glyphs clipped by ONE frame border whose remaining pixels differ from the cropped cell (see gen_overlay_atlas.py clip_patches):",
+            "// OV_PATCH_KEYS sorted; key = (((c - 32) * 2 + phase) * 4 + side) * 17 + k, side 0 top 1 bottom 2 left 3 right, k = cell rows / columns beyond it",
+            "constexpr int OV_PATCHES = %d;" % len(pkeys),
+            "static const uint32_t OV_PATCH_KEYS[%d] = {%s};" % (len(pkeys), ", ".join(str(k) for k in pkeys)),
+            "static const uint16_t OV_PATCH_CELLS[%d][%d] = {" % (len(pkeys), CELL_H)]
+    for r in prows:
+        out.append("  {%s}," % ", ".join("0x%04x" % int(v) for v in r))
     out += ["};", "}  // namespace vtd", ""]
     return "\n".join(out)
 

@@ -19,9 +19,11 @@
 //   * text = glyph cells from overlay_atlas.h (rendered by OpenCV itself, one cell per byte and sub-pixel pen phase), pen
 //     advancing OV_WIDTHS[c] half-pixels per glyph; bytes outside 32..126 draw '?' (putText's readCheck);
 //   * getTextSize: tw = rint(sum of widths / 2 + 1) (cvRound = round-half-even), th = OV_TEXT_H.
-// One known difference, measured in tests/test_gpu_overlay.py: where a glyph STROKE crosses the frame border OpenCV clips the
-// segment in 16.16 fixed point before rasterising it, which can move one or two of the stroke's remaining pixels; cells are
-// cropped instead.  Labels inside the frame are identical.
+//   * a glyph cut by ONE frame border: OpenCV clips a stroke that crosses the border in 16.16 fixed point before rasterising
+//     it, which can move one or two of the stroke's remaining pixels; overlay_atlas.h holds the 1 161 (glyph, phase, border,
+//     distance) cells where that happens, found by key (binary search), all others are the plain cell cropped.
+// One known difference is left, measured in tests/test_gpu_overlay.py: a glyph cut by TWO borders at once (a label in a frame
+// corner) is cropped from the plain cell.
 #include "common.cuh"
 #include "overlay_atlas.h"
 
@@ -33,6 +35,29 @@ struct OvConst {
   uint8_t widths[OV_LAST - OV_FIRST + 1];
 };
 __constant__ OvConst ov_tab;
+__device__ uint32_t ov_patch_keys[OV_PATCHES];
+__device__ uint16_t ov_patch_cells[OV_PATCHES][OV_CELL_H];
+
+// the cell row of glyph g at pen phase ph, row `row`, when the cell's top-left pixel is (px, ty0) in an h x w frame
+__device__ uint32_t glyph_row(int g, int ph, int row, int px, int ty0, int h, int w) {
+  const int kt = ty0 < 0 ? -ty0 : 0, kb = ty0 + OV_CELL_H - 1 > h - 1 ? ty0 + OV_CELL_H - h : 0;
+  const int kl = px < 0 ? -px : 0, kr = px + OV_CELL_W - 1 > w - 1 ? px + OV_CELL_W - w : 0;
+  const int sides = (kt > 0) + (kb > 0) + (kl > 0) + (kr > 0);
+  if (sides == 1) {
+    const int side = kt ? 0 : (kb ? 1 : (kl ? 2 : 3)), k = kt + kb + kl + kr;
+    if (k <= 16) {
+      const uint32_t key = (uint32_t)(((g * 2 + ph) * 4 + side) * 17 + k);
+      int lo = 0, hi = OV_PATCHES - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const uint32_t km = ov_patch_keys[mid];
+        if (km == key) return ov_patch_cells[mid][row];
+        if (km < key) lo = mid + 1; else hi = mid - 1;
+      }
+    }
+  }
+  return ov_tab.cells[g][ph][row];
+}
 
 struct Foot {            // inclusive pixel ranges, unclipped
   int ax, ay, bx, by;    // rectangle corners, ordered
@@ -62,24 +87,28 @@ __device__ __forceinline__ int label_width(const OverlayItem& it) {
 }
 
 // pens: half-pixel pen position before glyph k (prefix sums), or nullptr to accumulate on the fly
-__device__ bool text_covers(const OverlayItem& it, const Foot& f, const int* pens, int x, int y) {
+__device__ bool text_covers(const OverlayItem& it, const Foot& f, const int* pens, int x, int y, int h, int w) {
   if (x < f.tx0 || x > f.tx1 || y < f.ty0 || y > f.ty1) return false;
   const int row = y - f.ty0;
+  const bool inside = f.ty0 >= 0 && f.ty1 < h && f.tx0 >= 0 && f.tx1 < w;       // the whole label: no glyph is cut
   int pen2 = 2 * it.bbox[0];
   for (int k = 0; k < it.label_len; ++k) {
     const int g = glyph_of(it.label[k]);
     if (pens) pen2 = pens[k];
     const int b = x - (pen2 >> 1);
-    if (b >= 0 && b < OV_CELL_W && ((ov_tab.cells[g][pen2 & 1][row] >> b) & 1)) return true;
+    if (b >= 0 && b < OV_CELL_W) {
+      const uint32_t bits = inside ? ov_tab.cells[g][pen2 & 1][row] : glyph_row(g, pen2 & 1, row, pen2 >> 1, f.ty0, h, w);
+      if ((bits >> b) & 1) return true;
+    }
     if (!pens) pen2 += ov_tab.widths[g];
   }
   return false;
 }
 
 // 0 = untouched, 1 = green, 2 = black: the last of the detection's three primitives that covers (x, y)
-__device__ int item_covers(const OverlayItem& it, const Foot& f, const int* pens, int x, int y) {
+__device__ int item_covers(const OverlayItem& it, const Foot& f, const int* pens, int x, int y, int h, int w) {
   if (x < f.x0 || x > f.x1 || y < f.y0 || y > f.y1) return 0;
-  if (text_covers(it, f, pens, x, y)) return 2;
+  if (text_covers(it, f, pens, x, y, h, w)) return 2;
   if (x >= f.px0 && x <= f.px1 && y >= f.py0 && y <= f.py1) return 1;
   if (x >= f.ax - 1 && x <= f.bx + 1 && y >= f.ay - 1 && y <= f.by + 1) {
     const bool band = x <= f.ax + 1 || x >= f.bx - 1 || y <= f.ay + 1 || y >= f.by - 1;
@@ -138,13 +167,13 @@ __global__ void __launch_bounds__(OV_THREADS) overlay_kernel(uint8_t* const* __r
     const long long area = (long long)rw * (ry1 - ry0 + 1);
     for (long long q = threadIdx.x; q < area; q += OV_THREADS) {
       const int x = rx0 + (int)(q % rw), y = ry0 + (int)(q / rw);
-      int colour = item_covers(it, me, pens, x, y), best = colour ? i : -1;
+      int colour = item_covers(it, me, pens, x, y, h, w), best = colour ? i : -1;
       for (int s = 0; s < nl; ++s) {
         const int j = later[s];
         if (j < best) continue;
         Foot fj;
         if (s < 8) fj = later_foot[s]; else fj = footprint(items[j], label_width(items[j]));
-        const int cj = item_covers(items[j], fj, nullptr, x, y);
+        const int cj = item_covers(items[j], fj, nullptr, x, y, h, w);
         if (cj) { colour = cj; best = j; }
       }
       if (colour) {
@@ -161,7 +190,10 @@ cudaError_t overlay_upload_tables(cudaStream_t s) {
   static OvConst host;
   memcpy(host.cells, OV_CELLS, sizeof(host.cells));
   memcpy(host.widths, OV_WIDTHS, sizeof(host.widths));
-  return cudaMemcpyToSymbolAsync(ov_tab, &host, sizeof(host), 0, cudaMemcpyHostToDevice, s);
+  cudaError_t e = cudaMemcpyToSymbolAsync(ov_tab, &host, sizeof(host), 0, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(ov_patch_keys, OV_PATCH_KEYS, sizeof(OV_PATCH_KEYS), 0, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(ov_patch_cells, OV_PATCH_CELLS, sizeof(OV_PATCH_CELLS), 0, cudaMemcpyHostToDevice, s);
+  return e;
 }
 
 cudaError_t draw_overlay(uint8_t* const* frames, int h, int w, int pitch, const OverlayItem* items, const int* frame_end,
