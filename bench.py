@@ -573,6 +573,13 @@ def main():
         except Exception as ex:
             print("e2e_api unavailable: %r" % (ex,), file=sys.stderr)
 
+    # ---- the sink after the path: annotated frames drawn on the device (row N3), frames resident, one call per batch
+    if not args.no_extras and world == 1:
+        try:
+            extras["overlay"] = overlay_leg(_lib, engines[0], recs0, counts, dev_pool, B, SRC_H, SRC_W)
+        except Exception as ex:
+            print("overlay leg unavailable: %r" % (ex,), file=sys.stderr)
+
     if (args.trocr or args.config == 5) and world == 1 and not args.no_extras:
         try:
             extras["trocr"] = trocr_leg(args, _lib, synthetic, local_rank, recs0, counts, host_pool, B)
@@ -668,6 +675,29 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def overlay_leg(_lib, eng, recs0, counts, dev_pool, B, h, w):
+    """ProcessingService._draw_detections (processing_service.py:188-218) for a whole batch through vtd_draw_detections: the
+    boxes of the last batch with a label each, drawn into B resident BGR frames (a copy of the pool's first B); wall clock around
+    the C-ABI call (it uploads the draw list and synchronises)."""
+    import torch
+    from video_text_detection_system_b200.sinks import overlay_items
+    recs = recs0[0].reshape(B, KMAX, 128).view(_lib.RECORD_DTYPE).reshape(B, KMAX)
+    dets = [[{"bbox": [int(v) for v in recs[i][j]["bbox"]], "text": "text%02d" % j, "detection_confidence": float(recs[i][j]["det_conf"])}
+             for j in range(int(counts[i]))] for i in range(B)]
+    items = overlay_items(dets)
+    frames = dev_pool[:B].clone()
+    ptrs = [frames[i].data_ptr() for i in range(B)]
+    torch.cuda.synchronize()
+    eng.draw_detections(ptrs, items, on_device=True, h=h, w=w, pitch=w * 3)          # warm-up (uploads the glyph tables)
+    reps = 10
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        eng.draw_detections(ptrs, items, on_device=True, h=h, w=w, pitch=w * 3)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": B / dt, "unit": "frames/s", "ms_per_batch": dt * 1e3, "detections": int(len(items)),
+            "call": "vtd_draw_detections on %d resident %dx%d BGR frames, %d labelled boxes" % (B, h, w, len(items))}
 
 
 def trocr_leg(args, _lib, synthetic, device, recs0, counts, host_pool, B):
