@@ -706,7 +706,7 @@ def trocr_leg(args, _lib, synthetic, device, recs0, counts, host_pool, B):
     on the crops the detector found in the first frames of the last batch (host BGR crops -> vtd_trocr_generate_crops: H2D,
     device-side 384x384 processor resize, ViT encoder, 49 decoder steps, ids back).  Wall clock around the C-ABI call."""
     model = synthetic.random_trocr_model("base", seed=0)
-    chunk = 64
+    chunk = 128                                                   # crops per chunk (one decode loop serves them all)
     eng = _lib.Engine(device=device, dtype=args.dtype if args.dtype != "fp32" else "fp16", det_h=32, det_w=32, max_batch=1, max_boxes=64,
                       max_src_h=32, max_src_w=32)
     eng.load_trocr(model.state_dict(), crops_per_chunk=chunk)

@@ -28,7 +28,7 @@ logger = logging.getLogger(__name__)
 
 class TransformerRecognizer:
     def __init__(self, model_name: str = "microsoft/trocr-base-printed", dtype: Optional[str] = None, *, state_dict=None,
-                 decode: Optional[Callable[[List[int]], str]] = None, crops_per_chunk: int = 32, max_length: int = 50,
+                 decode: Optional[Callable[[List[int]], str]] = None, crops_per_chunk: int = 64, max_length: int = 50,
                  device: int = 0):
         self.device = "cuda"
         self.max_length = int(max_length)
