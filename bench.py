@@ -723,7 +723,7 @@ def trocr_leg(args, _lib, synthetic, device, recs0, counts, host_pool, B):
     crops = crops[:2 * chunk]
     if not crops:
         raise RuntimeError("no crops to recognise")
-    eng.trocr_generate_crops(crops[:8], 50)                       # warm-up
+    eng.trocr_generate_crops(crops, 50)                           # warm-up with the timed chunk sizes (one decode-step graph per size)
     t0 = time.perf_counter()
     ids, lens = eng.trocr_generate_crops(crops, 50)
     dt = time.perf_counter() - t0
