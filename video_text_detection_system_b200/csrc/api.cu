@@ -3,8 +3,9 @@
 // The host runtime is deliberately small: a context owns one stream, one device arena laid out at
 // vtd_create for the configured maximum batch, and two "programs" (detector, recogniser) -- flat lists
 // of conv / pool launches with every pointer, shape and tensor map bound when the weights are loaded, so
-// a batch is a fixed sequence of launches with no allocation, no shape logic and no host<->device sync
-// except the one that returns the per-frame box counts before the recogniser is sized.
+// a batch is a fixed sequence of launches with no allocation, no shape logic and no host<->device sync: in the
+// speed tier even the recogniser is launched against the crop count in device memory (recognize_locked); the
+// host looks at the count where it synchronises anyway and only then runs chunks beyond the first.
 #include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 #include "resize_tab.h"
@@ -106,6 +107,12 @@ struct vtd_ctx {
   const uint8_t** frame_ptrs_pinned = nullptr;
   cudaEvent_t ptrs_event = nullptr;
   OverlayItem* ov_items = nullptr; int* ov_end = nullptr; bool ov_tables = false;   // annotated-frame overlay (lazy)
+  // speed tier: the recogniser's first chunk is launched against the crop count ON THE DEVICE (no host round trip in the step);
+  // the host reads the total later, where it synchronises anyway, and only then runs the chunks beyond the first (rare)
+  bool rec_dyn_ok = false;                     // every recogniser launch can take the device-side count
+  const int* n_dyn = nullptr; int n_first = 0; // set while such a chunk is being launched (run_op passes them on)
+  cudaEvent_t total_event = nullptr;           // the crop total has reached pinned_int[0]
+  bool rec_pending = false; int pending_n = 0; // a batch whose total has not been looked at yet
   int cur_h = 0, cur_w = 0, cur_pitch = 0, cur_n = 0, cur_pix = 0;
   ResizeTab tx, ty; int tab_h = -1, tab_w = -1;
   float* norm_lut = nullptr;            // [3][256] u8 -> normalised fp32
@@ -306,9 +313,9 @@ cudaError_t run_op(vtd_ctx* c, const Op& op, int n) {
     return maxpool_nhwc<float>((const float*)op.pin, (float*)op.pout, n, op.H, op.W, op.C, op.kh, op.kw, op.sh, op.sw,
                                op.ph, op.pw, c->stream, &c->lc);
   }
-  if (op.sp) return stem_pool_tcgen05(op.sp, n, c->stream, &c->lc);
+  if (op.sp) return stem_pool_tcgen05(op.sp, n, c->stream, &c->lc, c->n_dyn, c->n_first);
   if (op.fused_head) return dbhead_fused_tcgen05(op.plan, n, c->cur_thr, c->cur_bias, c->stream, &c->lc);
-  if (op.plan) return conv_tcgen05(op.plan, n, c->stream, &c->lc);
+  if (op.plan) return conv_tcgen05(op.plan, n, c->stream, &c->lc, c->n_dyn, c->n_first);
   ConvDesc d = op.d;
   d.N = n;
   if (c->bf16_mode) return conv_generic<bf16>(d, c->stream, &c->lc);
@@ -679,6 +686,10 @@ int build_recognizer(vtd_ctx* c, const SD& sd) {
   if ((r = add_conv(c, nullptr, fc, B, in, 1, 0, false, nullptr, RES_NONE, true, &lo, &c->fc_op))) return r;
   c->logits = (float*)lo.p;
   c->dbg["logits"] = DebugEntry{lo.p, 97, 1, c->T, dense_layout(1, c->T, c->logits_ld), true, true};
+  // every launch of the recogniser on the tcgen05 / persistent-LSTM kernels: they take the crop count from device memory
+  bool dyn = c->bf16_mode && c->use_tclstm && c->use_plstm && c->xproj_op[0].plan && c->xproj_op[1].plan && c->fc_op.plan;
+  for (const Op& o : c->rec_prog) dyn = dyn && o.kind == Op::CONV && (o.plan || o.sp);
+  c->rec_dyn_ok = dyn;
   return VTD_OK;
 }
 
@@ -692,7 +703,7 @@ int run_crnn(vtd_ctx* c, int nc) {
     const float* xp = (const float*)c->xproj_op[l].d.out;
     StageTimer st(c, l == 0 ? ST_LSTM0 : ST_LSTM1);
     if (c->use_tclstm && c->use_plstm) {
-      CK(bilstm_layer_tcgen05(c->plstm[l], c->xproj_op[l].d.out, c->rnn_out[l], nc, c->T, c->stream, &c->lc));
+      CK(bilstm_layer_tcgen05(c->plstm[l], c->xproj_op[l].d.out, c->rnn_out[l], nc, c->T, c->stream, &c->lc, c->n_dyn, c->n_first));
     } else if (c->use_tclstm) {
       CK(cudaMemsetAsync(c->h16, 0, (size_t)2 * c->rc * 256 * 2, c->stream));          // h_0 = 0 (parity 0)
       CK(cudaMemsetAsync(c->cbuf, 0, (size_t)2 * c->rc * 256 * 4, c->stream));         // c_0 = 0
@@ -818,21 +829,9 @@ int extract_locked(vtd_ctx* c, int n, int orig_h, int orig_w) {
   return VTD_OK;
 }
 
-int recognize_locked(vtd_ctx* c, int n) {
-  CK(scan_counts(c->counts, n, c->offsets, c->stream, &c->lc));
-  int total;
-#ifdef VTD_DEV
-  if (const char* e = dev_env("VTD_ASSUME_TOTAL")) total = atoi(e);       // experiment: what the host round trip costs
-  else
-#endif
+// crops [first, first + nc) of the current batch -> crop gather, CRNN, CTC into the records
+int recognize_chunk(vtd_ctx* c, int n, int first, int nc) {
   {
-    CK(cudaMemcpyAsync(c->pinned_int, c->offsets + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    total = c->pinned_int[0];
-  }
-  for (int first = 0; first < total; first += c->rc) {
-    const int nc = total - first < c->rc ? total - first : c->rc;
-    {
     StageTimer st(c, ST_CROP);
     if (c->bf16_mode)
       CK(crop_resize_records<bf16>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
@@ -842,16 +841,58 @@ int recognize_locked(vtd_ctx* c, int n) {
       CK(crop_resize_records<float>(c->frame_ptrs_dev, c->cur_h, c->cur_w, c->cur_pitch, c->records, c->offsets, n,
                                     c->cfg.max_boxes, first, nc, c->cfg.crop_w, c->cur_pix == VTD_PIX_NV12, (float*)c->crops, c->crops_lay,
                                     c->stream, &c->lc));
-    }
-    int r = run_crnn(c, nc); if (r) return r;
-    StageTimer st(c, ST_CTC);
-    CK(ctc_into_records(c->logits, nc, first, c->T, 97, c->logits_ld, c->cfg.canonical_ctc, c->offsets, n, c->cfg.max_boxes,
-                        c->records, c->stream, &c->lc));
+  }
+  int r = run_crnn(c, nc); if (r) return r;
+  StageTimer st(c, ST_CTC);
+  CK(ctc_into_records(c->logits, nc, first, c->T, 97, c->logits_ld, c->cfg.canonical_ctc, c->offsets, n, c->cfg.max_boxes,
+                      c->records, c->stream, &c->lc));
+  return VTD_OK;
+}
+
+// The batch's crop total is looked at here, at a point where the host waits for the stream anyway: whatever lies beyond the
+// first chunk (more than `rc` crops in the batch) is recognised now.  Every entry point that reads results or reuses the
+// batch's frames calls this first.
+int finish_pending(vtd_ctx* c) {
+  if (!c->rec_pending) return VTD_OK;
+  c->rec_pending = false;
+  CK(cudaEventSynchronize(c->total_event));
+  const int total = c->pinned_int[0], n = c->pending_n;
+  for (int first = c->rc; first < total; first += c->rc) {
+    const int nc = total - first < c->rc ? total - first : c->rc;
+    int r = recognize_chunk(c, n, first, nc); if (r) return r;
+  }
+  return VTD_OK;
+}
+
+int recognize_locked(vtd_ctx* c, int n) {
+  CK(scan_counts(c->counts, n, c->offsets, c->stream, &c->lc));
+  CK(cudaMemcpyAsync(c->pinned_int, c->offsets + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (c->rec_dyn_ok) {
+    // first chunk against the device-side total: launches sized for what the batch can hold at most, the kernels process
+    // what it does hold; no synchronisation here
+    if (!c->total_event) CK(cudaEventCreateWithFlags(&c->total_event, cudaEventDisableTiming));
+    CK(cudaEventRecord(c->total_event, c->stream));
+    const long long most = (long long)n * c->cfg.max_boxes;
+    const int nc = most < c->rc ? (int)most : c->rc;
+    c->n_dyn = c->offsets + n; c->n_first = 0;
+    const int r = recognize_chunk(c, n, 0, nc);
+    c->n_dyn = nullptr;
+    if (r) return r;
+    c->rec_pending = most > c->rc;                      // only then can there be a second chunk
+    c->pending_n = n;
+    return VTD_OK;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  const int total = c->pinned_int[0];
+  for (int first = 0; first < total; first += c->rc) {
+    const int nc = total - first < c->rc ? total - first : c->rc;
+    int r = recognize_chunk(c, n, first, nc); if (r) return r;
   }
   return VTD_OK;
 }
 
 int read_records_locked(vtd_ctx* c, int n, vtd_record* rh, int* ch) {
+  { int fr = finish_pending(c); if (fr) return fr; }
   // the overflow flag rides along with the read-back (same synchronisation): vtd_overflow_flag() then costs nothing
   CK(cudaMemcpyAsync(c->pinned_int + 1, c->box_work + c->box_lay.overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   if (ch) CK(cudaMemcpyAsync(ch, c->counts, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1037,6 +1078,7 @@ void vtd_destroy(vtd_ctx* c) {
   if (c->frame_ptrs_pinned) cudaFreeHost(c->frame_ptrs_pinned);
   if (c->pinned_int) cudaFreeHost(c->pinned_int);
   if (c->ptrs_event) cudaEventDestroy(c->ptrs_event);
+  if (c->total_event) cudaEventDestroy(c->total_event);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -1049,7 +1091,13 @@ int vtd_set_stream(vtd_ctx* c, void* s) {
   return VTD_OK;
 }
 void* vtd_stream(vtd_ctx* c) { return c ? (void*)c->stream : nullptr; }
-int vtd_sync(vtd_ctx* c) { if (!c) return VTD_ERR_ARG; Guard g(c); CK(cudaStreamSynchronize(c->stream)); return VTD_OK; }
+int vtd_sync(vtd_ctx* c) {
+  if (!c) return VTD_ERR_ARG;
+  Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
+  CK(cudaStreamSynchronize(c->stream));
+  return VTD_OK;
+}
 int64_t vtd_launch_count(vtd_ctx* c) { return c ? c->lc.n : 0; }
 int vtd_time_T(vtd_ctx* c) { return c ? c->T : 0; }
 int vtd_overflow_flag(vtd_ctx* c) {
@@ -1115,12 +1163,14 @@ int vtd_load_recognizer(vtd_ctx* c, const vtd_tensor* t, int n) {
 int vtd_preprocess(vtd_ctx* c, const uint8_t* const* frames, int n, int h, int w, int pitch, int pixfmt, int on_dev) {
   if (!c || !frames) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   return preprocess_locked(c, frames, n, h, w, pitch, pixfmt, on_dev);
 }
 
 int vtd_detect_maps(vtd_ctx* c, int n, float thr, const float* logit_bias) {
   if (!c) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   if (!c->det_loaded) FAIL(VTD_ERR_STATE, "vtd_load_detector has not been called");
   if (n <= 0 || n > c->cfg.max_batch) FAIL(VTD_ERR_CAPACITY, "n=%d outside 1..max_batch=%d", n, c->cfg.max_batch);
   return detect_maps_locked(c, n, thr, logit_bias);
@@ -1147,6 +1197,7 @@ int vtd_read_maps(vtd_ctx* c, int n, float* ph, float* th, uint8_t* mh) {
 int vtd_dbnet_forward(vtd_ctx* c, const float* x, int n, float* ph, float* th) {
   if (!c || !x) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   if (!c->det_loaded) FAIL(VTD_ERR_STATE, "vtd_load_detector has not been called");
   if (n <= 0) FAIL(VTD_ERR_ARG, "n must be positive");
   const int B = c->cfg.max_batch, dh = c->cfg.det_h, dw = c->cfg.det_w;
@@ -1174,6 +1225,7 @@ int vtd_dbnet_forward(vtd_ctx* c, const float* x, int n, float* ph, float* th) {
 int vtd_extract_boxes(vtd_ctx* c, int n, int orig_h, int orig_w) {
   if (!c) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   if (n <= 0 || n > c->cfg.max_batch) FAIL(VTD_ERR_CAPACITY, "n=%d outside 1..max_batch", n);
   if (orig_h <= 0 || orig_w <= 0) FAIL(VTD_ERR_ARG, "orig size must be positive");
   return extract_locked(c, n, orig_h, orig_w);
@@ -1183,6 +1235,7 @@ int vtd_postprocess_map(vtd_ctx* c, const float* prob_host, int mh, int mw, int 
                         int orig_h, float thr, vtd_record* out, int cap, int* n_out) {
   if (!c || !prob_host || !n_out) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   if (mh <= 0 || mw <= 0 || clip_h <= 0 || clip_w <= 0 || orig_w <= 0 || orig_h <= 0) FAIL(VTD_ERR_ARG, "sizes must be positive");
   if ((long long)mh * mw > (1LL << 28)) FAIL(VTD_ERR_CAPACITY, "map too large");
   const int kmax = c->cfg.max_boxes;
@@ -1220,6 +1273,7 @@ int vtd_postprocess_map(vtd_ctx* c, const float* prob_host, int mh, int mw, int 
 int vtd_recognize_boxes(vtd_ctx* c, int n) {
   if (!c) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   if (!c->rec_loaded) FAIL(VTD_ERR_STATE, "vtd_load_recognizer has not been called");
   if (n <= 0 || n > c->cfg.max_batch || n > c->cur_n) FAIL(VTD_ERR_STATE, "n=%d does not match the preprocessed batch (%d)", n, c->cur_n);
   return recognize_locked(c, n);
@@ -1229,6 +1283,7 @@ int vtd_recognize_crops(vtd_ctx* c, const uint8_t* const* crops, const int* h, c
                         uint8_t* ids_out, int* len_out, float* conf_out, float* logits_out) {
   if (!c || !crops || !h || !w || !pitch) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   if (!c->rec_loaded) FAIL(VTD_ERR_STATE, "vtd_load_recognizer has not been called");
   if (n_crops <= 0) return VTD_OK;
   const int T = c->T;
@@ -1280,6 +1335,7 @@ int vtd_recognize_crops(vtd_ctx* c, const uint8_t* const* crops, const int* h, c
 int vtd_crnn_forward(vtd_ctx* c, const float* x, int n, float* logits_host) {
   if (!c || !x || !logits_host) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   if (!c->rec_loaded) FAIL(VTD_ERR_STATE, "vtd_load_recognizer has not been called");
   const int cw = c->cfg.crop_w, T = c->T;
   const size_t per = (size_t)3 * 32 * cw;
@@ -1446,6 +1502,7 @@ int vtd_run_batch(vtd_ctx* c, const uint8_t* const* frames, int n, int h, int w,
                   float thr, const float* logit_bias, int recognize, vtd_record* rh, int* ch) {
   if (!c || !frames) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   NvtxRange range("vtd_run_batch");
   if (!c->det_loaded) FAIL(VTD_ERR_STATE, "vtd_load_detector has not been called");
   if (recognize && !c->rec_loaded) FAIL(VTD_ERR_STATE, "vtd_load_recognizer has not been called");
@@ -1465,6 +1522,7 @@ int vtd_draw_detections(vtd_ctx* c, uint8_t* const* frames, int n, int h, int w,
   static_assert((int)VTD_OVERLAY_LABEL_MAX == OV_LABEL_MAX, "overlay label capacity");
   if (!c || !frames || (n_items > 0 && !items)) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   constexpr int PER_FRAME = 256;               // the kernel's list of later, overlapping detections (overlay.cu)
   if (n <= 0 || n > c->cfg.max_batch) FAIL(VTD_ERR_CAPACITY, "n=%d outside 1..max_batch=%d", n, c->cfg.max_batch);
   if (h <= 0 || w <= 0 || pitch < w * 3) FAIL(VTD_ERR_ARG, "frame %dx%d with pitch %d", h, w, pitch);
@@ -1598,6 +1656,7 @@ int vtd_op_info(vtd_ctx* c, int which, int idx, int64_t* info, double* ms) {
 int vtd_debug_tensor(vtd_ctx* c, const char* name, int n, float* host_out, int64_t capacity, int64_t* shape4) {
   if (!c || !name) return VTD_ERR_ARG;
   Guard g(c);
+  { int fr = finish_pending(c); if (fr) return fr; }
   auto it = c->dbg.find(name);
   if (it == c->dbg.end()) FAIL(VTD_ERR_ARG, "unknown debug tensor '%s'", name);
   const DebugEntry& d = it->second;

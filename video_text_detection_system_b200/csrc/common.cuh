@@ -116,7 +116,7 @@ struct LstmPlan;
 LstmPlan* lstm_plan_create(const void* whh /*[2*1024][256] bf16, rows (dir, unit tile, gate, unit)*/, std::string* err);
 void lstm_plan_destroy(LstmPlan*);
 cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*[B][T][2][1024] bf16*/, void* seq_out, int B, int T, cudaStream_t s,
-                                 LaunchCounter* lc);
+                                 LaunchCounter* lc, const int* n_dyn = nullptr, int n_first = 0);
 // DBNet stem (7x7 s2 + BN + ReLU) fused with the 3x3 s2 max-pool: the full-resolution stem map never reaches HBM
 struct StemPoolPlan;
 StemPoolPlan* stem_pool_plan_create(const void* in_padded, int N, int dh, int dw, const void* window_weights, const float* bias,
@@ -124,8 +124,11 @@ StemPoolPlan* stem_pool_plan_create(const void* in_padded, int N, int dh, int dw
 StemPoolPlan* stem_pool_plan_create_crnn(const void* crops_padded, int N, int crop_w, const void* window_weights, const float* bias,
                                          void* pooled_out, std::string* err);
 void stem_pool_plan_destroy(StemPoolPlan*);
-cudaError_t stem_pool_tcgen05(const StemPoolPlan* pl, int n, cudaStream_t s, LaunchCounter* lc);
-cudaError_t conv_tcgen05(const TcPlan* p, int n_actual, cudaStream_t s, LaunchCounter* lc);
+// n_dyn (optional, both): the launch is sized for n images but processes clamp(*n_dyn - n_first, 0, n) of them -- the crop count
+// of a batch lives on the device, so the recogniser is launched without a host round trip
+cudaError_t stem_pool_tcgen05(const StemPoolPlan* pl, int n, cudaStream_t s, LaunchCounter* lc, const int* n_dyn = nullptr,
+                              int n_first = 0);
+cudaError_t conv_tcgen05(const TcPlan* p, int n_actual, cudaStream_t s, LaunchCounter* lc, const int* n_dyn = nullptr, int n_first = 0);
 bool tc_supported(const ConvDesc& d);
 
 // ---- pooling -------------------------------------------------------------------------------------

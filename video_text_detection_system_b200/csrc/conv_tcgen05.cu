@@ -87,6 +87,9 @@ struct TcParams {
   int lw, lh;                 // log2(BW), log2(BH); BN = 128 >> (lw+lh)
   int tiles_x, tiles_y, tiles_n, n_blocks;
   int total_tiles;
+  // images of this launch known only on the device (the recogniser's crop count): N = clamp(*n_dyn - n_first, 0, N), the tile
+  // count follows; the grid was sized for N.  nullptr = the host values above.
+  const int* n_dyn; int n_first;
   int relu, res_mode, out_f32;
   const float* bias;
   const bf16* res;
@@ -124,6 +127,19 @@ struct HeadConsts {            // DB head tail constants, passed in the kernel p
   float pad_;
 };
 struct NoExtra { int unused; };
+
+struct DynCount { int N, tiles_n, total_tiles; };
+__device__ __forceinline__ DynCount dyn_count(const TcParams& p) {
+  DynCount d{p.N, p.tiles_n, p.total_tiles};
+  if (p.n_dyn) {
+    int c = *p.n_dyn - p.n_first;
+    c = c < 0 ? 0 : (c > p.N ? p.N : c);
+    const int bnn = 128 >> (p.lw + p.lh);
+    d.N = c; d.tiles_n = (c + bnn - 1) / bnn;
+    d.total_tiles = p.tiles_x * p.tiles_y * d.tiles_n * p.n_blocks;
+  }
+  return d;
+}
 
 // -DVTD_TIMERS (dev builds only): per-role wait/total cycle counters, printed per launch by launch_tc()
 #ifdef VTD_TIMERS
@@ -589,7 +605,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
   constexpr int acc_n = Cfg::ACC;
   const int kchunks = p.Cin / BLOCK_K;
   const int ksteps = MODE == MODE_WIN ? p.nr : ((MODE == MODE_CONV && p.halo) ? kchunks : p.KH * p.KW * kchunks);   // ring slots x kps per tile
-  const int total_tiles = p.total_tiles;
+  const DynCount dyn = dyn_count(p);
+  const int total_tiles = dyn.total_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
@@ -851,7 +868,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int ox = tx * BW + xx, oy = ty * BH + yy, n = t * BNt + nn;
-        if (ox < p.Wo && oy < p.Ho && n < p.N) {
+        if (ox < p.Wo && oy < p.Ho && n < dyn.N) {
           const size_t rpix = p.res_mode == RES_SAME ? ((size_t)n * p.Ho + oy) * p.Wo + ox
                                                      : ((size_t)n * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
           const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.Cout + nb * BLOCK_N + g_ * gcols);
@@ -905,7 +922,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p,
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
       const int ox = tx * BW + xx, oy = ty * BH + yy, n = t * BNt + nn;
-      const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
+      const bool valid = ox < p.Wo && oy < p.Ho && n < dyn.N;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(as * BLOCK_N);
       const uint32_t tfull_bar = tfull0 + 8 * as, parity = aphase;
       if constexpr (MODE == MODE_DBHEAD) {
@@ -1022,7 +1039,8 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 
   const int kchunks = p.Cin / BLOCK_K;
   const int tgroups = 9 / taps;
-  const int total_tiles = p.total_tiles;
+  const DynCount dyn = dyn_count(p);
+  const int total_tiles = dyn.total_tiles;
   const int npairs = (total_tiles + 1) >> 1;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   auto my_tile = [&](int pair) { const int t = 2 * pair + (int)rank; return t < total_tiles ? t : total_tiles - 1; };   // odd tail: the peer repeats the last tile
@@ -1120,7 +1138,7 @@ conv_tc2_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
       const int ox = tx * 8 + xx, oy = ty * 16 + yy, n = t;
-      const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
+      const bool valid = ox < p.Wo && oy < p.Ho && n < dyn.N;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BLOCK_N);
       mbar_wait(tfull0 + 8 * acc, accph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1213,7 +1231,8 @@ conv_tc2g_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
   const int BNt = BLOCK_M >> (p.lw + p.lh);
   const int kchunks = p.Cin / BLOCK_K;
   const int ksteps = p.KH * p.KW * kchunks;
-  const int spatial = p.tiles_x * p.tiles_y * p.tiles_n;
+  const DynCount dyn = dyn_count(p);
+  const int spatial = p.tiles_x * p.tiles_y * dyn.tiles_n;
   const int spairs = (spatial + 1) >> 1;
   const int npairs = spairs * p.n_blocks;
   const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
@@ -1300,7 +1319,7 @@ conv_tc2g_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
       int nb, tx, ty, tn;
       decode(pair, nb, tx, ty, tn);
       const int ox = tx * BW + xx, oy = ty * BH + yy, n = tn * BNt + nn;
-      const bool valid = ox < p.Wo && oy < p.Ho && n < p.N;
+      const bool valid = ox < p.Wo && oy < p.Ho && n < dyn.N;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BLOCK_N);
       mbar_wait(tfull0 + 8 * acc, accph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1706,6 +1725,7 @@ struct StemPoolParams {
   bf16* out;                  // pooled map [N][Hp][Wp][64]
   int N, Ho, Wo, Hp, Wp;      // stem map Ho x Wo, pooled map Hp x Wp
   int tiles_x, bands, rows_per_band, total_items, stages;
+  const int* n_dyn; int n_first;   // CRNN first layer: crop count on the device (see TcParams::n_dyn)
 };
 
 template <bool CRNN>
@@ -1741,6 +1761,12 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  int total_items = p.total_items;
+  if (p.n_dyn) {
+    int c = *p.n_dyn - p.n_first;
+    c = c < 0 ? 0 : (c > p.N ? p.N : c);
+    total_items = c * p.tiles_x * p.bands;
+  }
 
   // item -> image, column tile, band; the stem rows it computes: first = max(2 ya - 1, 0) .. last = 2 yb - 1
   auto decode = [&](int item, int& n, int& t, int& ya, int& yb) {
@@ -1751,13 +1777,13 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
 
   if (warp == 0) {
     // ===================== producer =====================
-    if ((int)blockIdx.x < p.total_items && elect_one()) {
+    if ((int)blockIdx.x < total_items && elect_one()) {
       mbar_expect_tx(wfull, (uint32_t)NR * B_ROW_BYTES);
       for (int j = 0; j < NR; ++j) tma_load_2d(w0 + j * B_ROW_BYTES, &wmap, wfull, j * 32, 0);
     }
     __syncwarp();
     int stage = 0; uint32_t phase = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int n, t, ya, yb; decode(item, n, t, ya, yb);
       const int x0 = CRNN ? 128 * t : SP_POOLED * 2 * t - 1;                      // first conv column of the tile
       const uint8_t* base = p.in + (size_t)n * p.in_ip + (CRNN ? (size_t)x0 * 16 : (size_t)(2 * x0 + 2) * 8);  // its first window byte in a padded row
@@ -1780,8 +1806,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
     // ===================== MMA issuer =====================
     const uint32_t idesc = umma_idesc(64);
     int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
-    if ((int)blockIdx.x < p.total_items) mbar_wait(wfull, 0);
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    if ((int)blockIdx.x < total_items) mbar_wait(wfull, 0);
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int n, t, ya, yb; decode(item, n, t, ya, yb);
       for (int r = CRNN ? 2 * ya : max(2 * ya - 1, 0); r <= 2 * yb - 1; ++r) {
         mbar_wait(tempty0 + 8 * as, aphase ^ 1);
@@ -1820,7 +1846,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) stem_pool_kernel(const __grid_c
     float bias[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias[j] = __ldg(p.bias + half * 32 + j);
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       int n, t, ya, yb; decode(item, n, t, ya, yb);
       const int x0 = CRNN ? 128 * t : SP_POOLED * 2 * t - 1;
       const int col = x0 + m;
@@ -2384,11 +2410,12 @@ StemPoolPlan* stem_pool_plan_create_crnn(const void* in, int N, int cw, const vo
 
 void stem_pool_plan_destroy(StemPoolPlan* p) { delete p; }
 
-cudaError_t stem_pool_tcgen05(const StemPoolPlan* pl, int n, cudaStream_t s, LaunchCounter* lc) {
+cudaError_t stem_pool_tcgen05(const StemPoolPlan* pl, int n, cudaStream_t s, LaunchCounter* lc, const int* n_dyn, int n_first) {
   if (n <= 0) return cudaSuccess;
   StemPoolParams p = pl->p;
   p.N = n < pl->p.N ? n : pl->p.N;
   p.total_items = p.N * p.tiles_x * p.bands;
+  p.n_dyn = n_dyn; p.n_first = n_first;
   static PerDeviceFlag attr_done[2];
   cudaError_t e = pl->crnn ? once_per_device(attr_done[1], [] {
     return cudaFuncSetAttribute(stem_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -2577,9 +2604,10 @@ static cudaError_t launch_tc(const TcPlan* pl, const TcParams& p, const typename
 }
 
 // n_actual: images (MODE_LSTM: sequences) actually present in this call (<= what the plan was built for)
-cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchCounter* lc) {
+cudaError_t conv_tcgen05(const TcPlan* pl, int n_actual, cudaStream_t s, LaunchCounter* lc, const int* n_dyn, int n_first) {
   if (n_actual <= 0) return cudaSuccess;
   TcParams p = pl->p;
+  p.n_dyn = n_dyn; p.n_first = n_first;
   const int bnn = 128 >> (p.lw + p.lh);
   p.N = n_actual < pl->p.N ? n_actual : pl->p.N;
   p.tiles_n = (p.N + bnn - 1) / bnn;

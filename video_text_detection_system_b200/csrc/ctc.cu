@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(1024) ctc_records_kernel(const float* __restri
   __shared__ float s_pm[MAXT];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int b = blockIdx.x;
+  if (first_crop + b >= offsets[n]) return;             // the launch may be sized for more crops than the batch holds
   for (int t = wid; t < T; t += nw) {
     int bi; float pm;
     row_argmax(x + ((size_t)b * T + t) * ld, V, 0, lane, &bi, &pm);

@@ -56,6 +56,7 @@ struct LstmParams {
   bf16* seq_out;          // [B][T][512]
   int B, T;
   int rows;               // sequences per cluster: 128, or 64 when that still fits one wave (halves the h exchange per step)
+  const int* n_dyn; int n_first;   // optional: the number of sequences lives on the device (clamp(*n_dyn - n_first, 0, B))
 };
 
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -118,6 +119,12 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
   const int jt = blockIdx.x;                            // == rank in cluster: hidden units 64*jt ..
   const int dir = blockIdx.y;
   const int b0 = blockIdx.z * p.rows;
+  int B = p.B;
+  if (p.n_dyn) {
+    const int c = *p.n_dyn - p.n_first;
+    B = c < 0 ? 0 : (c > p.B ? p.B : c);
+  }
+  if (b0 >= B) return;                                  // the whole cluster (same blockIdx.z) leaves before any barrier exists
 
   if (warp == 0 && lane == 0) {
     mbar_init(wfull, 1);
@@ -191,7 +198,7 @@ bilstm_persistent_kernel(const __grid_constant__ CUtensorMap map_whh, const Lstm
     const int q = warp & 3, half = (warp - 2) >> 2;   // half = which L_UPT-unit part of the 64 units
     const int m = q * 32 + lane;                        // sequence row inside the tile
     const int b = b0 + m;
-    const bool valid = b < p.B;
+    const bool valid = b < B;
     const bool active = q * 32 < p.rows;                // with 64 rows per cluster the upper two lane quarters carry no sequence
     const uint32_t epi_threads = (uint32_t)(p.rows * L_PARTS);
     const bool issuer = q == 0 && half == 0 && lane == 0;   // one thread of an always-active warp pushes the slice to the peers
@@ -363,7 +370,7 @@ LstmPlan* lstm_plan_create(const void* whh /*[2*1024][256] bf16, rows (dir, unit
 void lstm_plan_destroy(LstmPlan* p) { delete p; }
 
 cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*bf16*/, void* seq_out, int B, int T, cudaStream_t s,
-                                 LaunchCounter* lc) {
+                                 LaunchCounter* lc, const int* n_dyn, int n_first) {
   if (B <= 0 || T <= 0) return cudaSuccess;
   static PerDeviceFlag attr_done;
   {
@@ -375,6 +382,7 @@ cudaError_t bilstm_layer_tcgen05(const LstmPlan* pl, const void* xproj /*bf16*/,
   LstmParams p;
   p.xproj = reinterpret_cast<const bf16*>(xproj); p.seq_out = reinterpret_cast<bf16*>(seq_out); p.B = B; p.T = T;
   p.timers = nullptr;
+  p.n_dyn = n_dyn; p.n_first = n_first;
   // 64 sequences per cluster when all clusters are still resident at once: the MMA costs the same (M = 128 either way),
   // the per-step h exchange (DSMEM, ~9 B/cycle/SM measured) and the gate math per CTA halve
   p.rows = (((B + 63) / 64) * 8 <= tc::sm_count() && !dev_env("VTD_LSTM_ROWS128")) ? 64 : 128;
