@@ -194,7 +194,10 @@ int  vtd_run_batch(vtd_ctx* ctx, const uint8_t* const* frames, int n, int h, int
 int  vtd_read_records(vtd_ctx* ctx, int n, vtd_record* records_host, int* counts_host);
 /* Device pointers of the results: records [max_batch*max_boxes], counts [max_batch].  The counts directly follow the
  * records (counts_dev == (int*)(records_dev + max_batch*max_boxes)), so a rank's results are one contiguous block of
- * max_batch*(max_boxes*128 + 4) bytes: one collective gathers them (parallel.gather_packed). */
+ * max_batch*(max_boxes*128 + 4) bytes: one collective gathers them (parallel.gather_packed).
+ * A batch with more than 1024 crops is recognised completely only once the host has looked at its crop count, which every
+ * entry point that synchronises does (vtd_sync, vtd_read_records, the next vtd_run_batch): consume the device block after one
+ * of them, or stream-ordered after vtd_run_batch when max_batch*max_boxes <= 1024. */
 int  vtd_get_records(vtd_ctx* ctx, vtd_record** records_dev, int** counts_dev);
 
 /* ---- result sink, annotated frames: ProcessingService._draw_detections drop-in (app/services/processing_service.py:188-218).
