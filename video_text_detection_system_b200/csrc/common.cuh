@@ -223,7 +223,10 @@ cudaError_t layernorm_rows(const bf16* x, const float* gamma, const float* beta,
 cudaError_t attention_enc(const bf16* qkv /*[n][S][3D]*/, bf16* out /*[n][S][D]*/, int n, int S, int heads, float scale,
                           cudaStream_t s, LaunchCounter* lc);
 cudaError_t attention_decode(const bf16* q, int ldq, const bf16* k, const bf16* v, int ldkv, int Lcap, int L, int n, int heads,
-                             float scale, bf16* out /*[n][heads*64]*/, cudaStream_t s, LaunchCounter* lc, const int* tdev = nullptr);
+                             float scale, bf16* out /*[n][heads*64]*/, cudaStream_t s, LaunchCounter* lc, const int* tdev = nullptr,
+                             int head_major = 0);
+cudaError_t kv_to_head_major(const bf16* in /*[n][T][2][heads][64]*/, bf16* out /*[n][2][heads][T][64]*/, int n, int T, int heads,
+                             cudaStream_t s, LaunchCounter* lc);
 // tdev (optional, every decode-loop kernel below): the decode position lives in device memory, so that one captured CUDA
 // graph of a decode step can be replayed for every position; argmax_rows advances it
 cudaError_t vit_assemble(const bf16* patches, const bf16* cls, const bf16* pos, bf16* h, int n, int P, int D, cudaStream_t s,
