@@ -595,7 +595,7 @@ cudaError_t skinny_gemm(const bf16* X, int ldx, const bf16* W, const float* bias
   if (M <= 0) return cudaSuccess;
   if (!skinny_gemm_supported(M, N, K)) return cudaErrorInvalidValue;
   int WN = 1;
-  while (WN < 8 && (N + 8 * WN - 1) / (8 * WN) > 320) WN *= 2;     // enough CTAs for every SM, K slices of at least 256 / WN
+  while (WN < 2 && (N + 8 * WN - 1) / (8 * WN) > 320) WN *= 2;     // 8 or 16 columns per CTA: wider CTAs re-read the activations per warp and thrash L1
   while (WN < 8 && K % (32 * (8 / WN)) != 0) WN *= 2;              // a K slice is whole 32-wide blocks
   while (WN > 1 && (size_t)8 * WN * (2 * K + 64) > 160 * 1024) WN /= 2;
   const size_t smem = (size_t)8 * WN * (2 * K + 64);
