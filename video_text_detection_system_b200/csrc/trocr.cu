@@ -334,7 +334,8 @@ constexpr int AD_MAXL = 640;
 // Eight lanes share a key / value row: each reads 16 bytes (8 of the 64 head dimensions), so a warp instruction covers four
 // whole 128-byte rows, 16 rows per CTA pass, all loads of a pass independent (the rows of one head are 2*D*2 bytes apart in the
 // [token][K | V] buffers; one thread per row with eight dependent 16-byte loads ran at 2 TB/s).
-__global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k,
+constexpr int AD_THREADS = 256, AD_GROUPS = AD_THREADS / 8, AD_WARPS = AD_THREADS / 32;
+__global__ void __launch_bounds__(AD_THREADS) attention_decode_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k,
                                                                const bf16* __restrict__ v, int ldkv, long long crop_stride,
                                                                int head_stride, int L, float scale,
                                                                bf16* __restrict__ out, int D, const int* __restrict__ tdev) {
@@ -342,10 +343,10 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __res
   pdl_go();
   pdl_wait();
   if (tdev) L = *tdev + 1;                               // decode position on the device (graph replay): keys 0..t
-  __shared__ float red[4];
-  __shared__ float part[16][64];
+  __shared__ float red[AD_WARPS];
+  __shared__ float part[AD_GROUPS][64];
   const int hd = blockIdx.x, n = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int sub = t & 7, grp = t >> 3;                  // 8 dimensions sub*8.., row group 0..15
+  const int sub = t & 7, grp = t >> 3;                  // 8 dimensions sub*8.., row group 0..AD_GROUPS-1
   float qv[8];
   {
     const uint4 u = *reinterpret_cast<const uint4*>(q + (size_t)n * ldq + hd * 64 + sub * 8);
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __res
   const bf16* vb = v + (size_t)n * crop_stride + (size_t)hd * head_stride + sub * 8;
   float mx = -INFINITY;
 #pragma unroll 8
-  for (int j0 = 0; j0 < L; j0 += 16) {                  // uniform trip count: the shuffles below need the whole warp
+  for (int j0 = 0; j0 < L; j0 += AD_GROUPS) {                  // uniform trip count: the shuffles below need the whole warp
     const int j = j0 + grp;
     float acc = 0.f;
     if (j < L) {
@@ -378,19 +379,23 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __res
   for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
   if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < AD_WARPS; ++w) mx = fmaxf(mx, red[w]);
   __syncthreads();
   float sum = 0.f;
-  for (int j = t; j < L; j += 128) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
+  for (int j = t; j < L; j += AD_THREADS) { const float e = expf(sc[j] - mx); sc[j] = e; sum += e; }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
   if (lane == 0) red[warp] = sum;
   __syncthreads();
-  sum = red[0] + red[1] + red[2] + red[3];
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < AD_WARPS; ++w) sum += red[w];
   // out[d] = sum_j p[j] v[j][d]: row group grp walks every sixteenth key, 8 dimensions per lane
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
-  for (int j = grp; j < L; j += 16) {
+  for (int j = grp; j < L; j += AD_GROUPS) {
     const uint4 u = *reinterpret_cast<const uint4*>(vb + (size_t)j * ldkv);
     const bf16x2* h = reinterpret_cast<const bf16x2*>(&u);
     const float pj = sc[j];
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __res
   if (t < 64) {
     float o = 0.f;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) o += part[r][t];
+    for (int r = 0; r < AD_GROUPS; ++r) o += part[r][t];
     out[(size_t)n * D + hd * 64 + t] = f32_to_16(o / sum);
   }
 }
@@ -631,7 +636,7 @@ cudaError_t attention_decode(const bf16* q, int ldq, const bf16* k, const bf16* 
   // token-major: [n][Lcap][ldkv], head hd at column hd*64; head-major (kv_to_head_major): [n][2][heads][Lcap][64], rows of a head contiguous
   const long long crop_stride = head_major ? (long long)2 * heads * Lcap * 64 : (long long)Lcap * ldkv;
   const int head_stride = head_major ? Lcap * 64 : 64;
-  cudaError_t e = launch_pdl(attention_decode_kernel, dim3(heads, n), dim3(128), 0, s, q, ldq, k, v, head_major ? 64 : ldkv, crop_stride,
+  cudaError_t e = launch_pdl(attention_decode_kernel, dim3(heads, n), dim3(AD_THREADS), 0, s, q, ldq, k, v, head_major ? 64 : ldkv, crop_stride,
                              head_stride, L, scale, out, heads * 64, tdev);
   if (lc) lc->n++;
   return e;
