@@ -171,23 +171,36 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(const bf16* __restrict
     xrow[i][0] = X + (size_t)(r0 < M ? r0 : M - 1) * ldx + k0 + t * 8;
     xrow[i][1] = X + (size_t)(r1 < M ? r1 : M - 1) * ldx + k0 + t * 8;
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
-#pragma unroll 2
-  for (int kb = 0; kb < ks; kb += 32) {
-    const uint4 wv = *reinterpret_cast<const uint4*>(wrow + (size_t)kb * 2);
-    uint4 xa[MT], xb[MT];
+  // two 32-wide K blocks of activations are always in flight, and the first two are requested BEFORE the weights are waited
+  // for: the kernel's time is its chain of memory round trips, not its bytes
+  uint4 xa[2][MT], xb[2][MT];
+  auto load_x = [&](int st, int kb) {
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-      xa[i] = *reinterpret_cast<const uint4*>(xrow[i][0] + kb);
-      xb[i] = *reinterpret_cast<const uint4*>(xrow[i][1] + kb);
+      xa[st][i] = *reinterpret_cast<const uint4*>(xrow[i][0] + kb);
+      xb[st][i] = *reinterpret_cast<const uint4*>(xrow[i][1] + kb);
     }
+  };
+  auto mma_block = [&](int st, int kb) {
+    const uint4 wv = *reinterpret_cast<const uint4*>(wrow + (size_t)kb * 2);
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-      const uint32_t a1[4] = {xa[i].x, xb[i].x, xa[i].y, xb[i].y};
-      const uint32_t a2[4] = {xa[i].z, xb[i].z, xa[i].w, xb[i].w};
+      const uint32_t a1[4] = {xa[st][i].x, xb[st][i].x, xa[st][i].y, xb[st][i].y};
+      const uint32_t a2[4] = {xa[st][i].z, xb[st][i].z, xa[st][i].w, xb[st][i].w};
       mma16816(acc[i], a1, wv.x, wv.y);
       mma16816(acc[i], a2, wv.z, wv.w);
+    }
+  };
+  load_x(0, 0);
+  if (ks > 32) load_x(1, 32);
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  for (int kb = 0; kb < ks; kb += 64) {
+    mma_block(0, kb);
+    if (kb + 64 < ks) load_x(0, kb + 64);
+    if (kb + 32 < ks) {
+      mma_block(1, kb + 32);
+      if (kb + 96 < ks) load_x(1, kb + 96);
     }
   }
   // C fragment: (row g, cols 2t, 2t+1), (row g + 8, cols 2t, 2t+1)
